@@ -1,0 +1,119 @@
+// Shared device helpers: the categorical draw (stage 2) and small utilities.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <math_constants.h>
+
+#include "philox.cuh"
+
+#define DPMM_MAX_K 1024
+
+// ---------------------------------------------------------------------------------------------
+// Stage 2 -- sample_log_cat_array! (src/utils.jl:19-31) for ONE row, in place on `rs`
+// (element k at rs[k*stride], Float32 log-probabilities incl. log-weight).  Returns the 0-based
+// index.  Order of operations mirrors the reference line by line:
+//   :21 NaN -> -Inf        :22 row max        :23 subtract     :24 exp
+//   :26 row sum (left to right, Float32)      :27 divide
+//   :29 StatsBase.sample(ProbabilityWeights(row)):  t = rand() * sum(w)  (Float64 * Float32),
+//       i = 1; cw = w[1]; while cw < t && i < n: i += 1; cw += w[i]      (cw Float32)
+// exp is evaluated in Float64 and rounded once to Float32 -- a correctly rounded stand-in for
+// Julia's <1ulp Float32 exp, and exactly what the CPU oracle does, so that the only source of
+// label disagreement is the summation order of the quadratic form.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int dpmm_draw_inverse_cdf(float* rs, int stride, int K, double u) {
+  float mx = -CUDART_INF_F;
+  for (int k = 0; k < K; ++k) {
+    float v = rs[k * stride];
+    if (v != v) {
+      v = -CUDART_INF_F;
+      rs[k * stride] = v;
+    }
+    mx = fmaxf(mx, v);
+  }
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float e = (float)exp((double)(rs[k * stride] - mx));
+    rs[k * stride] = e;
+    s = __fadd_rn(s, e);
+  }
+  float tot = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float p = __fdiv_rn(rs[k * stride], s);
+    rs[k * stride] = p;
+    tot = __fadd_rn(tot, p);
+  }
+  const double t = u * (double)tot;
+  int i = 0;
+  float cw = rs[0];
+  while ((double)cw < t && i < K - 1) {
+    ++i;
+    cw = __fadd_rn(cw, rs[i * stride]);
+  }
+  return i;
+}
+
+// mapslices(argmax, parr, dims=[2]) (local_clusters_actions.jl:130): first maximal element, NaN
+// counts as maximal (Julia's argmax); no NaN sanitising on this branch.
+__device__ __forceinline__ int dpmm_draw_argmax(const float* rs, int stride, int K) {
+  int best = 0;
+  float bv = rs[0];
+  if (bv != bv) return 0;
+  for (int k = 1; k < K; ++k) {
+    const float v = rs[k * stride];
+    if (v != v) return k;
+    if (v > bv) {
+      bv = v;
+      best = k;
+    }
+  }
+  return best;
+}
+
+// Gumbel-max draw (optional fast mode; same categorical distribution as the inverse-CDF walk, but a
+// different random stream: one Philox block feeds 4 clusters).
+__device__ __forceinline__ int dpmm_draw_gumbel(const float* rs, int stride, int K, uint64_t seed,
+                                               uint32_t call, uint64_t gidx) {
+  int best = 0;
+  float bv = -CUDART_INF_F;
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    const Philox4 r = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), call,
+                                    DPMM_STREAM_GUMBEL + 8u * (uint32_t)(k0 >> 2), (uint32_t)seed,
+                                    (uint32_t)(seed >> 32));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + j;
+      if (k < K) {
+        float v = rs[k * stride];
+        if (v != v) v = -CUDART_INF_F;
+        const float uu = ((float)w[j] + 0.5f) * 2.3283064365386963e-10f;  // (0,1)
+        const float g = -__logf(-__logf(uu));
+        const float t = v + g;
+        if (t > bv || k == 0) {
+          bv = t;
+          best = k;
+        }
+      }
+    }
+  }
+  return best;
+}
+
+// Two-way draw for sub-labels: sample_log_cat_array! with C = 2 (create_subclusters_labels!,
+// local_clusters_actions.jl:83-95).  Returns 0 (left) or 1 (right).
+__device__ __forceinline__ int dpmm_draw_two(float rl, float rr, double u) {
+  float m[2] = {rl, rr};
+  return dpmm_draw_inverse_cdf(m, 1, 2, u);
+}
+
+__device__ __forceinline__ double dpmm_uniform(const double* inj, int64_t local_i, uint64_t seed,
+                                               uint32_t stream, uint32_t call, uint64_t gidx) {
+  if (inj != nullptr) return inj[local_i];
+  return philox_to_uniform(philox_draw(seed, stream, call, gidx));
+}
+
+__device__ __forceinline__ int dpmm_randbit(const uint8_t* inj, int64_t local_i, uint64_t seed,
+                                            uint32_t call, uint64_t gidx) {
+  if (inj != nullptr) return inj[local_i] & 1;
+  return (int)(philox_draw(seed, DPMM_STREAM_RANDBITS, call, gidx).x & 1u);
+}

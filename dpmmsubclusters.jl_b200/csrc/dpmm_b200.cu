@@ -1,0 +1,1171 @@
+// libdpmm_b200.so -- C ABI (include/dpmm_b200.h) over the sm_100a kernels of this directory.
+// One context = one GPU = one shard of points = one "worker" of the reference
+// (src/local_clusters_actions.jl *_worker! functions).  No CPU fallback exists: every entry point
+// needs a CUDA device and reports DPMM_ECUDA otherwise.
+#include "../../include/dpmm_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_gauss.cuh"
+#include "kernels_mnm.cuh"
+#include "kernels_sort.cuh"
+#include "kernels_stats.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+enum TimingKind {
+  TK_LABEL = 0,     // fused log-likelihood + label draw
+  TK_SORT,          // histogram / scan / scatter
+  TK_SUBLABEL,      // sub-label draw + left/right partition
+  TK_STATS,         // segmented sufficient statistics
+  TK_STATS_AUX,     // work list + finalise/pack
+  TK_RELABEL,       // LUT relabel / init
+  TK_ALLREDUCE,     // NCCL all-reduce of the packed statistics
+  TK_COUNT
+};
+static const char* kTimingNames[TK_COUNT] = {"label", "sort", "sublabel", "stats", "stats_aux", "relabel", "allreduce"};
+
+struct TimedEvent {
+  cudaEvent_t a, b;
+  int kind;
+};
+
+struct UidBlob {  // layout of ncclUniqueId (128 opaque bytes, passed by value)
+  char b[128];
+};
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, UidBlob, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+struct dpmm_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  int64_t n = 0;
+  int D = 0;
+  int prior = 0;
+  uint64_t seed = 0;
+  int64_t goff = 0;
+  uint32_t call = 0;
+  int sampler = 0;
+  std::string err;
+
+  float* x = nullptr;
+  int32_t* labels = nullptr;
+  uint8_t* sub = nullptr;
+  int32_t* perm = nullptr;
+  int32_t* perm2 = nullptr;
+  double* u_label = nullptr;
+  double* u_sub = nullptr;
+  uint8_t* r_bits = nullptr;
+
+  // K-sized state
+  int K = 0, Kcap = 0;    // K = number of clusters of the last set_params
+  int label_bound = 1;    // every label value is < label_bound (0-based)
+  bool params_set = false;
+  int rec_f = 0;          // floats per distribution record (NIW) / D (multinomial)
+  float* recs = nullptr;  // [3K][rec_f]
+  float* cst = nullptr;   // [3K]
+  float* logw = nullptr;  // [K]
+  float* loglr = nullptr; // [2K]
+  float* logp_t = nullptr;  // multinomial [D][KP]
+  int KP = 0;
+  int32_t* hist = nullptr;
+  int32_t* seg_off = nullptr;
+  int32_t* scat_cursor = nullptr;
+  int32_t* lr_cursor = nullptr;
+  int32_t* lut_l = nullptr;
+  int32_t* lut_r = nullptr;
+  uint8_t* rule = nullptr;
+  uint8_t* wanted = nullptr;
+  int32_t* idx_list = nullptr;
+  int stats_rec = 0;
+  double* acc = nullptr;
+  double* outbuf = nullptr;
+  StatsItem* items = nullptr;
+  int64_t items_cap = 0;
+  int32_t* item_ctr = nullptr;  // [0]=n_items [1]=next_item
+  int chunk = 1024;
+
+  // pinned staging
+  void* hstage = nullptr;
+  size_t hstage_bytes = 0;
+
+  bool hist_valid = false, sorted = false, partitioned = false;
+  int64_t launches = 0;
+  bool timing = false;
+  std::vector<TimedEvent> tev;
+  std::vector<cudaEvent_t> ev_pool;
+  double t_ms[TK_COUNT] = {0};
+  int64_t t_n[TK_COUNT] = {0};
+
+  NcclApi nccl;
+  void* comm = nullptr;
+  int world = 1, rank = 0;
+};
+
+static thread_local std::string g_err;
+
+static int fail(dpmm_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(ctx, DPMM_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+  } while (0)
+#define NEED(cond, code, msg) \
+  do {                        \
+    if (!(cond)) return fail(ctx, code, msg); \
+  } while (0)
+
+struct KernelTimer {
+  dpmm_ctx* c;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int kind;
+  KernelTimer(dpmm_ctx* c_, int kind_, int nlaunch = 1) : c(c_), kind(kind_) {
+    c->launches += nlaunch;
+    if (c->timing) {
+      auto get = [&]() {
+        cudaEvent_t e;
+        if (!c->ev_pool.empty()) {
+          e = c->ev_pool.back();
+          c->ev_pool.pop_back();
+        } else {
+          cudaEventCreate(&e);
+        }
+        return e;
+      };
+      a = get();
+      b = get();
+      cudaEventRecord(a, c->stream);
+    }
+  }
+  ~KernelTimer() {
+    if (a) {
+      cudaEventRecord(b, c->stream);
+      c->tev.push_back(TimedEvent{a, b, kind});
+      c->t_n[kind] += 1;
+    }
+  }
+};
+
+static int ensure_stage(dpmm_ctx* ctx, size_t bytes) {
+  if (ctx->hstage_bytes >= bytes) return 0;
+  if (ctx->hstage) cudaFreeHost(ctx->hstage);
+  ctx->hstage = nullptr;
+  ctx->hstage_bytes = 0;
+  size_t want = std::max(bytes, (size_t)1 << 20);
+  CK(cudaMallocHost(&ctx->hstage, want));
+  ctx->hstage_bytes = want;
+  return 0;
+}
+
+template <typename T>
+static cudaError_t dev_realloc(T** p, size_t count) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+}
+
+// number of label values any K-sized table must cover
+static int keff(const dpmm_ctx* c) { return std::max(std::max(c->K, c->label_bound), 1); }
+
+static int nrec_floats(const dpmm_ctx* c) {
+  if (c->prior == DPMM_PRIOR_MULTINOMIAL) return c->D;
+  const int D = c->D;
+  return ((D * (D + 1) / 2 + 3) & ~3) + ((D + 3) & ~3);
+}
+
+static int ensure_k(dpmm_ctx* ctx, int K) {
+  if (K <= ctx->Kcap) return 0;
+  int cap = std::max(K, std::max(8, ctx->Kcap * 2));
+  cap = std::min(cap, DPMM_MAX_K);
+  if (K > cap) return fail(ctx, DPMM_ELIMIT, "K exceeds DPMM_MAX_K");
+  // the stream may still read the old buffers
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int D = ctx->D;
+  ctx->rec_f = nrec_floats(ctx);
+  ctx->stats_rec = (ctx->prior == DPMM_PRIOR_NIW) ? 1 + D + D * D : 1 + D;
+  // preserve nothing: all K-sized buffers are rewritten by the next set_params / sort
+  CK(dev_realloc(&ctx->recs, (size_t)3 * cap * ctx->rec_f));
+  CK(dev_realloc(&ctx->cst, (size_t)3 * cap));
+  CK(dev_realloc(&ctx->logw, (size_t)cap));
+  CK(dev_realloc(&ctx->loglr, (size_t)2 * cap));
+  if (ctx->prior == DPMM_PRIOR_MULTINOMIAL) CK(dev_realloc(&ctx->logp_t, (size_t)D * (cap + MNM_KT)));
+  CK(dev_realloc(&ctx->hist, (size_t)cap));
+  CK(dev_realloc(&ctx->seg_off, (size_t)cap + 1));
+  CK(dev_realloc(&ctx->scat_cursor, (size_t)cap));
+  CK(dev_realloc(&ctx->lr_cursor, (size_t)2 * cap));
+  CK(dev_realloc(&ctx->lut_l, (size_t)cap));
+  CK(dev_realloc(&ctx->lut_r, (size_t)cap));
+  CK(dev_realloc(&ctx->rule, (size_t)cap));
+  CK(dev_realloc(&ctx->wanted, (size_t)cap));
+  CK(dev_realloc(&ctx->idx_list, (size_t)cap));
+  CK(dev_realloc(&ctx->acc, (size_t)2 * cap * ctx->stats_rec));
+  CK(dev_realloc(&ctx->outbuf, (size_t)3 * cap * ctx->stats_rec));
+  ctx->items_cap = ctx->n / ctx->chunk + 2 * (int64_t)cap + 2;
+  CK(dev_realloc(&ctx->items, (size_t)ctx->items_cap));
+  ctx->Kcap = cap;
+  ctx->hist_valid = ctx->sorted = ctx->partitioned = false;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// template dispatch over the feature dimension (NIW)
+// ------------------------------------------------------------------------------------------------
+#define DPMM_NIW_DIMS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(12) X(16) X(24) X(32) X(48) X(64)
+
+template <int D>
+struct LabelP {  // points per thread of the label kernel
+  static constexpr int P = (D <= 16) ? 4 : (D <= 32 ? 2 : 1);
+};
+
+static bool niw_dim_supported(int D) {
+  switch (D) {
+#define X(d) case d:
+    DPMM_NIW_DIMS(X)
+#undef X
+    return true;
+    default:
+      return false;
+  }
+}
+
+template <int D>
+static int launch_gauss_label(dpmm_ctx* ctx, GaussLabelArgs a) {
+  using C = GaussCfg<D>;
+  constexpr int P = LabelP<D>::P;
+  const size_t budget2 = 110 * 1024, budget1 = (size_t)ctx->smem_optin;
+  int T = 128, KC = a.K;
+  auto bytes = [&](int T_, int KC_) {
+    return ((size_t)T_ * P * C::DS + (size_t)a.K * T_ * P + (size_t)KC_ * C::REC) * 4 + (size_t)a.K * 4;
+  };
+  // prefer two CTAs per SM; shrink the staged-cluster chunk first, then the tile
+  bool ok = false;
+  for (size_t budget : {budget2, budget1}) {
+    for (int T_ : {128, 64, 32}) {
+      if (bytes(T_, 1) > budget) continue;
+      T = T_;
+      KC = a.K;
+      while (bytes(T, KC) > budget) KC = (KC + 1) / 2;
+      ok = true;
+      break;
+    }
+    if (ok) break;
+  }
+  if (!ok) return fail(ctx, DPMM_ELIMIT, "K too large for the label kernel's shared-memory slice");
+  a.KC = KC;
+  const int TP = T * P;
+  a.ntiles = (a.n + TP - 1) / TP;
+  const size_t sm = bytes(T, KC);
+  auto kern = gauss_label_kernel<D, P>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  int occ = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, sm));
+  occ = std::max(occ, 1);
+  const int64_t grid = std::min<int64_t>(a.ntiles, (int64_t)ctx->sm_count * occ);
+  KernelTimer kt(ctx, TK_LABEL);
+  kern<<<(unsigned)grid, T, sm, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <int D>
+static int launch_gauss_sublabel(dpmm_ctx* ctx, const SubLabelArgs& a, bool sample) {
+  const int T = 128;
+  const unsigned grid = (unsigned)((a.n + T - 1) / T);
+  KernelTimer kt(ctx, TK_SUBLABEL);
+  if (sample)
+    gauss_sublabel_kernel<D, true><<<grid, T, 0, ctx->stream>>>(a);
+  else
+    gauss_sublabel_kernel<D, false><<<grid, T, 0, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <int D>
+static int launch_niw_stats(dpmm_ctx* ctx, const StatsArgs& a) {
+  using C = StatsCfg<D>;
+  auto kern = niw_stats_kernel<D>;
+  int occ = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::WARPS * 32, 0));
+  occ = std::max(occ, 1);
+  KernelTimer kt(ctx, TK_STATS);
+  kern<<<ctx->sm_count * occ, C::WARPS * 32, 0, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* dpmm_last_error(const dpmm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+extern "C" int dpmm_limits(int32_t* out3) {
+  if (!out3) return DPMM_EINVAL;
+  out3[0] = 64;
+  out3[1] = 1024;
+  out3[2] = DPMM_MAX_K;
+  return 0;
+}
+
+extern "C" int dpmm_create(dpmm_ctx** out, const float* x, int64_t n_local, int32_t d, int32_t prior_kind,
+                           int32_t device, uint64_t seed, int64_t global_offset) {
+  dpmm_ctx* ctx = nullptr;
+  if (!out) return fail(nullptr, DPMM_EINVAL, "out is NULL");
+  *out = nullptr;
+  NEED(x != nullptr && n_local > 0 && d > 0, DPMM_EINVAL, "x must be non-NULL with n_local > 0 and d > 0");
+  NEED(n_local < ((int64_t)1 << 31) - 4096, DPMM_ELIMIT, "n_local must fit in int32 (shard the points over more GPUs)");
+  NEED(prior_kind == DPMM_PRIOR_NIW || prior_kind == DPMM_PRIOR_MULTINOMIAL, DPMM_EINVAL, "unknown prior kind");
+  if (prior_kind == DPMM_PRIOR_NIW)
+    NEED(niw_dim_supported(d), DPMM_ELIMIT,
+         "NIW: D must be one of 1-8, 12, 16, 24, 32, 48, 64 (zero-pad the features otherwise)");
+  else
+    NEED(d <= 1024, DPMM_ELIMIT, "multinomial: D must be <= 1024");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, DPMM_ECUDA, "no CUDA device: libdpmm_b200 has no CPU fallback");
+  NEED(device >= 0 && device < ndev, DPMM_EINVAL, "bad device ordinal");
+  ctx = new dpmm_ctx();
+  ctx->device = device;
+  ctx->n = n_local;
+  ctx->D = d;
+  ctx->prior = prior_kind;
+  ctx->seed = seed;
+  ctx->goff = global_offset;
+  auto bail = [&](int code) {
+    g_err = ctx->err;
+    dpmm_destroy(ctx);
+    return code;
+  };
+#define CKC(call)                                                                        \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                    \
+      return bail(DPMM_ECUDA);                                                           \
+    }                                                                                    \
+  } while (0)
+  CKC(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CKC(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    ctx->err = "device is not sm_100-class (Blackwell); this library ships sm_100a code only";
+    return bail(DPMM_ECUDA);
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CKC(cudaMalloc((void**)&ctx->x, (size_t)n_local * d * sizeof(float)));
+  CKC(cudaMalloc((void**)&ctx->labels, (size_t)n_local * sizeof(int32_t)));
+  CKC(cudaMalloc((void**)&ctx->sub, (size_t)n_local));
+  CKC(cudaMalloc((void**)&ctx->perm, (size_t)n_local * sizeof(int32_t)));
+  CKC(cudaMalloc((void**)&ctx->perm2, (size_t)n_local * sizeof(int32_t)));
+  CKC(cudaMalloc((void**)&ctx->item_ctr, 2 * sizeof(int32_t)));
+  CKC(cudaMemcpyAsync(ctx->x, x, (size_t)n_local * d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaMemsetAsync(ctx->labels, 0, (size_t)n_local * sizeof(int32_t), ctx->stream));
+  CKC(cudaMemsetAsync(ctx->sub, 0, (size_t)n_local, ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+#undef CKC
+  ctx->chunk = 1024;
+  *out = ctx;
+  return 0;
+}
+
+extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
+  for (auto& t : ctx->tev) {
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+  void* ptrs[] = {ctx->x, ctx->labels, ctx->sub, ctx->perm, ctx->perm2, ctx->u_label, ctx->u_sub, ctx->r_bits,
+                  ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->hist, ctx->seg_off,
+                  ctx->scat_cursor, ctx->lr_cursor, ctx->lut_l, ctx->lut_r, ctx->rule, ctx->wanted,
+                  ctx->idx_list, ctx->acc, ctx->outbuf, ctx->items, ctx->item_ctr};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (ctx->hstage) cudaFreeHost(ctx->hstage);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+extern "C" int dpmm_set_stream(dpmm_ctx* ctx, void* cuda_stream) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return 0;
+}
+
+extern "C" int dpmm_sync(dpmm_ctx* ctx) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int dpmm_set_sampler(dpmm_ctx* ctx, int32_t sampler) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  NEED(sampler == DPMM_SAMPLER_INVERSE_CDF || sampler == DPMM_SAMPLER_GUMBEL, DPMM_EINVAL, "unknown sampler");
+  ctx->sampler = sampler;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// relabel plumbing
+// ------------------------------------------------------------------------------------------------
+static int run_relabel(dpmm_ctx* ctx, const std::vector<int32_t>& ll, const std::vector<int32_t>& lr,
+                       const std::vector<uint8_t>& rule, bool uses_rng) {
+  const int K = (int)ll.size();
+  int rc = ensure_k(ctx, K);
+  if (rc) return rc;
+  const size_t b4 = (size_t)K * 4;
+  rc = ensure_stage(ctx, 2 * b4 + K);
+  if (rc) return rc;
+  // the staging buffer may still be in flight from a previous async copy
+  CK(cudaStreamSynchronize(ctx->stream));
+  char* h = (char*)ctx->hstage;
+  memcpy(h, ll.data(), b4);
+  memcpy(h + b4, lr.data(), b4);
+  memcpy(h + 2 * b4, rule.data(), K);
+  CK(cudaMemcpyAsync(ctx->lut_l, h, b4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->lut_r, h + b4, b4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->rule, h + 2 * b4, K, cudaMemcpyHostToDevice, ctx->stream));
+  if (uses_rng) ctx->call += 1;
+  {
+    KernelTimer kt(ctx, TK_RELABEL);
+    const int T = 256;
+    const unsigned grid = (unsigned)std::min<int64_t>((ctx->n + T - 1) / T, (int64_t)ctx->sm_count * 16);
+    relabel_kernel<<<grid, T, 0, ctx->stream>>>(ctx->labels, ctx->sub, ctx->n, K, ctx->lut_l, ctx->lut_r, ctx->rule,
+                                                ctx->r_bits, ctx->seed, ctx->call, ctx->goff);
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+extern "C" int dpmm_init_labels(dpmm_ctx* ctx, int32_t init_clusters, int32_t outlier) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  NEED(init_clusters >= 1 && init_clusters + (outlier ? 1 : 0) <= DPMM_MAX_K, DPMM_EINVAL, "bad init_clusters");
+  CK(cudaSetDevice(ctx->device));
+  ctx->label_bound = init_clusters + (outlier ? 1 : 0);
+  {
+    int rc = ensure_k(ctx, ctx->label_bound);
+    if (rc) return rc;
+  }
+  ctx->call += 1;
+  {
+    KernelTimer kt(ctx, TK_RELABEL);
+    const int T = 256;
+    const unsigned grid = (unsigned)std::min<int64_t>((ctx->n + T - 1) / T, (int64_t)ctx->sm_count * 16);
+    init_labels_kernel<<<grid, T, 0, ctx->stream>>>(ctx->labels, ctx->n, init_clusters, outlier ? 1 : 0, ctx->seed,
+                                                    ctx->call, ctx->goff);
+    CK(cudaGetLastError());
+  }
+  ctx->hist_valid = ctx->sorted = ctx->partitioned = false;
+  return dpmm_randomize_sublabels(ctx, nullptr, 0);
+}
+
+extern "C" int dpmm_randomize_sublabels(dpmm_ctx* ctx, const int64_t* indices, int32_t n_indices) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  int K = keff(ctx);
+  if (indices != nullptr) {
+    for (int i = 0; i < n_indices; ++i) {
+      NEED(indices[i] >= 1 && indices[i] <= DPMM_MAX_K, DPMM_EINVAL, "cluster index out of range");
+      K = std::max<int>(K, (int)indices[i]);
+    }
+  }
+  std::vector<int32_t> ll(K), lr(K);
+  std::vector<uint8_t> rule(K, indices == nullptr ? 3 : 0);
+  for (int k = 0; k < K; ++k) ll[k] = lr[k] = k;
+  if (indices != nullptr) {
+    if (n_indices == 0) return 0;
+    for (int i = 0; i < n_indices; ++i) rule[indices[i] - 1] = 3;
+  }
+  ctx->partitioned = false;
+  return run_relabel(ctx, ll, lr, rule, true);
+}
+
+extern "C" int dpmm_apply_split(dpmm_ctx* ctx, const int64_t* indices, const int64_t* new_indices, int32_t n) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return 0;
+  NEED(indices && new_indices && n > 0, DPMM_EINVAL, "bad split lists");
+  int K = keff(ctx);
+  for (int i = 0; i < n; ++i) {
+    NEED(indices[i] >= 1 && new_indices[i] >= 1 && indices[i] <= DPMM_MAX_K && new_indices[i] <= DPMM_MAX_K,
+         DPMM_EINVAL, "cluster index out of range");
+    K = std::max<int>(K, (int)std::max(indices[i], new_indices[i]));
+  }
+  // sequential semantics of the reference loop (local_clusters_actions.jl:269-277) composed into
+  // one table: maps are tracked per ORIGINAL (label, side).
+  std::vector<int32_t> ll(K), lr(K);
+  std::vector<uint8_t> rule(K, 0);
+  for (int k = 0; k < K; ++k) ll[k] = lr[k] = k;
+  for (int i = 0; i < n; ++i) {
+    const int idx = (int)indices[i] - 1, nw = (int)new_indices[i] - 1;
+    for (int k = 0; k < K; ++k) {
+      // points currently labelled idx: those whose left/right image is idx.  A point that already
+      // received a fresh random sub-label (rule 3) has an unknown side; the reference only ever
+      // issues disjoint splits, so reject the ambiguous case instead of guessing.
+      const bool hit_l = ll[k] == idx, hit_r = lr[k] == idx;
+      if (!hit_l && !hit_r) continue;
+      NEED(rule[k] == 0 && hit_l && hit_r, DPMM_EINVAL, "split lists must be disjoint");
+      lr[k] = nw;
+      rule[k] = 3;
+    }
+  }
+  ctx->label_bound = std::max(ctx->label_bound, K);
+  ctx->hist_valid = ctx->sorted = ctx->partitioned = false;
+  return run_relabel(ctx, ll, lr, rule, true);
+}
+
+extern "C" int dpmm_apply_merge(dpmm_ctx* ctx, const int64_t* indices, const int64_t* new_indices, int32_t n) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return 0;
+  NEED(indices && new_indices && n > 0, DPMM_EINVAL, "bad merge lists");
+  int K = keff(ctx);
+  for (int i = 0; i < n; ++i) {
+    NEED(indices[i] >= 1 && new_indices[i] >= 1 && indices[i] <= DPMM_MAX_K && new_indices[i] <= DPMM_MAX_K,
+         DPMM_EINVAL, "cluster index out of range");
+    K = std::max<int>(K, (int)std::max(indices[i], new_indices[i]));
+  }
+  // merge never looks at the sub-label, so the sequential loop (:297-303) composes exactly:
+  // lab[k] = current label of points that started with label k, rule[k] = their forced side.
+  std::vector<int32_t> lab(K);
+  std::vector<uint8_t> rule(K, 0);
+  for (int k = 0; k < K; ++k) lab[k] = k;
+  for (int i = 0; i < n; ++i) {
+    const int idx = (int)indices[i] - 1, nw = (int)new_indices[i] - 1;
+    for (int k = 0; k < K; ++k)
+      if (lab[k] == idx) rule[k] = 1;
+    for (int k = 0; k < K; ++k)
+      if (lab[k] == nw) {
+        rule[k] = 2;
+        lab[k] = idx;
+      }
+  }
+  ctx->hist_valid = ctx->sorted = ctx->partitioned = false;
+  return run_relabel(ctx, lab, lab, rule, false);
+}
+
+extern "C" int dpmm_remove_empty(dpmm_ctx* ctx, const int64_t* pts_count, int32_t k) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  NEED(pts_count && k >= 1 && k <= DPMM_MAX_K, DPMM_EINVAL, "bad pts_count");
+  // remove_empty_clusters_worker! (:446-455): new = old - #{empty clusters with index < old}
+  std::vector<int32_t> lab(k);
+  std::vector<uint8_t> rule(k, 0);
+  int removed = 0;
+  bool any = false;
+  for (int i = 0; i < k; ++i) {
+    lab[i] = i - removed;
+    if (pts_count[i] == 0) {
+      ++removed;
+      any = true;
+    }
+  }
+  if (!any) return 0;
+  NEED(ctx->label_bound <= k, DPMM_EINVAL, "pts_count is shorter than the number of label values in use");
+  ctx->label_bound = std::max(1, k - removed);
+  ctx->K = std::min(ctx->K, ctx->label_bound);  // parameters of the dropped clusters are stale anyway
+  ctx->params_set = false;
+  ctx->hist_valid = ctx->sorted = ctx->partitioned = false;
+  return run_relabel(ctx, lab, lab, rule, false);
+}
+
+// ------------------------------------------------------------------------------------------------
+// label gather / restore
+// ------------------------------------------------------------------------------------------------
+extern "C" int dpmm_get_labels(dpmm_ctx* ctx, int64_t* out) {
+  NEED(ctx && out, DPMM_EINVAL, "NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_stage(ctx, (size_t)ctx->n * 4);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->hstage, ctx->labels, (size_t)ctx->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int32_t* h = (const int32_t*)ctx->hstage;
+  for (int64_t i = 0; i < ctx->n; ++i) out[i] = (int64_t)h[i] + 1;
+  return 0;
+}
+
+extern "C" int dpmm_get_sublabels(dpmm_ctx* ctx, int64_t* out) {
+  NEED(ctx && out, DPMM_EINVAL, "NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_stage(ctx, (size_t)ctx->n);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->hstage, ctx->sub, (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const uint8_t* h = (const uint8_t*)ctx->hstage;
+  for (int64_t i = 0; i < ctx->n; ++i) out[i] = (int64_t)h[i] + 1;
+  return 0;
+}
+
+extern "C" int dpmm_set_labels(dpmm_ctx* ctx, const int64_t* labels) {
+  NEED(ctx && labels, DPMM_EINVAL, "NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_stage(ctx, (size_t)ctx->n * 4);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  int32_t* h = (int32_t*)ctx->hstage;
+  int64_t mx = 0;
+  for (int64_t i = 0; i < ctx->n; ++i) {
+    NEED(labels[i] >= 1 && labels[i] <= DPMM_MAX_K, DPMM_EINVAL, "label out of range [1, DPMM_MAX_K]");
+    h[i] = (int32_t)(labels[i] - 1);
+    mx = std::max(mx, labels[i]);
+  }
+  ctx->label_bound = (int)mx;
+  rc = ensure_k(ctx, (int)mx);
+  if (rc) return rc;
+  h = (int32_t*)ctx->hstage;
+  CK(cudaMemcpyAsync(ctx->labels, h, (size_t)ctx->n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->hist_valid = ctx->sorted = ctx->partitioned = false;
+  return 0;
+}
+
+extern "C" int dpmm_set_sublabels(dpmm_ctx* ctx, const int64_t* sublabels) {
+  NEED(ctx && sublabels, DPMM_EINVAL, "NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_stage(ctx, (size_t)ctx->n);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  uint8_t* h = (uint8_t*)ctx->hstage;
+  for (int64_t i = 0; i < ctx->n; ++i) {
+    NEED(sublabels[i] == 1 || sublabels[i] == 2, DPMM_EINVAL, "sub-label must be 1 or 2");
+    h[i] = (uint8_t)(sublabels[i] - 1);
+  }
+  CK(cudaMemcpyAsync(ctx->sub, h, (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->partitioned = false;
+  return 0;
+}
+
+extern "C" int dpmm_set_uniforms(dpmm_ctx* ctx, const double* u_label, const double* u_sub, const uint8_t* r_bits) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  auto put = [&](auto** dev, const auto* host, size_t bytes) -> cudaError_t {
+    if (host == nullptr) {
+      if (*dev) cudaFree(*dev);
+      *dev = nullptr;
+      return cudaSuccess;
+    }
+    if (*dev == nullptr) {
+      cudaError_t e = cudaMalloc((void**)dev, bytes);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice);
+  };
+  CK(put(&ctx->u_label, u_label, (size_t)ctx->n * 8));
+  CK(put(&ctx->u_sub, u_sub, (size_t)ctx->n * 8));
+  CK(put(&ctx->r_bits, r_bits, (size_t)ctx->n));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------------
+static void common_weights(dpmm_ctx* ctx, int K, const float* weights, const float* lr_weights, float* h_logw,
+                           float* h_loglr) {
+  // log(v) at local_clusters_actions.jl:126 and :92-93 is a Float32 log; evaluate in Float64 and
+  // round once (matches the oracle's log_f32).
+  for (int k = 0; k < K; ++k) h_logw[k] = (float)std::log((double)weights[k]);
+  for (int k = 0; k < 2 * K; ++k) h_loglr[k] = (float)std::log((double)lr_weights[k]);
+}
+
+extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, const float* inv_sigma,
+                                   const float* logdet, const float* weights, const float* lr_weights) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  NEED(ctx->prior == DPMM_PRIOR_NIW, DPMM_ESTATE, "context was created with the multinomial prior");
+  NEED(K >= 1 && K <= DPMM_MAX_K, DPMM_ELIMIT, "K out of range");
+  NEED(mu && inv_sigma && logdet && weights && lr_weights, DPMM_EINVAL, "NULL parameter array");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_k(ctx, K);
+  if (rc) return rc;
+  const int D = ctx->D, REC = ctx->rec_f, TRIP = (D * (D + 1) / 2 + 3) & ~3;
+  const size_t nrec = (size_t)3 * K;
+  const size_t bytes = (nrec * REC + nrec + K + 2 * K) * sizeof(float);
+  rc = ensure_stage(ctx, bytes);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));  // staging buffer reuse
+  float* h_recs = (float*)ctx->hstage;
+  float* h_cst = h_recs + nrec * REC;
+  float* h_logw = h_cst + nrec;
+  float* h_loglr = h_logw + K;
+  std::vector<double> L((size_t)D * D);
+  const float log2pi = (float)std::log(2.0 * M_PI);  // Float32(log(2pi)), mv_gaussian.jl:24
+  for (size_t t = 0; t < nrec; ++t) {
+    const float* A = inv_sigma + t * D * D;
+    float* rec = h_recs + t * REC;
+    std::fill(rec, rec + REC, 0.f);
+    // Cholesky A = L L' in Float64; U = L' (upper), so z'Az = |U z|^2.
+    bool ok = true;
+    for (int j = 0; j < D && ok; ++j) {
+      double s = 0.5 * ((double)A[(size_t)j * D + j] + (double)A[(size_t)j * D + j]);
+      for (int p = 0; p < j; ++p) s -= L[(size_t)j * D + p] * L[(size_t)j * D + p];
+      if (!(s > 0.0) || !std::isfinite(s)) {
+        ok = false;
+        break;
+      }
+      const double ljj = std::sqrt(s);
+      L[(size_t)j * D + j] = ljj;
+      for (int i = j + 1; i < D; ++i) {
+        double v = 0.5 * ((double)A[(size_t)i * D + j] + (double)A[(size_t)j * D + i]);
+        for (int p = 0; p < j; ++p) v -= L[(size_t)i * D + p] * L[(size_t)j * D + p];
+        L[(size_t)i * D + j] = v / ljj;
+      }
+    }
+    int e = 0;
+    for (int i = 0; i < D; ++i)
+      for (int j = i; j < D; ++j) rec[e++] = ok ? (float)L[(size_t)j * D + i] : NAN;  // U[i][j] = L[j][i]
+    for (int j = 0; j < D; ++j) rec[TRIP + j] = mu[t * D + j];
+    h_cst[t] = ((float)(D * D) * log2pi + logdet[t]) / 2.f;
+  }
+  common_weights(ctx, K, weights, lr_weights, h_logw, h_loglr);
+  CK(cudaMemcpyAsync(ctx->recs, h_recs, nrec * REC * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->cst, h_cst, nrec * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->logw, h_logw, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->loglr, h_loglr, (size_t)2 * K * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->K = K;
+  ctx->params_set = true;
+  return 0;
+}
+
+extern "C" int dpmm_set_params_multinomial(dpmm_ctx* ctx, int32_t K, const float* log_p, const float* weights,
+                                           const float* lr_weights) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  NEED(ctx->prior == DPMM_PRIOR_MULTINOMIAL, DPMM_ESTATE, "context was created with the NIW prior");
+  NEED(K >= 1 && K <= DPMM_MAX_K, DPMM_ELIMIT, "K out of range");
+  NEED(log_p && weights && lr_weights, DPMM_EINVAL, "NULL parameter array");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_k(ctx, K);
+  if (rc) return rc;
+  const int D = ctx->D;
+  const int KP = (K + MNM_KT - 1) / MNM_KT * MNM_KT;
+  const size_t nrec = (size_t)3 * K;
+  const size_t bytes = (nrec * D + (size_t)D * KP + K + 2 * K) * sizeof(float);
+  rc = ensure_stage(ctx, bytes);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  float* h_recs = (float*)ctx->hstage;
+  float* h_t = h_recs + nrec * D;
+  float* h_logw = h_t + (size_t)D * KP;
+  float* h_loglr = h_logw + K;
+  memcpy(h_recs, log_p, nrec * D * 4);
+  std::fill(h_t, h_t + (size_t)D * KP, 0.f);
+  for (int k = 0; k < K; ++k)
+    for (int d = 0; d < D; ++d) h_t[(size_t)d * KP + k] = log_p[(size_t)(3 * k) * D + d];
+  common_weights(ctx, K, weights, lr_weights, h_logw, h_loglr);
+  CK(cudaMemcpyAsync(ctx->recs, h_recs, nrec * D * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->logp_t, h_t, (size_t)D * KP * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->logw, h_logw, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->loglr, h_loglr, (size_t)2 * K * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->K = K;
+  ctx->KP = KP;
+  ctx->params_set = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the sweep
+// ------------------------------------------------------------------------------------------------
+static int run_sample_labels(dpmm_ctx* ctx, int final_iter, float* dump) {
+  NEED(ctx->params_set, DPMM_ESTATE, "set_params must precede sample_labels");
+  const int K = ctx->K;
+  ctx->call += 1;
+  CK(cudaMemsetAsync(ctx->hist, 0, (size_t)K * 4, ctx->stream));
+  if (ctx->prior == DPMM_PRIOR_NIW) {
+    GaussLabelArgs a{};
+    a.x = ctx->x; a.n = ctx->n; a.K = K; a.recs = ctx->recs; a.cst = ctx->cst; a.logw = ctx->logw;
+    a.labels = ctx->labels; a.hist = ctx->hist; a.u_inj = ctx->u_label; a.seed = ctx->seed; a.call = ctx->call;
+    a.goff = ctx->goff; a.final_iter = final_iter; a.sampler = ctx->sampler; a.dump = dump;
+    int rc = DPMM_ELIMIT;
+    switch (ctx->D) {
+#define X(d) case d: rc = launch_gauss_label<d>(ctx, a); break;
+      DPMM_NIW_DIMS(X)
+#undef X
+    }
+    if (rc) return rc;
+  } else {
+    MnmLabelArgs a{};
+    a.x = ctx->x; a.n = ctx->n; a.D = ctx->D; a.DS = ctx->D | 1; a.K = K; a.KP = ctx->KP; a.logp_t = ctx->logp_t;
+    a.logw = ctx->logw; a.labels = ctx->labels; a.hist = ctx->hist; a.u_inj = ctx->u_label; a.seed = ctx->seed;
+    a.call = ctx->call; a.goff = ctx->goff; a.final_iter = final_iter; a.sampler = ctx->sampler; a.dump = dump;
+    int T = 128;
+    auto bytes = [&](int T_) { return ((size_t)a.D * a.KP + (size_t)T_ * a.DS + (size_t)K * T_) * 4 + (size_t)K * 4; };
+    while (T > 32 && bytes(T) > (size_t)ctx->smem_optin) T /= 2;
+    NEED(bytes(T) <= (size_t)ctx->smem_optin, DPMM_ELIMIT, "multinomial: D*K too large for the shared-memory table");
+    a.ntiles = (a.n + T - 1) / T;
+    const size_t sm = bytes(T);
+    CK(cudaFuncSetAttribute(mnm_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mnm_label_kernel, T, sm));
+    occ = std::max(occ, 1);
+    const int64_t grid = std::min<int64_t>(a.ntiles, (int64_t)ctx->sm_count * occ);
+    KernelTimer kt(ctx, TK_LABEL);
+    mnm_label_kernel<<<(unsigned)grid, T, sm, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+  }
+  ctx->hist_valid = true;
+  ctx->sorted = false;
+  ctx->partitioned = false;
+  ctx->label_bound = K;
+  return 0;
+}
+
+static int ensure_sorted(dpmm_ctx* ctx) {
+  if (ctx->sorted) return 0;
+  const int K = keff(ctx);
+  {
+    int rc = ensure_k(ctx, K);
+    if (rc) return rc;
+  }
+  KernelTimer kt(ctx, TK_SORT, ctx->hist_valid ? 2 : 3);
+  if (!ctx->hist_valid) {
+    CK(cudaMemsetAsync(ctx->hist, 0, (size_t)K * 4, ctx->stream));
+    const int T = 256;
+    const unsigned grid = (unsigned)std::min<int64_t>((ctx->n + T - 1) / T, (int64_t)ctx->sm_count * 8);
+    label_hist_kernel<<<grid, T, (size_t)K * 4, ctx->stream>>>(ctx->labels, ctx->n, K, ctx->hist);
+    CK(cudaGetLastError());
+    ctx->hist_valid = true;
+  }
+  label_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hist, K, ctx->seg_off, ctx->scat_cursor, ctx->lr_cursor);
+  CK(cudaGetLastError());
+  {
+    const int T = 256;
+    const unsigned grid = (unsigned)((ctx->n + (int64_t)T * SCATTER_PPT - 1) / ((int64_t)T * SCATTER_PPT));
+    label_scatter_kernel<<<grid, T, (size_t)K * 8, ctx->stream>>>(ctx->labels, ctx->n, K, ctx->scat_cursor, ctx->perm);
+    CK(cudaGetLastError());
+  }
+  ctx->sorted = true;
+  ctx->partitioned = false;
+  return 0;
+}
+
+// sub-label draw (sample=true) or partition only (sample=false); both leave perm2 partitioned.
+static int run_sublabels(dpmm_ctx* ctx, bool sample, float* dump) {
+  int rc = ensure_sorted(ctx);
+  if (rc) return rc;
+  if (ctx->partitioned) {
+    // cursors were consumed by a previous partition of the same sort: rebuild them
+    KernelTimer kt(ctx, TK_SORT);
+    label_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hist, keff(ctx), ctx->seg_off, ctx->scat_cursor,
+                                                   ctx->lr_cursor);
+    CK(cudaGetLastError());
+  }
+  SubLabelArgs a{};
+  a.x = ctx->x; a.n = ctx->n; a.K = ctx->K; a.recs = ctx->recs; a.cst = ctx->cst; a.loglr = ctx->loglr;
+  a.labels = ctx->labels; a.sub = ctx->sub; a.perm = ctx->perm; a.perm2 = ctx->perm2; a.cursor = ctx->lr_cursor;
+  a.u_inj = ctx->u_sub; a.seed = ctx->seed; a.call = ctx->call; a.goff = ctx->goff; a.dump = dump; a.D = ctx->D;
+  if (ctx->prior == DPMM_PRIOR_NIW) {
+    rc = DPMM_ELIMIT;
+    switch (ctx->D) {
+#define X(d) case d: rc = launch_gauss_sublabel<d>(ctx, a, sample); break;
+      DPMM_NIW_DIMS(X)
+#undef X
+    }
+    if (rc) return rc;
+  } else {
+    const int T = 128;
+    const unsigned grid = (unsigned)((a.n + T - 1) / T);
+    KernelTimer kt(ctx, TK_SUBLABEL);
+    if (sample)
+      mnm_sublabel_kernel<true><<<grid, T, 0, ctx->stream>>>(a);
+    else
+      mnm_sublabel_kernel<false><<<grid, T, 0, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+  }
+  ctx->partitioned = true;
+  return 0;
+}
+
+extern "C" int dpmm_sample_labels(dpmm_ctx* ctx, int32_t final_iter) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  return run_sample_labels(ctx, final_iter, nullptr);
+}
+
+extern "C" int dpmm_sample_sublabels(dpmm_ctx* ctx) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->params_set, DPMM_ESTATE, "set_params must precede sample_sublabels");
+  NEED(ctx->label_bound <= ctx->K, DPMM_ESTATE, "labels refer to clusters beyond the K of set_params");
+  ctx->call += 1;
+  return run_sublabels(ctx, true, nullptr);
+}
+
+extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_indices, int64_t* counts,
+                               double* sum_x, double* sum_xx) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  const int K = keff(ctx);
+  int rc = ensure_k(ctx, K);
+  if (rc) return rc;
+  const int D = ctx->D, rec = ctx->stats_rec;
+  std::vector<int32_t> idx;
+  if (indices == nullptr) {
+    idx.resize(K);
+    for (int k = 0; k < K; ++k) idx[k] = k;
+  } else {
+    NEED(n_indices >= 0, DPMM_EINVAL, "n_indices < 0");
+    idx.resize(n_indices);
+    for (int i = 0; i < n_indices; ++i) {
+      NEED(indices[i] >= 1 && indices[i] <= K, DPMM_EINVAL, "cluster index out of range [1, K]");
+      idx[i] = (int32_t)indices[i] - 1;
+    }
+  }
+  const int m = (int)idx.size();
+  if (m == 0) return 0;
+  NEED(m <= ctx->Kcap, DPMM_EINVAL, "more indices than clusters");
+  if (!ctx->partitioned) {
+    rc = run_sublabels(ctx, false, nullptr);
+    if (rc) return rc;
+  }
+  const bool all = (indices == nullptr);
+  rc = ensure_stage(ctx, std::max<size_t>((size_t)m * 4 + K, (size_t)m * 3 * rec * 8));
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  {
+    int32_t* h_idx = (int32_t*)ctx->hstage;
+    uint8_t* h_w = (uint8_t*)(h_idx + m);
+    memcpy(h_idx, idx.data(), (size_t)m * 4);
+    CK(cudaMemcpyAsync(ctx->idx_list, h_idx, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (!all) {
+      memset(h_w, 0, K);
+      for (int v : idx) h_w[v] = 1;
+      CK(cudaMemcpyAsync(ctx->wanted, h_w, K, cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  {
+    KernelTimer kt(ctx, TK_STATS_AUX);
+    stats_worklist_kernel<<<1, 256, (size_t)2 * K * 4, ctx->stream>>>(ctx->seg_off, ctx->lr_cursor,
+                                                                      all ? nullptr : ctx->wanted, K, ctx->chunk,
+                                                                      ctx->items, ctx->item_ctr, ctx->item_ctr + 1);
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemsetAsync(ctx->acc, 0, (size_t)2 * K * rec * 8, ctx->stream));
+  StatsArgs sa{};
+  sa.x = ctx->x; sa.D = D; sa.perm2 = ctx->perm2; sa.items = ctx->items; sa.n_items = ctx->item_ctr;
+  sa.next_item = ctx->item_ctr + 1; sa.acc = ctx->acc; sa.rec = rec;
+  if (ctx->prior == DPMM_PRIOR_NIW) {
+    rc = DPMM_ELIMIT;
+    switch (D) {
+#define X(d) case d: rc = launch_niw_stats<d>(ctx, sa); break;
+      DPMM_NIW_DIMS(X)
+#undef X
+    }
+    if (rc) return rc;
+  } else {
+    const int DPAD = (D + 31) & ~31;
+    const int T = std::max(256, DPAD);
+    const size_t sm = (size_t)MNM_STATS_TPTS * (D | 1) * 4;
+    CK(cudaFuncSetAttribute(mnm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mnm_stats_kernel, T, sm));
+    occ = std::max(occ, 1);
+    KernelTimer kt(ctx, TK_STATS);
+    mnm_stats_kernel<<<ctx->sm_count * occ, T, sm, ctx->stream>>>(sa);
+    CK(cudaGetLastError());
+  }
+  {
+    KernelTimer kt(ctx, TK_STATS_AUX);
+    const int T = 256;
+    dim3 grid((unsigned)std::min((rec + T - 1) / T, 64), (unsigned)m);
+    stats_finalize_kernel<<<grid, T, 0, ctx->stream>>>(ctx->acc, ctx->seg_off, ctx->lr_cursor, ctx->idx_list, m, D, rec,
+                                                       ctx->prior == DPMM_PRIOR_NIW ? 1 : 0, ctx->outbuf);
+    CK(cudaGetLastError());
+  }
+  if (ctx->comm != nullptr) {
+    KernelTimer kt(ctx, TK_ALLREDUCE);
+    // aggregate_suff_stats across workers (niw.jl:64-66; local_clusters_actions.jl:194-196, 246-248)
+    const int r = ctx->nccl.AllReduce(ctx->outbuf, ctx->outbuf, (size_t)m * 3 * rec, /*ncclFloat64*/ 8, /*ncclSum*/ 0,
+                                      ctx->comm, ctx->stream);
+    if (r != 0) return fail(ctx, DPMM_ENCCL, std::string("ncclAllReduce: ") + ctx->nccl.GetErrorString(r));
+  }
+  if (counts == nullptr && sum_x == nullptr && sum_xx == nullptr) return 0;
+  double* h = (double*)ctx->hstage;
+  CK(cudaMemcpyAsync(h, ctx->outbuf, (size_t)m * 3 * rec * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int a = 0; a < m; ++a)
+    for (int s = 0; s < 3; ++s) {
+      const double* r = h + ((size_t)a * 3 + s) * rec;
+      if (counts) counts[a * 3 + s] = (int64_t)llround(r[0]);
+      if (sum_x) memcpy(sum_x + ((size_t)a * 3 + s) * D, r + 1, (size_t)D * 8);
+      if (sum_xx && ctx->prior == DPMM_PRIOR_NIW)
+        memcpy(sum_xx + ((size_t)a * 3 + s) * D * D, r + 1 + D, (size_t)D * D * 8);
+    }
+  return 0;
+}
+
+extern "C" int dpmm_debug_loglik(dpmm_ctx* ctx, int32_t which, float* out) {
+  NEED(ctx && out, DPMM_EINVAL, "NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->params_set, DPMM_ESTATE, "set_params must precede debug_loglik");
+  NEED(which == 0 || which == 1, DPMM_EINVAL, "which must be 0 or 1");
+  const size_t cols = which == 0 ? (size_t)ctx->K : 2;
+  float* dump = nullptr;
+  CK(cudaMalloc((void**)&dump, cols * ctx->n * 4));
+  int rc = 0;
+  if (which == 0) {
+    // a dry run of the label kernel on a scratch label array: state (labels, RNG counter) untouched
+    int32_t* keep = ctx->labels;
+    int32_t* scratch = nullptr;
+    const uint32_t call0 = ctx->call;
+    const int lb0 = ctx->label_bound;
+    if (cudaMalloc((void**)&scratch, (size_t)ctx->n * 4) != cudaSuccess) {
+      cudaFree(dump);
+      return fail(ctx, DPMM_ECUDA, "cudaMalloc(scratch labels) failed");
+    }
+    ctx->labels = scratch;
+    rc = run_sample_labels(ctx, 1, dump);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->labels = keep;
+    ctx->call = call0;
+    ctx->label_bound = lb0;
+    ctx->hist_valid = ctx->sorted = ctx->partitioned = false;  // the histogram describes the scratch labels
+    cudaFree(scratch);
+  } else {
+    // sub-label matrix under the CURRENT labels; sub-labels are restored afterwards
+    uint8_t* keep = nullptr;
+    const uint32_t call0 = ctx->call;
+    if (ctx->label_bound > ctx->K) {
+      cudaFree(dump);
+      return fail(ctx, DPMM_ESTATE, "labels refer to clusters beyond the K of set_params");
+    }
+    if (cudaMalloc((void**)&keep, (size_t)ctx->n) != cudaSuccess) {
+      cudaFree(dump);
+      return fail(ctx, DPMM_ECUDA, "cudaMalloc(scratch sub-labels) failed");
+    }
+    cudaMemcpyAsync(keep, ctx->sub, (size_t)ctx->n, cudaMemcpyDeviceToDevice, ctx->stream);
+    rc = run_sublabels(ctx, true, dump);
+    cudaMemcpyAsync(ctx->sub, keep, (size_t)ctx->n, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->call = call0;
+    ctx->partitioned = false;
+    cudaFree(keep);
+  }
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpy(out, dump, cols * ctx->n * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(ctx, DPMM_ECUDA, std::string("cudaMemcpy(dump): ") + cudaGetErrorString(e));
+  }
+  cudaFree(dump);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// timing hooks
+// ------------------------------------------------------------------------------------------------
+extern "C" int dpmm_timing_kinds(void) { return TK_COUNT; }
+extern "C" const char* dpmm_timing_name(int32_t kind) { return (kind >= 0 && kind < TK_COUNT) ? kTimingNames[kind] : ""; }
+extern "C" int64_t dpmm_launch_count(const dpmm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static void drain_timers(dpmm_ctx* ctx) {
+  for (auto& t : ctx->tev) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) ctx->t_ms[t.kind] += ms;
+    ctx->ev_pool.push_back(t.a);
+    ctx->ev_pool.push_back(t.b);
+  }
+  ctx->tev.clear();
+}
+
+extern "C" int dpmm_timing_enable(dpmm_ctx* ctx, int32_t on) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  drain_timers(ctx);
+  ctx->timing = on != 0;
+  return 0;
+}
+
+extern "C" int dpmm_timing_read(dpmm_ctx* ctx, double* ms, int64_t* launches, int32_t reset) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  drain_timers(ctx);
+  for (int k = 0; k < TK_COUNT; ++k) {
+    if (ms) ms[k] = ctx->t_ms[k];
+    if (launches) launches[k] = ctx->t_n[k];
+    if (reset) {
+      ctx->t_ms[k] = 0;
+      ctx->t_n[k] = 0;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL (resolved at run time so that single-GPU users need no NCCL at all)
+// ------------------------------------------------------------------------------------------------
+static int load_nccl(dpmm_ctx* ctx, NcclApi& api) {
+  if (api.handle) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) return fail(ctx, DPMM_ENCCL, std::string("dlopen(libnccl.so.2) failed: ") + dlerror());
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+  api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy || !api.GetErrorString)
+    return fail(ctx, DPMM_ENCCL, "libnccl is missing a required symbol");
+  return 0;
+}
+
+extern "C" int dpmm_nccl_unique_id(void* out128) {
+  dpmm_ctx* ctx = nullptr;
+  NEED(out128, DPMM_EINVAL, "out128 is NULL");
+  static NcclApi api;
+  int rc = load_nccl(nullptr, api);
+  if (rc) return rc;
+  const int r = api.GetUniqueId(out128);
+  if (r != 0) return fail(nullptr, DPMM_ENCCL, std::string("ncclGetUniqueId: ") + api.GetErrorString(r));
+  return 0;
+}
+
+extern "C" int dpmm_comm_init(dpmm_ctx* ctx, const void* unique_id128, int32_t rank, int32_t world_size) {
+  NEED(ctx && unique_id128, DPMM_EINVAL, "NULL argument");
+  NEED(world_size >= 1 && rank >= 0 && rank < world_size, DPMM_EINVAL, "bad rank / world size");
+  CK(cudaSetDevice(ctx->device));
+  int rc = load_nccl(ctx, ctx->nccl);
+  if (rc) return rc;
+  UidBlob id;
+  memcpy(id.b, unique_id128, 128);
+  const int r = ctx->nccl.CommInitRank(&ctx->comm, world_size, id, rank);
+  if (r != 0) return fail(ctx, DPMM_ENCCL, std::string("ncclCommInitRank: ") + ctx->nccl.GetErrorString(r));
+  ctx->world = world_size;
+  ctx->rank = rank;
+  return 0;
+}

@@ -1,0 +1,316 @@
+// Stage 3: segmented sufficient statistics.
+//
+//   create_suff_stats_dict_worker            src/local_clusters_actions.jl:149-169
+//   create_sufficient_statistics (NIW)       src/priors/niw.jl:42-51      N, sum x, S = X X' (Float64)
+//   create_sufficient_statistics (multinom.) src/priors/multinomial_prior.jl:27-32   N, sum x
+//   aggregate_suff_stats                     niw.jl:64-66, multinomial_prior.jl:41-43
+//
+// The reference masks + gathers + widens the points of every cluster three times (cluster, left,
+// right) and runs three DGEMMs.  Here the points are already bucketed by (label, side) in `perm2`
+// (kernels_gauss.cuh: sublabel_partition), so each work item is a run of points with ONE key; the
+// rank-1 updates are accumulated per key for left and right only (cluster = left + right in the
+// finalise kernel), upper-triangular blocks only, in Float32 registers over <= `chunk` points and
+// then added in Float64 (atomicAdd(double)) to the per-key accumulator, which is what crosses NVLink.
+#pragma once
+#include "common.cuh"
+
+struct StatsItem {
+  int32_t key;    // 2*k + side
+  int32_t begin;  // range in perm2
+  int32_t end;
+};
+
+// Builds the work list: for every wanted cluster k, its left run [seg_off[k], lr_cursor[2k]) and
+// right run [lr_cursor[2k], seg_off[k+1]) cut into chunks of `chunk` points.  Single CTA.
+__global__ void stats_worklist_kernel(const int32_t* __restrict__ seg_off, const int32_t* __restrict__ lr_cursor,
+                                      const uint8_t* __restrict__ wanted, int K, int chunk, StatsItem* items,
+                                      int32_t* n_items, int32_t* next_item) {
+  extern __shared__ int sc[];  // [2K] chunk counts -> exclusive offsets
+  const int tid = threadIdx.x;
+  for (int key = tid; key < 2 * K; key += blockDim.x) {
+    const int k = key >> 1;
+    int len = 0;
+    if (wanted == nullptr || wanted[k]) {
+      const int mid = lr_cursor[2 * k];
+      len = (key & 1) ? seg_off[k + 1] - mid : mid - seg_off[k];
+    }
+    sc[key] = (len + chunk - 1) / chunk;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int key = 0; key < 2 * K; ++key) {
+      const int c = sc[key];
+      sc[key] = run;
+      run += c;
+    }
+    *n_items = run;
+    *next_item = 0;
+  }
+  __syncthreads();
+  for (int key = tid; key < 2 * K; key += blockDim.x) {
+    const int k = key >> 1;
+    if (wanted != nullptr && !wanted[k]) continue;
+    const int mid = lr_cursor[2 * k];
+    const int b = (key & 1) ? mid : seg_off[k];
+    const int e = (key & 1) ? seg_off[k + 1] : mid;
+    int o = sc[key];
+    for (int s = b; s < e; s += chunk) items[o++] = StatsItem{key, s, min(e, s + chunk)};
+  }
+}
+
+// Transposed warp reduction: on entry every lane holds EP partial sums v[0..EP); on exit lane l
+// holds in v[0..EP/32) the warp totals of entries  e = (bits of l, MSB first) * (EP/2, EP/4, ...) + j.
+// 2*(EP - EP/32) selects + (EP - EP/32) shuffles instead of 5*EP shuffles.
+template <int EP>
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[EP], int lane) {
+  static_assert(EP % 32 == 0, "EP must be a multiple of 32");
+  int h = EP / 2;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int off = 16 >> s;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int e = 0; e < EP / 2; ++e) {
+      if (e < h) {
+        const float send = up ? v[e] : v[e + h];
+        const float keep = up ? v[e + h] : v[e];
+        v[e] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    h >>= 1;
+  }
+}
+// entry index owned by `lane` in slot j after warp_transpose_reduce<EP>
+template <int EP>
+__device__ __forceinline__ int warp_transpose_entry(int lane, int j) {
+  int e = j, h = EP / 2;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    if (lane & (16 >> s)) e += h;
+    h >>= 1;
+  }
+  return e;
+}
+
+template <int D>
+struct StatsCfg {
+  static constexpr int BS = (D <= 8) ? D : 8;            // register block edge
+  static constexpr int NB = (D + BS - 1) / BS;           // blocks per matrix edge
+  static constexpr int NU = NB * (NB + 1) / 2;           // upper-triangular blocks = warps per slice
+  static constexpr int DPAD = NB * BS;
+  static constexpr bool VEC = (BS % 4 == 0);
+  static constexpr int DS = VEC ? 4 * ((DPAD / 4) | 1) : ((DPAD & 1) ? DPAD : DPAD + 1);
+  static constexpr int E = BS * BS;
+  static constexpr int EP = (E + 31) / 32 * 32;
+  static constexpr int G = (NU + 15) / 16;               // block groups: a CTA covers NU/G blocks (<= 16 warps)
+  static constexpr int WPG = (NU + G - 1) / G;           // warps (= blocks) per group
+  static constexpr int NS = (WPG >= 8) ? 1 : (8 / WPG);  // point slices so that a CTA has ~8+ warps
+  static constexpr int WARPS = WPG * NS;
+  static constexpr int R = (NS >= 8) ? 2 : 4;            // points per lane per tile
+  static constexpr int TPTS = 32 * NS * R;               // points per shared-memory tile
+};
+
+struct StatsArgs {
+  const float* x;
+  int D;                    // runtime D (== template D for NIW)
+  const int32_t* perm2;
+  const StatsItem* items;
+  const int32_t* n_items;
+  int32_t* next_item;
+  double* acc;              // [2K][rec]  rec = 1 + D + D*D (NIW) or 1 + D (multinomial); count slot unused here
+  int rec;
+};
+
+// K5: NIW.  Warp w of a CTA owns upper block u = g*WPG + w % WPG of S (g = block group of the work
+// unit; G > 1 only when S has more than 16 upper blocks, i.e. D > 40) and point slice w / WPG; lane l
+// owns the points l, l+32, ... of its slice, so the warp's 32 lanes read 32 different staged points
+// at the same column offset (conflict-free LDS.128) and the 32 partial blocks are combined once per
+// item.
+template <int D>
+__global__ void __launch_bounds__(StatsCfg<D>::WARPS * 32, 1)
+niw_stats_kernel(const StatsArgs a) {
+  using C = StatsCfg<D>;
+  constexpr int BS = C::BS;
+  __shared__ __align__(16) float xs[C::TPTS * C::DS];
+  __shared__ int32_t sidx[C::TPTS];
+  __shared__ int s_item;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slice = warp / C::WPG;
+  for (int e = tid; e < C::TPTS * C::DS; e += blockDim.x) xs[e] = 0.f;  // zero padding columns once
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(a.next_item, 1);
+    __syncthreads();
+    const int it = s_item;
+    if (it >= *a.n_items * C::G) break;
+    const StatsItem item = a.items[it / C::G];
+    const int u = (it % C::G) * C::WPG + warp % C::WPG;
+    const bool live = u < C::NU;
+    int bi = 0, bj = 0;
+    if (live) {
+      int r = u;
+      while (r >= C::NB - bi) {
+        r -= C::NB - bi;
+        ++bi;
+      }
+      bj = bi + r;
+    }
+    const bool diag = live && (bi == bj);
+    float acc[C::EP];
+    float sx[BS];
+#pragma unroll
+    for (int e = 0; e < C::EP; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int e = 0; e < BS; ++e) sx[e] = 0.f;
+
+    for (int t0 = item.begin; t0 < item.end; t0 += C::TPTS) {
+      const int tn = min(C::TPTS, item.end - t0);
+      __syncthreads();
+      for (int p = tid; p < C::TPTS; p += blockDim.x) sidx[p] = (p < tn) ? a.perm2[t0 + p] : -1;
+      __syncthreads();
+      if constexpr (D % 4 == 0) {
+        for (int e = tid; e < C::TPTS * (D / 4); e += blockDim.x) {
+          const int p = e / (D / 4), c = e - p * (D / 4);
+          const int idx = sidx[p];
+          const float4 v = (idx >= 0) ? __ldg(reinterpret_cast<const float4*>(a.x + (size_t)idx * D) + c)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(xs + p * C::DS + 4 * c) = v;
+        }
+      } else {
+        for (int e = tid; e < C::TPTS * D; e += blockDim.x) {
+          const int p = e / D, c = e - p * D;
+          const int idx = sidx[p];
+          xs[p * C::DS + c] = (idx >= 0) ? __ldg(a.x + (size_t)idx * D + c) : 0.f;
+        }
+      }
+      __syncthreads();
+      if (live)
+#pragma unroll
+      for (int r = 0; r < C::R; ++r) {
+        const float* row = xs + (slice * 32 * C::R + r * 32 + lane) * C::DS;
+        float xi[BS], xj[BS];
+        if constexpr (C::VEC) {
+#pragma unroll
+          for (int q4 = 0; q4 < BS / 4; ++q4) {
+            const float4 vi = *reinterpret_cast<const float4*>(row + bi * BS + 4 * q4);
+            const float4 vj = *reinterpret_cast<const float4*>(row + bj * BS + 4 * q4);
+            xi[4 * q4] = vi.x; xi[4 * q4 + 1] = vi.y; xi[4 * q4 + 2] = vi.z; xi[4 * q4 + 3] = vi.w;
+            xj[4 * q4] = vj.x; xj[4 * q4 + 1] = vj.y; xj[4 * q4 + 2] = vj.z; xj[4 * q4 + 3] = vj.w;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < BS; ++q) {
+            xi[q] = row[bi * BS + q];
+            xj[q] = row[bj * BS + q];
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < BS; ++p)
+#pragma unroll
+          for (int q = 0; q < BS; ++q) acc[p * BS + q] = fmaf(xi[p], xj[q], acc[p * BS + q]);
+        if (diag) {
+#pragma unroll
+          for (int p = 0; p < BS; ++p) sx[p] += xi[p];
+        }
+      }
+    }
+    // ---- combine the 32 lanes and add to the key's Float64 accumulator ----
+    if (!live) continue;
+    warp_transpose_reduce<C::EP>(acc, lane);
+    double* dst = a.acc + (size_t)item.key * a.rec;
+#pragma unroll
+    for (int j = 0; j < C::EP / 32; ++j) {
+      const int e = warp_transpose_entry<C::EP>(lane, j);
+      if (e < C::E) {
+        const int gi = bi * BS + e / BS, gj = bj * BS + e % BS;
+        if (gi < D && gj < D && gi <= gj) atomicAdd(dst + 1 + D + (size_t)gi * D + gj, (double)acc[j]);
+      }
+    }
+    if (diag) {
+#pragma unroll
+      for (int p = 0; p < BS; ++p) {
+        float v = sx[p];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == p && bi * BS + p < D) atomicAdd(dst + 1 + bi * BS + p, (double)v);
+      }
+    }
+  }
+}
+
+// K6: multinomial.  sum x per key; thread = (feature d, point slice).
+#define MNM_STATS_TPTS 64
+__global__ void mnm_stats_kernel(const StatsArgs a) {
+  extern __shared__ __align__(16) float xsm[];  // [TPTS][DS]
+  __shared__ int32_t sidx[MNM_STATS_TPTS];
+  __shared__ int s_item;
+  const int D = a.D;
+  const int DS = D | 1;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int DPAD = (D + 31) & ~31;
+  const int NSL = T / DPAD;  // point slices (host guarantees >= 1)
+  const int d = tid % DPAD, sl = tid / DPAD;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(a.next_item, 1);
+    __syncthreads();
+    const int it = s_item;
+    if (it >= *a.n_items) break;
+    const StatsItem item = a.items[it];
+    float s = 0.f;
+    for (int t0 = item.begin; t0 < item.end; t0 += MNM_STATS_TPTS) {
+      const int tn = min(MNM_STATS_TPTS, item.end - t0);
+      __syncthreads();
+      for (int p = tid; p < MNM_STATS_TPTS; p += T) sidx[p] = (p < tn) ? a.perm2[t0 + p] : -1;
+      __syncthreads();
+      for (int e = tid; e < MNM_STATS_TPTS * D; e += T) {
+        const int p = e / D, c = e - p * D;
+        const int idx = sidx[p];
+        xsm[p * DS + c] = (idx >= 0) ? __ldg(a.x + (size_t)idx * D + c) : 0.f;
+      }
+      __syncthreads();
+      if (d < D && sl < NSL)
+        for (int p = sl; p < tn; p += NSL) s += xsm[p * DS + d];
+    }
+    if (d < D && sl < NSL && s != 0.f) atomicAdd(a.acc + (size_t)item.key * a.rec + 1 + d, (double)s);
+  }
+}
+
+// K8: finalise + pack.  out[m][3][rec] for the m requested clusters: cluster = left + right, S
+// mirrored from its upper triangle, counts from the partition cursors.
+__global__ void stats_finalize_kernel(const double* __restrict__ acc, const int32_t* __restrict__ seg_off,
+                                      const int32_t* __restrict__ lr_cursor, const int32_t* __restrict__ idx_list,
+                                      int m, int D, int rec, int niw, double* out) {
+  const int a = blockIdx.y;
+  if (a >= m) return;
+  const int k = idx_list[a];
+  const double* L = acc + (size_t)(2 * k) * rec;
+  const double* R = acc + (size_t)(2 * k + 1) * rec;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < rec; e += gridDim.x * blockDim.x) {
+    double l, r;
+    if (e == 0) {
+      const int mid = lr_cursor[2 * k];
+      l = (double)(mid - seg_off[k]);
+      r = (double)(seg_off[k + 1] - mid);
+    } else if (e <= D || !niw) {
+      l = L[e];
+      r = R[e];
+    } else {
+      const int q = e - 1 - D;
+      int i = q / D, j = q - i * D;
+      if (i > j) {
+        const int t = i;
+        i = j;
+        j = t;
+      }
+      l = L[1 + D + (size_t)i * D + j];
+      r = R[1 + D + (size_t)i * D + j];
+    }
+    double* o = out + (size_t)a * 3 * rec;
+    o[e] = l + r;
+    o[rec + e] = l;
+    o[2 * rec + e] = r;
+  }
+}

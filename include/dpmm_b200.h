@@ -1,0 +1,159 @@
+/*
+ * dpmm_b200.h -- C ABI of libdpmm_b200.so: the B200 (sm_100a) data-parallel sweep of the
+ * DPMM sub-cluster sampler.
+ *
+ * This library replaces the WORKER side of DPMMSubClusters.jl (v0.1.13): everything the master
+ * reaches through Distributed.@spawnat / remotecall in src/local_clusters_actions.jl.  The host
+ * (Julia, or the Python mirror shipped in this repo) keeps fit()/dp_parallel(), the prior plugin
+ * types, calc_posterior, parameter sampling and the Hastings ratios.  Every entry point below names
+ * the reference call site it replaces (file:line under the reference tree).
+ *
+ * Conventions
+ *   - plain C, no exceptions; every call returns 0 on success or a negative DPMM_E* code, and
+ *     dpmm_last_error(ctx) returns a human-readable message (ctx may be NULL for create failures).
+ *   - one context = one GPU = one shard of the points (one "worker" of the reference); one host
+ *     thread per context; calls are enqueued on the context's CUDA stream in call order (the
+ *     reference relies on per-worker FIFO order of @spawnat tasks, local_clusters_actions.jl:64-68,
+ *     102-109 -- a stream gives the same semantics).  Calls that return data synchronise.
+ *   - labels and sub-labels cross the boundary as 1-based int64 (Julia Int64, ds.jl:54-55);
+ *     cluster indices in index lists are 1-based int64 as well.
+ *   - points are float32, D x N column-major (each point = D contiguous floats, ds.jl:53).
+ *   - host buffers are borrowed for the duration of the call only (x is copied at create).
+ *   - there is NO CPU fallback: without a CUDA device every call fails with DPMM_ECUDA.
+ */
+#ifndef DPMM_B200_H
+#define DPMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPMM_OK 0
+#define DPMM_EINVAL (-1)   /* bad argument                                   */
+#define DPMM_ECUDA (-2)    /* CUDA runtime error / no device                 */
+#define DPMM_ESTATE (-3)   /* call order violated (e.g. sampling before set_params) */
+#define DPMM_ELIMIT (-4)   /* size outside the supported range (see dpmm_limits)    */
+#define DPMM_ENCCL (-5)    /* NCCL error                                      */
+
+#define DPMM_PRIOR_NIW 0          /* niw_hyperparams   -> mv_gaussian       (src/priors/niw.jl)               */
+#define DPMM_PRIOR_MULTINOMIAL 1  /* multinomial_hyper -> multinomial_dist  (src/priors/multinomial_prior.jl) */
+
+#define DPMM_SAMPLER_INVERSE_CDF 0 /* reference semantics: StatsBase.sample(ProbabilityWeights), utils.jl:29 */
+#define DPMM_SAMPLER_GUMBEL 1      /* Gumbel-max: same distribution, different stream, no per-point K storage */
+
+typedef struct dpmm_ctx dpmm_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* init_model_from_data: `data = distribute(all_data)` (src/dp-parallel-sampling.jl:42-44) for ONE
+ * shard.  x: host float32 [d x n_local] column-major, copied to the device.  global_offset = index
+ * (0-based) of this shard's first point in the whole data set: the counter-based RNG is keyed by the
+ * global point index so results do not depend on how many GPUs the points are spread over.
+ * device: CUDA ordinal.  seed: replaces `@everywhere Random.seed!(seed)` (:37-39). */
+int dpmm_create(dpmm_ctx** out, const float* x, int64_t n_local, int32_t d, int32_t prior_kind,
+                int32_t device, uint64_t seed, int64_t global_offset);
+int dpmm_destroy(dpmm_ctx* ctx);
+const char* dpmm_last_error(const dpmm_ctx* ctx);
+/* Use an externally owned cudaStream_t (e.g. the host framework's current stream) for all work. */
+int dpmm_set_stream(dpmm_ctx* ctx, void* cuda_stream);
+int dpmm_sync(dpmm_ctx* ctx);
+/* out[0]=max D (NIW), out[1]=max D (multinomial), out[2]=max K. */
+int dpmm_limits(int32_t* out3);
+
+/* ---- labels: initialisation, gather, resume ------------------------------------------------- */
+
+/* labels = rand(1:init_clusters, N) (+1 if outlier); sub-labels = rand(1:2, N)
+ * (src/dp-parallel-sampling.jl:49-50). */
+int dpmm_init_labels(dpmm_ctx* ctx, int32_t init_clusters, int32_t outlier);
+/* split_first_cluster_worker! (local_clusters_actions.jl:257-261) when indices==NULL: all
+ * sub-labels <- rand(1:2); reset_bad_clusters_worker! / rand_subclusters_labels! (:474-488)
+ * otherwise: only points whose label is listed. */
+int dpmm_randomize_sublabels(dpmm_ctx* ctx, const int64_t* indices, int32_t n_indices);
+/* Array(group.labels) / Array(group.labels_subcluster) (dp-parallel-sampling.jl:218,276,371;
+ * ds.jl:85-87).  out: host int64[n_local]. */
+int dpmm_get_labels(dpmm_ctx* ctx, int64_t* out);
+int dpmm_get_sublabels(dpmm_ctx* ctx, int64_t* out);
+/* distribute(group.labels) on resume (dp-parallel-sampling.jl:437-438). */
+int dpmm_set_labels(dpmm_ctx* ctx, const int64_t* labels);
+int dpmm_set_sublabels(dpmm_ctx* ctx, const int64_t* sublabels);
+
+/* ---- parameters ------------------------------------------------------------------------------ */
+
+/* broadcast_cluster_params -> set_global_data (local_clusters_actions.jl:518-549): ship the thin
+ * cluster parameters (ds.jl:29-34) and the mixture weights.  Distributions are ordered
+ * [cluster k][cluster_dist, l_dist, r_dist], i.e. 3*K of them.
+ *   mu        float32 [3K][D]        mv_gaussian.mu        (mv_gaussian.jl:13)
+ *   inv_sigma float32 [3K][D][D]     mv_gaussian.invSigma  (:15; symmetric, either major order)
+ *   logdet    float32 [3K]           mv_gaussian.logdetSigma (:16)
+ *   weights   float32 [K]            group.weights (ds.jl:57);  lr_weights float32 [K][2] (ds.jl:33)
+ * The library factors invSigma = U'U on the host in float64 (the reference carries the same factor
+ * in mv_gaussian.invChol, :17) and evaluates z'invSigma z as |U z|^2. */
+int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t k, const float* mu, const float* inv_sigma,
+                        const float* logdet, const float* weights, const float* lr_weights);
+/* log_p float32 [3K][D] = multinomial_dist.alpha (log-probabilities, multinomial_dist.jl:8-10). */
+int dpmm_set_params_multinomial(dpmm_ctx* ctx, int32_t k, const float* log_p, const float* weights,
+                                const float* lr_weights);
+int dpmm_set_sampler(dpmm_ctx* ctx, int32_t sampler);
+
+/* ---- the sweep ------------------------------------------------------------------------------- */
+
+/* sample_labels! -> sample_labels_worker! (local_clusters_actions.jl:98-134): per point
+ * log-likelihood under every cluster_dist + log weight, then (final != 0) first-argmax or
+ * sample_log_cat_array! (utils.jl:19-31).  The N x K matrix is never written to memory. */
+int dpmm_sample_labels(dpmm_ctx* ctx, int32_t final_iter);
+/* sample_sub_clusters! -> sample_sub_clusters_worker! -> create_subclusters_labels! (:64-95):
+ * each point, under the l/r distributions of its (fresh) label. */
+int dpmm_sample_sublabels(dpmm_ctx* ctx);
+/* update_suff_stats_posterior! -> create_suff_stats_dict_worker (:149-169, :206-254) with
+ * create_sufficient_statistics (niw.jl:42-51, multinomial_prior.jl:27-32) and the worker->leader->
+ * master aggregate_suff_stats reduction (niw.jl:64-66, :171-203, :246-248), which becomes one NCCL
+ * all-reduce when a communicator is attached.
+ * indices: 1-based cluster indices (NULL = all K clusters, n_indices ignored).  Outputs (host, may
+ * each be NULL; if all are NULL the statistics are left on the device and the call does not
+ * synchronise), m = number of indices:
+ *   counts  int64  [m][3]            N of {cluster, left, right}
+ *   sum_x   double [m][3][D]         points_sum
+ *   sum_xx  double [m][3][D][D]      S (symmetric; NIW only, ignored for multinomial) */
+int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_indices, int64_t* counts,
+                    double* sum_x, double* sum_xx);
+
+/* ---- relabelling after split / merge / compaction ------------------------------------------- */
+
+/* split_cluster_local_worker! (local_clusters_actions.jl:265-278). */
+int dpmm_apply_split(dpmm_ctx* ctx, const int64_t* indices, const int64_t* new_indices, int32_t n);
+/* merge_clusters_worker! (:293-304). */
+int dpmm_apply_merge(dpmm_ctx* ctx, const int64_t* indices, const int64_t* new_indices, int32_t n);
+/* remove_empty_clusters_worker! (:446-455); pts_count[k] as the host holds it. */
+int dpmm_remove_empty(dpmm_ctx* ctx, const int64_t* pts_count, int32_t k);
+
+/* ---- multi-GPU (one process per GPU) --------------------------------------------------------- */
+
+/* 128-byte ncclUniqueId, created on rank 0 and shipped to the other ranks by the host's own means. */
+int dpmm_nccl_unique_id(void* out128);
+int dpmm_comm_init(dpmm_ctx* ctx, const void* unique_id128, int32_t rank, int32_t world_size);
+
+/* ---- parity / measurement hooks -------------------------------------------------------------- */
+
+/* Inject randomness (host arrays of length n_local, or NULL to return to Philox):
+ * u_label / u_sub: the one uniform each point consumes in the label / sub-label draw;
+ * r_bits: the rand(1:2)-1 bit used by randomize_sublabels / apply_split. */
+int dpmm_set_uniforms(dpmm_ctx* ctx, const double* u_label, const double* u_sub, const uint8_t* r_bits);
+/* which=0: out float32 [n_local x K] column-major = parr of sample_labels_worker! (:120-127);
+ * which=1: out float32 [n_local x 2] = the l/r matrix of create_subclusters_labels! (:89-93) under
+ * each point's current label. */
+int dpmm_debug_loglik(dpmm_ctx* ctx, int32_t which, float* out);
+/* Per-kernel device timing (CUDA events around every launch) for roofline reporting. */
+int dpmm_timing_enable(dpmm_ctx* ctx, int32_t on);
+int dpmm_timing_kinds(void);
+const char* dpmm_timing_name(int32_t kind);
+/* Synchronises; ms[kind] = summed device time, launches[kind] = count since enable/reset. */
+int dpmm_timing_read(dpmm_ctx* ctx, double* ms, int64_t* launches, int32_t reset);
+/* Number of kernels this context has launched since creation. */
+int64_t dpmm_launch_count(const dpmm_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPMM_B200_H */

@@ -1,0 +1,245 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+the CPU oracle on the same seeded inputs and the same injected uniforms.
+
+Bars (north_star / SURVEY.md 8c): labels, sub-labels and counts bit-exact except documented near-ties;
+log-likelihoods within 1e-4 relative; sum x / sum xx' within 1e-4 (relative to sqrt(S_ii S_jj));
+multinomial count vectors exact; relabelling exact."""
+import os
+
+import numpy as np
+import pytest
+
+import dpmm_pkg
+from oracle import dpmm_oracle as O
+from tests.util import (check_draws, check_loglik, check_stats, compare_sweeps, make_mnm_case, make_niw_case,
+                        set_params, tie_tolerance)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as g
+    g.build()
+    return dpmm_pkg.load()
+
+
+NIW_CASES = [  # (D, K, n)
+    (2, 6, 10000),     # config C1
+    (1, 3, 1000), (3, 10, 5000), (4, 2, 777), (5, 7, 4099), (6, 3, 1500), (7, 3, 1500), (8, 9, 3000),
+    (12, 4, 2048), (16, 5, 4000), (24, 3, 2000),
+    (32, 20, 20000),   # config C2 shape
+    (48, 3, 1500),
+    (64, 12, 3000),    # config C5 shape
+    (32, 1, 5000), (5, 50, 8000),   # K = 1; config C4 shape
+    (32, 100, 3000),   # K large enough that the staged clusters are chunked
+]
+
+
+@pytest.mark.parametrize("D,K,n", NIW_CASES)
+def test_niw_full_sweep_parity(pkg, D, K, n):
+    case = make_niw_case(D, K, n, seed=100 + D + K)
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=7)
+    o = O.OracleSweep(case["x"], O.NIW, seed=7)
+    rep = compare_sweeps(g, o, case, np.random.default_rng(D * 1000 + K))
+    g.close()
+    print(f"D={D} K={K} n={n}: {rep}")
+
+
+@pytest.mark.parametrize("D,K,n", [(2, 6, 5000), (32, 20, 10000), (64, 4, 2000)])
+def test_niw_final_argmax_parity(pkg, D, K, n):
+    case = make_niw_case(D, K, n, seed=5)
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=7)
+    o = O.OracleSweep(case["x"], O.NIW, seed=7)
+    compare_sweeps(g, o, case, np.random.default_rng(1), final=True)
+    g.close()
+
+
+MNM_CASES = [(100, 20, 20000), (100, 2, 1000), (10, 5, 3000), (33, 17, 2500), (257, 3, 600), (7, 40, 4000)]
+
+
+@pytest.mark.parametrize("D,K,n", MNM_CASES)
+def test_multinomial_full_sweep_parity(pkg, D, K, n):
+    case = make_mnm_case(D, K, n, seed=200 + D)
+    g = pkg.GpuSweep(case["x"], pkg.MULTINOMIAL, seed=9)
+    o = O.OracleSweep(case["x"], O.MULTINOMIAL, seed=9)
+    rep = compare_sweeps(g, o, case, np.random.default_rng(D))
+    g.close()
+    print(f"mnm D={D} K={K} n={n}: {rep}")
+
+
+def test_multinomial_final_argmax(pkg):
+    case = make_mnm_case(100, 20, 5000, seed=4)
+    g = pkg.GpuSweep(case["x"], pkg.MULTINOMIAL, seed=9)
+    o = O.OracleSweep(case["x"], O.MULTINOMIAL, seed=9)
+    compare_sweeps(g, o, case, np.random.default_rng(2), final=True)
+    g.close()
+
+
+def test_philox_streams_match_oracle(pkg):
+    """Without injected uniforms both sides draw from Philox keyed by the global point index, so a
+    whole sweep agrees (up to near-ties) and sharding does not change the stream."""
+    case = make_niw_case(8, 5, 6000, seed=11)
+    off = 2 ** 32 - 1000                      # crosses into the second counter word
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=0xDEADBEEFCAFE, global_offset=off)
+    o = O.OracleSweep(case["x"], O.NIW, seed=0xDEADBEEFCAFE, global_offset=off)
+    for s in (g, o):
+        s.init_labels(3)
+    np.testing.assert_array_equal(g.get_labels(), o.get_labels())
+    np.testing.assert_array_equal(g.get_sublabels(), o.get_sublabels())
+    assert set(np.unique(g.get_labels())) == {1, 2, 3}
+    for s in (g, o):
+        set_params(s, case)
+        s.sample_labels(False)
+    u = O.philox_uniform(0xDEADBEEFCAFE, O.STREAM_LABEL, o.call, o.gidx)
+    check_draws(o.debug_loglik(0), u, g.get_labels(), o.get_labels(), "philox labels")
+    o.set_labels(g.get_labels())
+    for s in (g, o):
+        s.sample_sublabels()
+    u = O.philox_uniform(0xDEADBEEFCAFE, O.STREAM_SUBLABEL, o.call, o.gidx)
+    check_draws(o.debug_loglik(1), u, g.get_sublabels(), o.get_sublabels(), "philox sub-labels")
+    for s in (g, o):
+        s.randomize_sublabels([2, 4])
+    o.set_sublabels(np.where(np.isin(o.get_labels(), [2, 4]), o.get_sublabels(), g.get_sublabels()))
+    np.testing.assert_array_equal(g.get_sublabels(), o.get_sublabels())
+    g.close()
+
+
+def test_golden_niw_checkpoint_through_cabi(pkg, golden_dir):
+    """Stage 3 against the statistics stored in the reference's own checkpoint__50.jld2."""
+    gd = np.load(os.path.join(golden_dir, "niw_2d1k_checkpoint50.npz"))
+    g = pkg.GpuSweep(gd["x"].astype(np.float32), pkg.NIW)
+    g.set_labels(gd["labels"]); g.set_sublabels(gd["sublabels"])
+    g.K = 5
+    got = g.suff_stats()
+    check_stats(got, (gd["counts"], gd["sum_x"], gd["sum_xx"]), O.NIW, "golden NIW checkpoint")
+    g.close()
+
+
+def test_golden_multinomial_checkpoint_bytes_through_cabi(pkg, golden_dir):
+    gd = np.load(os.path.join(golden_dir, "mnm_1k_checkpoint20.npz"))
+    g = pkg.GpuSweep(gd["x"], pkg.MULTINOMIAL)
+    g.set_labels(gd["labels"]); g.set_sublabels(gd["sublabels"])
+    g.K = 2
+    counts, sum_x, _ = g.suff_stats()
+    np.testing.assert_array_equal(counts, gd["counts"])
+    assert sum_x.astype(np.float32).tobytes() == gd["sum_x"].tobytes()   # byte-exact with the reference's Float32
+    g.close()
+
+
+def test_edge_cases(pkg):
+    rng = np.random.default_rng(0)
+    # a single point
+    case = make_niw_case(3, 2, 1, seed=1)
+    g = pkg.GpuSweep(case["x"], pkg.NIW); o = O.OracleSweep(case["x"], O.NIW)
+    compare_sweeps(g, o, case, rng); g.close()
+    # empty clusters (K larger than the labels in use) and empty sides give zero statistics
+    case = make_niw_case(4, 6, 500, seed=2)
+    g = pkg.GpuSweep(case["x"], pkg.NIW); o = O.OracleSweep(case["x"], O.NIW)
+    lab = rng.integers(1, 3, 500); sub = np.ones(500, np.int64)
+    for s in (g, o):
+        set_params(s, case); s.set_labels(lab); s.set_sublabels(sub)
+    gs, os_ = g.suff_stats(), o.suff_stats()
+    check_stats(gs, os_, O.NIW, "empty clusters")
+    assert (gs[0][2:] == 0).all() and (gs[0][:, 2] == 0).all()
+    g.close()
+    # NaN / -Inf log-likelihoods: a non-PD invSigma gives NaN for that cluster -> treated as -Inf when
+    # sampling (utils.jl:21); all clusters NaN -> label 1
+    case = make_niw_case(2, 3, 400, seed=3)
+    case["inv_sigma"][1, 0] = np.array([[1, 2], [2, 1]], np.float32)   # indefinite
+    g = pkg.GpuSweep(case["x"], pkg.NIW)
+    set_params(g, case)
+    ll = g.debug_loglik(0)
+    assert np.isnan(ll[:, 1]).all() and np.isfinite(ll[:, [0, 2]]).all()
+    g.set_uniforms(rng.random(400), None, None)
+    g.sample_labels(False)
+    assert not (g.get_labels() == 2).any()
+    for k in range(3):
+        case["inv_sigma"][k, 0] = np.array([[1, 2], [2, 1]], np.float32)
+    set_params(g, case)
+    g.sample_labels(False)
+    assert (g.get_labels() == 1).all()
+    g.sample_labels(True)          # argmax branch: NaN is maximal, first index wins
+    assert (g.get_labels() == 1).all()
+    g.close()
+
+
+def test_error_behaviour(pkg):
+    E = pkg._lib
+    x = np.zeros((2, 16), np.float32)
+    g = pkg.GpuSweep(x, pkg.NIW)
+    with pytest.raises(E.DpmmError) as ei:
+        g.sample_labels()
+    assert ei.value.code == E.ESTATE
+    with pytest.raises(E.DpmmError) as ei:
+        g.set_labels(np.zeros(16, np.int64))          # labels are 1-based
+    assert ei.value.code == E.EINVAL
+    with pytest.raises(E.DpmmError) as ei:
+        g.set_params_multinomial(np.zeros((1, 3, 2), np.float32), np.ones(1, np.float32), np.ones(2, np.float32))
+    assert ei.value.code == E.ESTATE
+    g.close()
+    with pytest.raises(E.DpmmError) as ei:
+        pkg.GpuSweep(np.zeros((9, 4), np.float32), pkg.NIW)     # D=9 is not an instantiated width
+    assert ei.value.code == E.ELIMIT
+
+
+def test_gumbel_sampler_is_statistically_equivalent(pkg):
+    case = make_niw_case(2, 4, 200000, seed=21, spread=0.8)
+    case["x"][:] = case["x"][:, :1]                    # every point identical -> one categorical law
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=3)
+    set_params(g, case)
+    ll = g.debug_loglik(0)[0].astype(np.float64)
+    p = np.exp(ll - ll.max()); p /= p.sum()
+    freqs = []
+    for sampler in (pkg._lib.SAMPLER_INVERSE_CDF, pkg._lib.SAMPLER_GUMBEL):
+        g.set_sampler(sampler)
+        g.sample_labels(False)
+        freqs.append(np.bincount(g.get_labels(), minlength=5)[1:] / case["n"])
+    g.close()
+    for f in freqs:
+        np.testing.assert_allclose(f, p, atol=5e-3)
+
+
+def test_full_size_properties_c2(pkg):
+    """BASELINE config C2 shape (N=1e6, D=32, K=20): size-independent properties + oracle parity on a
+    random sub-sample of points (the draw of a point depends only on that point and the parameters)."""
+    n, D, K = 1_000_000, 32, 20
+    case = make_niw_case(D, K, n, seed=77)
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=123)
+    set_params(g, case)
+    g.sample_labels(False); g.sample_sublabels()
+    lab, sub = g.get_labels(), g.get_sublabels()
+    counts, sx, sxx = g.suff_stats()
+    assert lab.min() >= 1 and lab.max() <= K and set(np.unique(sub)) <= {1, 2}
+    np.testing.assert_array_equal(counts[:, 0], np.bincount(lab, minlength=K + 1)[1:])
+    np.testing.assert_array_equal(counts[:, 1], np.bincount(lab[sub == 1], minlength=K + 1)[1:])
+    np.testing.assert_array_equal(counts[:, 0], counts[:, 1] + counts[:, 2])
+    np.testing.assert_allclose(sx[:, 0], sx[:, 1] + sx[:, 2], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(sxx[:, 0], sxx[:, 1] + sxx[:, 2], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(sx[:, 0].sum(0), case["x"].astype(np.float64).sum(1), rtol=1e-6)
+    tot = case["x"].astype(np.float64) @ case["x"].astype(np.float64).T
+    np.testing.assert_allclose(sxx[:, 0].sum(0), tot, rtol=1e-5, atol=1e-5 * np.abs(tot).max())
+    # oracle on a sub-sample with the same Philox draws
+    sel = np.sort(np.random.default_rng(0).choice(n, 20000, replace=False))
+    o = O.OracleSweep(case["x"][:, sel], O.NIW, seed=123)
+    o.gidx = sel.astype(np.uint64)
+    set_params(o, case)
+    o.sample_labels(False)
+    u = O.philox_uniform(123, O.STREAM_LABEL, 1, o.gidx)
+    check_draws(o.debug_loglik(0), u, lab[sel], o.get_labels(), "C2 labels (sub-sample)")
+    o.set_labels(lab[sel])
+    o.sample_sublabels()
+    u = O.philox_uniform(123, O.STREAM_SUBLABEL, 2, o.gidx)
+    check_draws(o.debug_loglik(1), u, sub[sel], o.get_sublabels(), "C2 sub-labels (sub-sample)")
+    # idempotence of the statistics and a relabel round trip at full size
+    c2, sx2, sxx2 = g.suff_stats()
+    np.testing.assert_array_equal(counts, c2)
+    np.testing.assert_allclose(sxx, sxx2, rtol=1e-6, atol=1e-6 * np.abs(sxx).max())
+    g.apply_split([1], [K + 1])
+    lab2 = g.get_labels()
+    np.testing.assert_array_equal(lab2 == K + 1, (lab == 1) & (sub == 2))
+    g.apply_merge([1], [K + 1])
+    np.testing.assert_array_equal(g.get_labels(), lab)
+    s2 = g.get_sublabels()
+    np.testing.assert_array_equal(s2[lab == 1], sub[lab == 1])      # former-1 points -> 1, former-(K+1) -> 2
+    g.close()
