@@ -108,6 +108,7 @@ struct dpmm_ctx {
   size_t hstage_bytes = 0;
 
   bool hist_valid = false, sorted = false, partitioned = false;
+  bool cursors_fresh = false;  // lr_cursor still holds the segment bounds (not yet consumed by a partition)
   int64_t launches = 0;
   bool timing = false;
   std::vector<TimedEvent> tev;
@@ -868,6 +869,7 @@ static int ensure_sorted(dpmm_ctx* ctx) {
   }
   ctx->sorted = true;
   ctx->partitioned = false;
+  ctx->cursors_fresh = true;
   return 0;
 }
 
@@ -875,7 +877,7 @@ static int ensure_sorted(dpmm_ctx* ctx) {
 static int run_sublabels(dpmm_ctx* ctx, bool sample, float* dump) {
   int rc = ensure_sorted(ctx);
   if (rc) return rc;
-  if (ctx->partitioned) {
+  if (!ctx->cursors_fresh) {
     // cursors were consumed by a previous partition of the same sort: rebuild them
     KernelTimer kt(ctx, TK_SORT);
     label_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hist, keff(ctx), ctx->seg_off, ctx->scat_cursor,
@@ -905,6 +907,7 @@ static int run_sublabels(dpmm_ctx* ctx, bool sample, float* dump) {
     CK(cudaGetLastError());
   }
   ctx->partitioned = true;
+  ctx->cursors_fresh = false;
   return 0;
 }
 
