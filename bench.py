@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- Gibbs iterations/sec of the data-parallel sweep (BASELINE.json metric).
+
+A "step" is one sweep of the hot path at a FROZEN converged parameter state:
+    [set_params] -> sample_labels -> sample_sublabels -> suff_stats (all clusters)
+i.e. group_step's worker side (src/local_clusters_actions.jl:660-663) without the host's parameter
+sampling.  Workload at N GPUs: BASELINE config C2 per GPU (NIW, N=1e6 points per GPU, D=32,
+K_true=20, generate_gaussian_data restated), one NCCL all-reduce of the packed statistics per step.
+
+  value  : device-timed (CUDA events) sweeps/s with X and the parameters resident in HBM
+  e2e    : the same step through the C ABI with HOST buffers (parameters H2D, statistics D2H every step)
+  --impl reference : the restated reference (NumPy/OpenBLAS oracle) on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (prior, N per GPU, D, K_true)
+    "c1": ("niw", 10_000, 2, 6),
+    "c2": ("niw", 1_000_000, 32, 20),
+    "c3": ("mnm", 1_000_000, 100, 20),
+    "c4": ("niw", 10_000_000, 5, 50),
+    "c5s": ("niw", 2_000_000, 64, 100),   # a 1/50 slice of C5 (N=1e8) per GPU
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def build_case(name, rank=0, seed=0):
+    """Synthetic data of the named config + a frozen, converged parameter state: posterior draws of
+    every cluster / sub-cluster given the ground-truth assignment (random halves as sub-clusters)."""
+    import dpmm_pkg
+    pkg = dpmm_pkg.load()
+    from dpmmsubclusters_jl_b200 import priors as P
+    from dpmmsubclusters_jl_b200.data_generators import (generate_gaussian_data, generate_gaussian_mixture,
+                                                         generate_mnmm_data)
+    prior, n, D, K = WORKLOADS[name]
+    alpha = 10.0
+    prng = np.random.default_rng(seed + 7)            # parameter draws: identical on every rank
+    if prior == "niw":
+        mix = generate_gaussian_mixture(D, K, 100.0, np.random.default_rng(seed))
+        x, z, _, _ = generate_gaussian_data(n, D, K, 100.0, np.random.default_rng(seed + 1000 + rank), mixture=mix)
+        z = z.astype(np.int64)
+        hyper = P.niw_hyperparams(1.0, np.zeros(D), D + 3, np.eye(D))    # fit() default, dp-parallel-sampling.jl:272-274
+        # parameters come from rank 0's shard so that every rank holds the same state
+        if rank != 0:
+            x0, z0, _, _ = generate_gaussian_data(n, D, K, 100.0, np.random.default_rng(seed + 1000), mixture=mix)
+            z0 = z0.astype(np.int64)
+        else:
+            x0, z0 = x, z
+    else:
+        x, z, _ = generate_mnmm_data(n, D, K, 50, np.random.default_rng(seed))
+        hyper = P.multinomial_hyper(np.ones(D, np.float32))
+        x0, z0 = x, z
+    keep = [k for k in range(1, K + 1) if (z0 == k).sum() >= 2]
+    Ke = len(keep)
+    srng = np.random.default_rng(seed + 99)
+    sub0 = srng.integers(1, 3, x0.shape[1])
+    dists, counts, lrw = [], [], []
+    for k in keep:
+        m = z0 == k
+        trip = []
+        for sel in (m, m & (sub0 == 1), m & (sub0 == 2)):
+            pts = x0[:, sel].astype(np.float64)
+            if prior == "niw":
+                ss = P.make_suff_stats(hyper, pts.shape[1], pts.sum(1), pts @ pts.T)
+            else:
+                ss = P.make_suff_stats(hyper, pts.shape[1], pts.sum(1))
+            trip.append(P.sample_distribution(P.calc_posterior(hyper, ss), prng))
+        dists.append(trip)
+        counts.append(m.sum())
+        lrw.append(prng.dirichlet([(m & (sub0 == 1)).sum() + alpha / 2, (m & (sub0 == 2)).sum() + alpha / 2]))
+    w = prng.dirichlet(np.array(counts + [alpha], np.float64))[:-1].astype(np.float32)
+    case = dict(K=Ke, D=D, n=x.shape[1], x=x, weights=w, lr_weights=np.asarray(lrw, np.float32), gt=z, name=name)
+    if prior == "niw":
+        case["kind"] = pkg.NIW
+        case["mu"] = np.array([[d.μ for d in t] for t in dists], np.float32)
+        case["inv_sigma"] = np.array([[d.invΣ for d in t] for t in dists], np.float32)
+        case["logdet"] = np.array([[d.logdetΣ for d in t] for t in dists], np.float32)
+    else:
+        case["kind"] = pkg.MULTINOMIAL
+        case["log_p"] = np.array([[d.α for d in t] for t in dists], np.float32)
+    return case
+
+
+def set_params(sw, case):
+    if "mu" in case:
+        sw.set_params_niw(case["mu"], case["inv_sigma"], case["logdet"], case["weights"], case["lr_weights"])
+    else:
+        sw.set_params_multinomial(case["log_p"], case["weights"], case["lr_weights"])
+
+
+def algorithmic_work(case):
+    """SURVEY.md 8d / BASELINE.md 3 per-unit figures x the units one launch processes."""
+    n, D, K = case["n"], case["D"], case["K"]
+    niw = "mu" in case
+    w = {}
+    if niw:
+        w["label_flops"] = n * K * (2 * D * D + 3 * D)           # every point x K clusters: matvec 2D^2, subtract+dot 3D
+        w["sublabel_flops"] = n * 2 * (2 * D * D + 3 * D)
+        w["stats_bytes"] = n * (4 * D + 5) + 2 * K * (1 + D + D * D) * 8
+    else:
+        w["label_flops"] = n * K * 2 * D
+        w["sublabel_flops"] = n * 2 * 2 * D
+        w["stats_bytes"] = n * (4 * D + 5) + 2 * K * (1 + D) * 8
+    w["label_bytes"] = n * (4 * D + 4)                           # read X once, write int32 label
+    w["sublabel_bytes"] = n * (4 * D + 4 + 4 + 1 + 4)            # gather X, perm, label, sub-label, perm2
+    return w
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, str(e)
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
+
+
+def run_reference(args):
+    """`--impl reference`: the restated reference on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_sweep
+    case = build_case(args.workload, 0, args.seed)
+    cores = os.cpu_count() or 1
+    workers = args.cpu_workers or cores
+    r = cpu_sweep.time_cpu_sweep(case["x"], case, workers, steps=max(args.steps, 1), warmup=max(args.warmup, 1),
+                                 target_step_s=args.cpu_step_s)
+    scale = case["n"] / r["n_sample"]
+    ms_step = float(np.mean(r["step_s"])) * 1e3
+    val = 1e3 / (ms_step * scale)
+    unit = "iters/s"
+    line = {"impl": "reference", "metric": "gibbs_iters_per_sec", "value": val, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step * scale, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(case, args, 1),
+            "cpu_baseline": {"value": val, "unit": unit, "cores": r["workers"], "kind": "port",
+                             "sample": f"{r['n_sample']} of {case['n']} points (strided), {args.steps} sweeps of "
+                                       f"{ms_step:.0f} ms, scaled linearly to N={case['n']}; restated reference "
+                                       f"(NumPy/OpenBLAS oracle), {r['workers']} worker processes x 1 BLAS thread; "
+                                       f"Julia is not installed"},
+            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(case, args, world):
+    prior, n, D, K = WORKLOADS[case["name"]]
+    return {"workload": f"{case['name'].upper()}: {'NIW Gaussian' if prior == 'niw' else 'multinomial'} N={n} points per GPU, "
+                        f"D={D}, K_true={K} (K={case['K']} non-empty), alpha=10, frozen converged parameters; "
+                        f"step = sample_labels + sample_sublabels + suff_stats(all)",
+            "n_points_per_gpu": n, "n_points_total": n * world, "D": D, "K": case["K"],
+            "generator": "generate_gaussian_data(N,D,K,100.0) restated" if prior == "niw" else "generate_mnmm_data(N,D,K,50) restated",
+            "sampler": "inverse-CDF (reference semantics)", "parallelism": f"points sharded over {world} GPU(s), 1 NCCL all-reduce/step" if world > 1 else "1 GPU",
+            "l2": f"inputs per step ({n * D * 4 / 1e6:.0f} MB X + labels) exceed the 126 MB L2; no explicit flush"
+                  if n * D * 4 > 126e6 else "inputs fit in L2: a 256 MB buffer is written between steps of the roofline pass"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-workers", type=int, default=0)
+    ap.add_argument("--cpu-step-s", type=float, default=1.5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import dpmm_pkg
+    import __graft_entry__ as ge
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        ge.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: this framework has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    pkg = dpmm_pkg.load()
+    args.steps = max(args.steps, 1)
+    args.warmup = max(args.warmup, 3)
+
+    case = build_case(args.workload, rank, args.seed)
+    t0 = time.perf_counter()
+    g = pkg.GpuSweep(case["x"], case["kind"], seed=args.seed + 1, global_offset=rank * case["n"], device=local)
+    g.sync()
+    x_upload_ms = (time.perf_counter() - t0) * 1e3
+    stream = torch.cuda.current_stream()
+    g.set_stream(stream.cuda_stream)
+    if world > 1:
+        ids = [pkg.GpuSweep.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        g.comm_init(ids[0], rank, world)
+    set_params(g, case)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sweep_device():
+        g.sample_labels(False)
+        g.sample_sublabels()
+        g.suff_stats(fetch=False)
+
+    def sweep_e2e():
+        set_params(g, case)
+        g.sample_labels(False)
+        g.sample_sublabels()
+        return g.suff_stats()
+
+    # ---- value: device-resident sweep, CUDA events on the launching stream ----
+    for _ in range(args.warmup):
+        sweep_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = g.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        sweep_device()
+    e1.record(stream)
+    barrier()
+    launches = g.launch_count() - l0
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.result()
+    ms_step = dev_ms / args.steps
+
+    # ---- e2e: host parameters in, host statistics out, every step ----
+    for _ in range(3):
+        sweep_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = sweep_e2e()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    K, D = case["K"], case["D"]
+    if "mu" in case:
+        h2d = 4 * (3 * K * (D + D * D + 1) + 3 * K)
+        d2h = 8 * 3 * K * (1 + D + D * D)
+    else:
+        h2d = 4 * (3 * K * D + 3 * K)
+        d2h = 8 * 3 * K * (1 + D)
+    assert int(out[0][:, 0].sum()) == case["n"] * world, "statistics do not cover every point"
+
+    # ---- per-kernel durations (CUDA events around every launch) for the roofline ----
+    flush = None
+    if case["n"] * D * 4 <= 126e6:
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    g.timing_enable(True)
+    nprof = min(args.steps, 50)
+    for _ in range(nprof):
+        if flush is not None:
+            flush.fill_(1)
+        sweep_device()
+    tim = g.timing_read()
+    g.timing_enable(False)
+    work = algorithmic_work(case)
+    pk = peaks()
+    tf32_peak = pk["bf16_tflops"] / 2.0
+    stages = {}
+    for name, (ms, cnt) in tim.items():
+        if cnt:
+            stages[name] = {"us_per_step": ms / nprof * 1e3, "launches_per_step": cnt / nprof}
+    lab_s = stages["label"]["us_per_step"] * 1e-6
+    stages["label"].update({"algorithmic_tflops": work["label_flops"] / lab_s / 1e12,
+                            "hbm_gbs": work["label_bytes"] / lab_s / 1e9})
+    st_s = stages["stats"]["us_per_step"] * 1e-6
+    stages["stats"].update({"bound": "hbm", "achieved_gbs": work["stats_bytes"] / st_s / 1e9,
+                            "frac": work["stats_bytes"] / st_s / 1e9 / pk["hbm_gbs"]})
+    sl_s = stages["sublabel"]["us_per_step"] * 1e-6
+    stages["sublabel"].update({"algorithmic_tflops": work["sublabel_flops"] / sl_s / 1e12,
+                               "hbm_gbs": work["sublabel_bytes"] / sl_s / 1e9})
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(case["name"], {}).get("label")
+    if "mu" in case:
+        roofline = {"kernel": "gauss_label_kernel (fused log-likelihood + label draw)", "bound": "tensor",
+                    "achieved": stages["label"]["algorithmic_tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": stages["label"]["algorithmic_tflops"] / tf32_peak, "traffic": traffic,
+                    "peak_source": f"TF32 dense = 1/2 x bf16 {pk['bf16_tflops']} TFLOP/s, {pk['source']}",
+                    "pipe": "fp32 FFMA (triangular |U z|^2, issues half the algorithmic flops)",
+                    "algorithmic_flops_per_launch": work["label_flops"]}
+    else:
+        roofline = {"kernel": "mnm_label_kernel (fused log-likelihood + label draw)", "bound": "hbm",
+                    "achieved": stages["label"]["hbm_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": stages["label"]["hbm_gbs"] / pk["hbm_gbs"], "traffic": traffic,
+                    "peak_source": pk["source"], "algorithmic_bytes_per_launch": work["label_bytes"]}
+
+    line = None
+    if rank == 0:
+        value = world * 1e3 / ms_step
+        line = {"metric": "gibbs_iters_per_sec", "value": value,
+                "unit": "iters/s (sweeps of 1e6-point shards per second, summed over GPUs)" if world > 1 else "iters/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(case, args, world),
+                "e2e": {"value": world * 1e3 / e2e_ms, "unit": "iters/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "note": "X stays resident across iterations as in fit(); its one-time upload is x_upload_ms"},
+                "x_upload_ms": x_upload_ms, "x_bytes": int(case["n"] * D * 4),
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages}
+    g.close()
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_sweep
+        cores = os.cpu_count() or 1
+        workers = args.cpu_workers or cores
+        r = cpu_sweep.time_cpu_sweep(case["x"], case, workers, steps=4, warmup=1, target_step_s=args.cpu_step_s)
+        scale = case["n"] / r["n_sample"]
+        cpu_ms = float(np.mean(r["step_s"])) * 1e3 * scale
+        line["cpu_baseline"] = {"value": 1e3 / cpu_ms, "unit": "iters/s", "cores": r["workers"], "kind": "port",
+                                "sample": f"{r['n_sample']} of {case['n']} points (strided), 4 sweeps, scaled linearly; "
+                                          f"restated reference (NumPy/OpenBLAS oracle), {r['workers']} worker processes "
+                                          f"x 1 BLAS thread, host has {cores} cores; Julia is not installed"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
