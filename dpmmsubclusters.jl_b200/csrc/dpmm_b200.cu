@@ -194,7 +194,7 @@ static int keff(const dpmm_ctx* c) { return std::max(std::max(c->K, c->label_bou
 static int nrec_floats(const dpmm_ctx* c) {
   if (c->prior == DPMM_PRIOR_MULTINOMIAL) return c->D;
   const int D = c->D;
-  return ((D * (D + 1) / 2 + 3) & ~3) + ((D + 3) & ~3);
+  return gauss_col_off(D) + ((D + 3) & ~3);
 }
 
 static int ensure_k(dpmm_ctx* ctx, int K) {
@@ -252,10 +252,14 @@ static bool niw_dim_supported(int D) {
   }
 }
 
-template <int D>
-static int launch_gauss_label(dpmm_ctx* ctx, GaussLabelArgs a) {
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+template <int D, int P>
+static int launch_gauss_label_p(dpmm_ctx* ctx, GaussLabelArgs a) {
   using C = GaussCfg<D>;
-  constexpr int P = LabelP<D>::P;
   const size_t budget2 = 110 * 1024, budget1 = (size_t)ctx->smem_optin;
   int T = 128, KC = a.K;
   auto bytes = [&](int T_, int KC_) {
@@ -275,6 +279,10 @@ static int launch_gauss_label(dpmm_ctx* ctx, GaussLabelArgs a) {
     if (ok) break;
   }
   if (!ok) return fail(ctx, DPMM_ELIMIT, "K too large for the label kernel's shared-memory slice");
+  // development overrides (tools/): DPMM_LABEL_T / DPMM_LABEL_KC
+  T = env_int("DPMM_LABEL_T", T);
+  KC = std::min(a.K, env_int("DPMM_LABEL_KC", KC));
+  if (bytes(T, KC) > budget1) return fail(ctx, DPMM_ELIMIT, "label kernel override exceeds shared memory");
   a.KC = KC;
   const int TP = T * P;
   a.ntiles = (a.n + TP - 1) / TP;
@@ -289,6 +297,18 @@ static int launch_gauss_label(dpmm_ctx* ctx, GaussLabelArgs a) {
   kern<<<(unsigned)grid, T, sm, ctx->stream>>>(a);
   CK(cudaGetLastError());
   return 0;
+}
+
+template <int D>
+static int launch_gauss_label(dpmm_ctx* ctx, GaussLabelArgs a) {
+#ifdef DPMM_EXPERIMENT
+  if constexpr (D == 32) {
+    const int p = env_int("DPMM_LABEL_P", LabelP<D>::P);
+    if (p == 1) return launch_gauss_label_p<D, 1>(ctx, a);
+    if (p == 4) return launch_gauss_label_p<D, 4>(ctx, a);
+  }
+#endif
+  return launch_gauss_label_p<D, LabelP<D>::P>(ctx, a);
 }
 
 template <int D>
@@ -712,7 +732,7 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
   CK(cudaSetDevice(ctx->device));
   int rc = ensure_k(ctx, K);
   if (rc) return rc;
-  const int D = ctx->D, REC = ctx->rec_f, TRIP = (D * (D + 1) / 2 + 3) & ~3;
+  const int D = ctx->D, REC = ctx->rec_f, TRIP = gauss_col_off(D);
   const size_t nrec = (size_t)3 * K;
   const size_t bytes = (nrec * REC + nrec + K + 2 * K) * sizeof(float);
   rc = ensure_stage(ctx, bytes);
@@ -745,9 +765,10 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
         L[(size_t)i * D + j] = v / ljj;
       }
     }
-    int e = 0;
-    for (int i = 0; i < D; ++i)
-      for (int j = i; j < D; ++j) rec[e++] = ok ? (float)L[(size_t)j * D + i] : NAN;  // U[i][j] = L[j][i]
+    for (int j = 0; j < D; ++j) {  // column j of U = row j of L, padded to a multiple of 4 floats
+      const int off = gauss_col_off(j);
+      for (int i = 0; i <= j; ++i) rec[off + i] = ok ? (float)L[(size_t)j * D + i] : NAN;  // U[i][j] = L[j][i]
+    }
     for (int j = 0; j < D; ++j) rec[TRIP + j] = mu[t * D + j];
     h_cst[t] = ((float)(D * D) * log2pi + logdet[t]) / 2.f;
   }

@@ -14,12 +14,19 @@
 #pragma once
 #include "common.cuh"
 
+// Offset (floats) of column j of the packed factor: column j holds U[0..j][j] padded to a multiple
+// of 4 floats so that every column starts 16-byte aligned.
+__host__ __device__ constexpr int gauss_col_off(int j) {
+  int s = 0;
+  for (int c = 0; c < j; ++c) s += 4 * (c / 4 + 1);
+  return s;
+}
+
 template <int D>
 struct GaussCfg {
-  static constexpr int TRI = D * (D + 1) / 2;
-  static constexpr int TRIP = (TRI + 3) & ~3;
+  static constexpr int TRIP = gauss_col_off(D);   // floats of the packed upper-triangular factor
   static constexpr int DP4 = (D + 3) & ~3;
-  static constexpr int REC = TRIP + DP4;  // floats per distribution record: [U packed rows | mu]
+  static constexpr int REC = TRIP + DP4;  // floats per distribution record: [U packed columns | mu]
   static constexpr bool VEC = (D % 4 == 0);
   // shared-memory row stride of a staged point: 16B-aligned rows whose float4 index is odd (no
   // bank conflicts for LDS.128 with lane <-> point), or an odd scalar stride.
@@ -46,59 +53,100 @@ struct GaussLabelArgs {
   int64_t ntiles;
 };
 
-// z[pp][:] = x_pp - mu for points staged in shared memory (row pointers from `xrow`).
-template <int D, int P, typename XF>
-__device__ __forceinline__ void gauss_center_smem(const float* __restrict__ rec, XF xrow, float (&z)[P][D]) {
+// q[pp] = |U (x_pp - mu)|^2 for P points owned by this thread.
+//   rec     : distribution record [U packed by columns | mu] in shared memory
+//   load4   : load4(pp, j0) -> the 4 coordinates j0..j0+3 of point pp (zero beyond D)
+// Column-major accumulation: all D partial sums y_i = sum_{j>=i} U_ij z_j of a point live in
+// registers and column j adds U[0..j][j] * z_j to y[0..j], so a thread always has >= D independent
+// FMA chains in flight and z_j = x_j - mu_j is formed once per column (never stored).  The factor is
+// read as float4 words at compile-time offsets: one LDS.128 per 4*P FMAs.
+template <int D, int P, typename LF>
+__device__ __forceinline__ void gauss_quadform(const float* __restrict__ rec, LF load4, float (&q)[P]) {
   using C = GaussCfg<D>;
+  constexpr int NP = C::DP4 / 2;  // packed row pairs (rows 2i, 2i+1)
+  constexpr int NV = C::DP4 / 4;  // float4 words of the longest column
+  f32x2_t y[P][NP];
+#pragma unroll
+  for (int pp = 0; pp < P; ++pp)
+#pragma unroll
+    for (int i = 0; i < NP; ++i) y[pp][i] = 0ull;
   const float* mu = rec + C::TRIP;
-  if constexpr (C::VEC) {
+  // Software pipeline (everything is unrolled, so all of this lives in registers): the factor
+  // words of column j+1 and the point/mean words of the next 4-column block are loaded while
+  // column j is being accumulated, which keeps the shared-memory latency off the FMA chains.
+  ulonglong2 ub[2][NV];
+  float4 xb[2][P], mb[2];
+  ub[0][0] = *reinterpret_cast<const ulonglong2*>(rec);
+  mb[0] = *reinterpret_cast<const float4*>(mu);
 #pragma unroll
-    for (int j4 = 0; j4 < D / 4; ++j4) {
-      const float4 m = *reinterpret_cast<const float4*>(mu + 4 * j4);
+  for (int pp = 0; pp < P; ++pp) xb[0][pp] = load4(pp, 0);
+  int off = 0;
 #pragma unroll
-      for (int pp = 0; pp < P; ++pp) {
-        const float4 v = *reinterpret_cast<const float4*>(xrow(pp) + 4 * j4);
-        z[pp][4 * j4 + 0] = v.x - m.x;
-        z[pp][4 * j4 + 1] = v.y - m.y;
-        z[pp][4 * j4 + 2] = v.z - m.z;
-        z[pp][4 * j4 + 3] = v.w - m.w;
+  for (int j0 = 0; j0 < D; j0 += 4) {
+    const int cb = (j0 >> 2) & 1;
+    if (j0 + 4 < D) {
+      mb[cb ^ 1] = *reinterpret_cast<const float4*>(mu + j0 + 4);
+#pragma unroll
+      for (int pp = 0; pp < P; ++pp) xb[cb ^ 1][pp] = load4(pp, j0 + 4);
+    }
+    float zj[P][4];
+#pragma unroll
+    for (int pp = 0; pp < P; ++pp) {
+      zj[pp][0] = xb[cb][pp].x - mb[cb].x;
+      zj[pp][1] = xb[cb][pp].y - mb[cb].y;
+      zj[pp][2] = xb[cb][pp].z - mb[cb].z;
+      zj[pp][3] = xb[cb][pp].w - mb[cb].w;
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = j0 + jj;
+      if (j < D) {
+        const int ncur = 4 * (j / 4 + 1);
+        if (j + 1 < D) {  // prefetch column j+1
+#pragma unroll
+          for (int i4 = 0; i4 <= (j + 1) / 4; ++i4)
+            ub[(j + 1) & 1][i4] = *reinterpret_cast<const ulonglong2*>(rec + off + ncur + 4 * i4);
+        }
+        f32x2_t z2[P];
+#pragma unroll
+        for (int pp = 0; pp < P; ++pp) z2[pp] = f2_pack(zj[pp][jj], zj[pp][jj]);
+#pragma unroll
+        for (int i4 = 0; i4 <= j / 4; ++i4) {
+          // rows 4*i4 .. 4*i4+3 of column j: two packed pairs (entries below the diagonal are 0)
+          const ulonglong2 u = ub[j & 1][i4];
+#pragma unroll
+          for (int pp = 0; pp < P; ++pp) {
+            y[pp][2 * i4] = f2_fma(u.x, z2[pp], y[pp][2 * i4]);
+            if (4 * i4 + 2 <= j) y[pp][2 * i4 + 1] = f2_fma(u.y, z2[pp], y[pp][2 * i4 + 1]);
+          }
+        }
+        off += ncur;
       }
     }
-  } else {
+  }
 #pragma unroll
-    for (int j = 0; j < D; ++j) {
-      const float m = mu[j];
+  for (int pp = 0; pp < P; ++pp) {
+    f32x2_t s = 0ull;
 #pragma unroll
-      for (int pp = 0; pp < P; ++pp) z[pp][j] = xrow(pp)[j] - m;
-    }
+    for (int i = 0; i < NP; ++i) s = f2_fma(y[pp][i], y[pp][i], s);
+    float lo, hi;
+    f2_unpack(s, lo, hi);
+    q[pp] = lo + hi;
   }
 }
 
-// q[pp] = |U z_pp|^2 for P centred points held in registers.  `rec` points to the distribution
-// record [U packed upper-triangular rows | mu] in shared or global memory; the triangle is read as
-// float4 words at compile-time offsets (one LDS.128 / LDG.128 per 4*P FMAs).
-template <int D, int P>
-__device__ __forceinline__ void gauss_quadform(const float* __restrict__ rec, const float (&z)[P][D], float (&q)[P]) {
-#pragma unroll
-  for (int pp = 0; pp < P; ++pp) q[pp] = 0.f;
-  const float4* U4 = reinterpret_cast<const float4*>(rec);
-  float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  int e = 0;
-#pragma unroll
-  for (int i = 0; i < D; ++i) {
-    float acc[P];
-#pragma unroll
-    for (int pp = 0; pp < P; ++pp) acc[pp] = 0.f;
-#pragma unroll
-    for (int j = i; j < D; ++j) {
-      if ((e & 3) == 0) u4 = U4[e >> 2];
-      const float u = ((e & 3) == 0) ? u4.x : ((e & 3) == 1) ? u4.y : ((e & 3) == 2) ? u4.z : u4.w;
-#pragma unroll
-      for (int pp = 0; pp < P; ++pp) acc[pp] = fmaf(u, z[pp][j], acc[pp]);
-      ++e;
-    }
-#pragma unroll
-    for (int pp = 0; pp < P; ++pp) q[pp] = fmaf(acc[pp], acc[pp], q[pp]);
+// load4 functor over a point row in shared or global memory (16B-aligned rows when D % 4 == 0)
+template <int D>
+__device__ __forceinline__ float4 gauss_row_load4(const float* row, int j0) {
+  if constexpr (D % 4 == 0) {
+    return *reinterpret_cast<const float4*>(row + j0);
+  } else {
+    float4 v;
+    v.x = row[j0];
+    v.y = (j0 + 1 < D) ? row[j0 + 1] : 0.f;
+    v.z = (j0 + 2 < D) ? row[j0 + 2] : 0.f;
+    v.w = (j0 + 3 < D) ? row[j0 + 3] : 0.f;
+    return v;
   }
 }
 
@@ -117,7 +165,7 @@ __device__ __forceinline__ float gauss_finish(float c, float q, float logw) {
 //   hs [K]        histogram of the labels drawn by this CTA (feeds the label sort)
 // ---------------------------------------------------------------------------------------------
 template <int D, int P>
-__global__ void gauss_label_kernel(const GaussLabelArgs a) {
+__global__ void __launch_bounds__(128, 2) gauss_label_kernel(const GaussLabelArgs a) {
   using C = GaussCfg<D>;
   extern __shared__ __align__(16) float smem[];
   const int T = blockDim.x;
@@ -168,12 +216,11 @@ __global__ void gauss_label_kernel(const GaussLabelArgs a) {
       for (int kk = 0; kk < kcn; ++kk) {
         const int k = kc0 + kk;
         float q[P];
-        {
-          float z[P][D];
-          gauss_center_smem<D, P>(us + (size_t)kk * C::REC,
-                                  [&](int pp) { return xs + (size_t)(tid + pp * T) * C::DS; }, z);
-          gauss_quadform<D, P>(us + (size_t)kk * C::REC, z, q);
-        }
+        gauss_quadform<D, P>(us + (size_t)kk * C::REC,
+                             [&](int pp, int j0) {
+                               return gauss_row_load4<D>(xs + (size_t)(tid + pp * T) * C::DS, j0);
+                             },
+                             q);
         const float c = __ldg(a.cst + 3 * k), lw = __ldg(a.logw + k);
 #pragma unroll
         for (int pp = 0; pp < P; ++pp) rs[(size_t)k * TP + tid + pp * T] = gauss_finish(c, q[pp], lw);
@@ -269,22 +316,34 @@ __device__ __forceinline__ void sublabel_partition(const SubLabelArgs& a, bool a
   }
 }
 
+#define SUBLABEL_SPAN 2  // clusters whose l/r records are staged per pass
+
 template <int D, bool SAMPLE>
 __global__ void gauss_sublabel_kernel(const SubLabelArgs a) {
   using C = GaussCfg<D>;
   __shared__ int s_cnt[2 * 256];
   __shared__ int s_base[2 * 256];
   __shared__ int s_first[2];
-  const int tid = threadIdx.x;
-  const int64_t pos = (int64_t)blockIdx.x * blockDim.x + tid;
+  __shared__ __align__(16) float us[SAMPLE ? SUBLABEL_SPAN * 2 * C::REC : 4];
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int64_t pos0 = (int64_t)blockIdx.x * T;
+  const int64_t pos = pos0 + tid;
   const bool active = pos < a.n;
   int32_t idx = 0;
   int k = 0, side = 0;
   if (active) {
     idx = a.perm[pos];
     k = a.labels[idx];
-    if constexpr (SAMPLE) {
-      float xr[C::DP4];
+    if constexpr (!SAMPLE) side = a.sub[idx];
+  }
+  if constexpr (SAMPLE) {
+    const int nact = (int)min((int64_t)T, a.n - pos0);
+    if (tid == 0) s_first[0] = k;
+    if (tid == nact - 1) s_first[1] = k;
+    float xr[C::DP4];
+#pragma unroll
+    for (int j = 0; j < C::DP4; ++j) xr[j] = 0.f;
+    if (active) {
       const float* xp = a.x + (size_t)idx * D;
       if constexpr (C::VEC) {
 #pragma unroll
@@ -296,21 +355,32 @@ __global__ void gauss_sublabel_kernel(const SubLabelArgs a) {
 #pragma unroll
         for (int j = 0; j < D; ++j) xr[j] = __ldg(xp + j);
       }
-      float ql[1], qr[1];
-      {
-        const float* recl = a.recs + (size_t)(3 * k + 1) * C::REC;
-        const float* recr = a.recs + (size_t)(3 * k + 2) * C::REC;
-        float zl[1][D], zr[1][D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-          zl[0][j] = xr[j] - __ldg(recl + C::TRIP + j);
-          zr[0][j] = xr[j] - __ldg(recr + C::TRIP + j);
-        }
-        gauss_quadform<D, 1>(recl, zl, ql);
-        gauss_quadform<D, 1>(recr, zr, qr);
+    }
+    __syncthreads();
+    const int kfirst = s_first[0], klast = s_first[1];
+    float rl = 0.f, rr = 0.f;
+    // the tile is label-sorted: stage the l/r records of SUBLABEL_SPAN consecutive labels at a time
+    // (almost always a single pass); lanes of a warp then read them as shared-memory broadcasts
+    for (int kb = kfirst; kb <= klast; kb += SUBLABEL_SPAN) {
+      const int nk = min(SUBLABEL_SPAN, klast - kb + 1);
+      __syncthreads();
+      for (int e = tid; e < nk * 2 * (C::REC / 4); e += T) {
+        const int r = e / (C::REC / 4), c = e - r * (C::REC / 4);
+        const int kk = kb + (r >> 1), s = 1 + (r & 1);
+        reinterpret_cast<float4*>(us)[e] =
+            __ldg(reinterpret_cast<const float4*>(a.recs + (size_t)(3 * kk + s) * C::REC) + c);
       }
-      const float rl = gauss_finish(__ldg(a.cst + 3 * k + 1), ql[0], __ldg(a.loglr + 2 * k));
-      const float rr = gauss_finish(__ldg(a.cst + 3 * k + 2), qr[0], __ldg(a.loglr + 2 * k + 1));
+      __syncthreads();
+      if (active && k >= kb && k < kb + nk) {
+        float ql[1], qr[1];
+        auto ld = [&](int, int j0) { return make_float4(xr[j0], xr[j0 + 1], xr[j0 + 2], xr[j0 + 3]); };
+        gauss_quadform<D, 1>(us + (size_t)((k - kb) * 2) * C::REC, ld, ql);
+        gauss_quadform<D, 1>(us + (size_t)((k - kb) * 2 + 1) * C::REC, ld, qr);
+        rl = gauss_finish(__ldg(a.cst + 3 * k + 1), ql[0], __ldg(a.loglr + 2 * k));
+        rr = gauss_finish(__ldg(a.cst + 3 * k + 2), qr[0], __ldg(a.loglr + 2 * k + 1));
+      }
+    }
+    if (active) {
       if (a.dump != nullptr) {
         a.dump[idx] = rl;
         a.dump[a.n + idx] = rr;
@@ -318,9 +388,8 @@ __global__ void gauss_sublabel_kernel(const SubLabelArgs a) {
       const double u = dpmm_uniform(a.u_inj, idx, a.seed, DPMM_STREAM_SUBLABEL, a.call, (uint64_t)(a.goff + idx));
       side = dpmm_draw_two(rl, rr, u);
       a.sub[idx] = (uint8_t)side;
-    } else {
-      side = a.sub[idx];
     }
+    __syncthreads();
   }
   sublabel_partition(a, active, k, side, idx, s_cnt, s_base, s_first);
 }
