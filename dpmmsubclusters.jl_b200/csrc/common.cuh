@@ -42,8 +42,26 @@ __device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
 // the documented near-tie band (1e-5 in log space).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int dpmm_draw_inverse_cdf(float* rs, int stride, int K, double u) {
+  // Every pass is unrolled by 4 with the loads issued together: the passes are serial per point, so
+  // instruction-level parallelism is what hides the shared-memory latency here.  Floating-point
+  // ORDER is unchanged: the sums run left to right.
+  const int K4 = K & ~3;
+  // ---- :21-22  NaN -> -Inf, row max ----
   float mx = -CUDART_INF_F;
-  for (int k = 0; k < K; ++k) {
+  for (int k = 0; k < K4; k += 4) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = rs[(k + j) * stride];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (v[j] != v[j]) {
+        v[j] = -CUDART_INF_F;
+        rs[(k + j) * stride] = v[j];
+      }
+    }
+    mx = fmaxf(mx, fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])));
+  }
+  for (int k = K4; k < K; ++k) {
     float v = rs[k * stride];
     if (v != v) {
       v = -CUDART_INF_F;
@@ -51,34 +69,79 @@ __device__ __forceinline__ int dpmm_draw_inverse_cdf(float* rs, int stride, int 
     }
     mx = fmaxf(mx, v);
   }
+  // ---- :23-26  subtract, exp, row sum ----
   float s = 0.f;
-  for (int k = 0; k < K; ++k) {
-    // exp(d) rounds to +0 in Float32 for d < -104 (half the smallest denormal is e^-103.97): skip the
-    // Float64 evaluation for the many clusters that are far from the point (same value, much cheaper)
-    const float d = rs[k * stride] - mx;
-    const float e = expf(d);
+  for (int k = 0; k < K4; k += 4) {
+    float e[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) e[j] = expf(rs[(k + j) * stride] - mx);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      rs[(k + j) * stride] = e[j];
+      s = __fadd_rn(s, e[j]);
+    }
+  }
+  for (int k = K4; k < K; ++k) {
+    const float e = expf(rs[k * stride] - mx);
     rs[k * stride] = e;
     s = __fadd_rn(s, e);
   }
-  float tot = 0.f;
+  // ---- :27  divide; the running sum cw_k replaces p_k in place (it is all the walk needs) ----
+  // The IEEE division takes a ~70-instruction slow path for zero / denormal numerators, which is what
+  // most far-away clusters produce (e^d for d < -87.3).  0 / s is exactly 0 for finite s > 0, and a
+  // denormal weight (< 1.2e-38) can never decide the walk: the smallest non-zero t is 2^-53 * sum(w)
+  // ~ 1e-16 and for t == 0 the walk stops at i = 1 regardless.  Those lanes therefore divide 1 by s,
+  // discard the quotient and use p = 0.
   const bool s_regular = (s > 0.f) && (s < CUDART_INF_F);
-  for (int k = 0; k < K; ++k) {
-    // 0 / s == 0 exactly for finite s > 0.  The IEEE division takes a ~70-instruction slow path for
-    // zero / denormal numerators (most far-away clusters), so those lanes divide 1 by s instead and
-    // the quotient is discarded.
+  float cw = 0.f;
+  bool first = true;  // cw starts AT w[1] (not 0 + w[1]): keeps -0 / NaN semantics of the reference
+  for (int k = 0; k < K4; k += 4) {
+    float p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float e = rs[(k + j) * stride];
+      const bool zero = (e < 1.17549435e-38f) && s_regular;
+      const float quo = __fdiv_rn(zero ? 1.f : e, s);
+      p[j] = zero ? 0.f : quo;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      cw = first ? p[j] : __fadd_rn(cw, p[j]);
+      first = false;
+      rs[(k + j) * stride] = cw;
+    }
+  }
+  for (int k = K4; k < K; ++k) {
     const float e = rs[k * stride];
-    const bool zero = (e == 0.f) && s_regular;
+    const bool zero = (e < 1.17549435e-38f) && s_regular;
     const float quo = __fdiv_rn(zero ? 1.f : e, s);
     const float p = zero ? 0.f : quo;
-    rs[k * stride] = p;
-    tot = __fadd_rn(tot, p);
+    cw = first ? p : __fadd_rn(cw, p);
+    first = false;
+    rs[k * stride] = cw;
   }
-  const double t = u * (double)tot;
-  int i = 0;
-  float cw = rs[0];
-  while ((double)cw < t && i < K - 1) {
-    ++i;
-    cw = __fadd_rn(cw, rs[i * stride]);
+  // ---- :29  t = rand() * sum(w);  first i with !(cw_i < t), clamped to n ----
+  const double t = u * (double)cw;  // sum(w) accumulated left to right == the last running sum
+  int i = K - 1;
+  for (int k = 0; k < K4; k += 4) {
+    float c[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = rs[(k + j) * stride];
+    int hit = -1;
+#pragma unroll
+    for (int j = 3; j >= 0; --j)
+      if (!((double)c[j] < t)) hit = k + j;
+    if (hit >= 0) {
+      i = hit;
+      break;
+    }
+  }
+  if (i == K - 1) {
+    for (int k = K4; k < K - 1; ++k)
+      if (!((double)rs[k * stride] < t)) {
+        i = k;
+        break;
+      }
   }
   return i;
 }

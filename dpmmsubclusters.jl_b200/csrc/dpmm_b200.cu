@@ -328,11 +328,12 @@ template <int D>
 static int launch_niw_stats(dpmm_ctx* ctx, const StatsArgs& a) {
   using C = StatsCfg<D>;
   auto kern = niw_stats_kernel<D>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   int occ = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::WARPS * 32, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::WARPS * 32, C::SMEM_BYTES));
   occ = std::max(occ, 1);
   KernelTimer kt(ctx, TK_STATS);
-  kern<<<ctx->sm_count * occ, C::WARPS * 32, 0, ctx->stream>>>(a);
+  kern<<<ctx->sm_count * occ, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(a);
   CK(cudaGetLastError());
   return 0;
 }

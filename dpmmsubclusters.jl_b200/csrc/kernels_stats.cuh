@@ -95,13 +95,14 @@ __device__ __forceinline__ int warp_transpose_entry(int lane, int j) {
 
 template <int D>
 struct StatsCfg {
-  static constexpr int BS = (D <= 8) ? D : 8;            // register block edge
+  static constexpr int BS = (D <= 8) ? D : 8;            // register block edge (rows)
+  static constexpr int BSQ = (BS + 1) & ~1;              // block columns, padded to whole FFMA2 pairs
   static constexpr int NB = (D + BS - 1) / BS;           // blocks per matrix edge
-  static constexpr int NU = NB * (NB + 1) / 2;           // upper-triangular blocks = warps per slice
-  static constexpr int DPAD = NB * BS;
+  static constexpr int NU = NB * (NB + 1) / 2;           // upper-triangular blocks
+  static constexpr int DPAD = NB * BS + (BSQ - BS);
   static constexpr bool VEC = (BS % 4 == 0);
   static constexpr int DS = VEC ? 4 * ((DPAD / 4) | 1) : ((DPAD & 1) ? DPAD : DPAD + 1);
-  static constexpr int E = BS * BS;
+  static constexpr int E = BS * BSQ;
   static constexpr int EP = (E + 31) / 32 * 32;
   static constexpr int G = (NU + 15) / 16;               // block groups: a CTA covers NU/G blocks (<= 16 warps)
   static constexpr int WPG = (NU + G - 1) / G;           // warps (= blocks) per group
@@ -109,6 +110,8 @@ struct StatsCfg {
   static constexpr int WARPS = WPG * NS;
   static constexpr int R = (NS >= 8) ? 2 : 4;            // points per lane per tile
   static constexpr int TPTS = 32 * NS * R;               // points per shared-memory tile
+  static constexpr int SMEM_BYTES = 2 * TPTS * DS * 4;   // double-buffered tile
+  static constexpr int MIN_CTAS = (WARPS * 32 <= 320) ? 2 : 1;
 };
 
 struct StatsArgs {
@@ -122,22 +125,54 @@ struct StatsArgs {
   int rec;
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // K5: NIW.  Warp w of a CTA owns upper block u = g*WPG + w % WPG of S (g = block group of the work
 // unit; G > 1 only when S has more than 16 upper blocks, i.e. D > 40) and point slice w / WPG; lane l
 // owns the points l, l+32, ... of its slice, so the warp's 32 lanes read 32 different staged points
 // at the same column offset (conflict-free LDS.128) and the 32 partial blocks are combined once per
-// item.
+// item.  The gathered rows of tile t+1 stream in with cp.async (zero-filled past the end of the run)
+// while tile t is accumulated; the rank-1 updates are packed FFMA2 (two columns per instruction).
 template <int D>
-__global__ void __launch_bounds__(StatsCfg<D>::WARPS * 32, 1)
+__global__ void __launch_bounds__(StatsCfg<D>::WARPS * 32, StatsCfg<D>::MIN_CTAS)
 niw_stats_kernel(const StatsArgs a) {
   using C = StatsCfg<D>;
-  constexpr int BS = C::BS;
-  __shared__ __align__(16) float xs[C::TPTS * C::DS];
-  __shared__ int32_t sidx[C::TPTS];
+  constexpr int BS = C::BS, BSQ = C::BSQ, NQ = C::BSQ / 2;
+  extern __shared__ __align__(16) float xs_all[];  // [2][TPTS][DS]
   __shared__ int s_item;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slice = warp / C::WPG;
-  for (int e = tid; e < C::TPTS * C::DS; e += blockDim.x) xs[e] = 0.f;  // zero padding columns once
+  for (int e = tid; e < 2 * C::TPTS * C::DS; e += blockDim.x) xs_all[e] = 0.f;  // padding columns stay 0
+
+  auto prefetch = [&](const StatsItem& item, int t0, int buf) {
+    float* xs = xs_all + buf * C::TPTS * C::DS;
+    const int tn = min(C::TPTS, item.end - t0);
+    if constexpr (D % 4 == 0) {
+      for (int e = tid; e < C::TPTS * (D / 4); e += blockDim.x) {
+        const int p = e / (D / 4), c = e - p * (D / 4);
+        const bool ok = p < tn;
+        const int idx = ok ? __ldg(a.perm2 + t0 + p) : 0;
+        cp_async16(xs + p * C::DS + 4 * c, a.x + (size_t)idx * D + 4 * c, ok ? 16 : 0);
+      }
+    } else {
+      for (int e = tid; e < C::TPTS * D; e += blockDim.x) {
+        const int p = e / D, c = e - p * D;
+        const bool ok = p < tn;
+        const int idx = ok ? __ldg(a.perm2 + t0 + p) : 0;
+        cp_async4(xs + p * C::DS + c, a.x + (size_t)idx * D + c, ok ? 4 : 0);
+      }
+    }
+    cp_async_commit();
+  };
 
   for (;;) {
     __syncthreads();
@@ -158,74 +193,72 @@ niw_stats_kernel(const StatsArgs a) {
       bj = bi + r;
     }
     const bool diag = live && (bi == bj);
-    float acc[C::EP];
+    f32x2_t acc[BS][NQ];
     float sx[BS];
 #pragma unroll
-    for (int e = 0; e < C::EP; ++e) acc[e] = 0.f;
+    for (int p = 0; p < BS; ++p) {
+      sx[p] = 0.f;
 #pragma unroll
-    for (int e = 0; e < BS; ++e) sx[e] = 0.f;
+      for (int q = 0; q < NQ; ++q) acc[p][q] = 0ull;
+    }
 
-    for (int t0 = item.begin; t0 < item.end; t0 += C::TPTS) {
-      const int tn = min(C::TPTS, item.end - t0);
-      __syncthreads();
-      for (int p = tid; p < C::TPTS; p += blockDim.x) sidx[p] = (p < tn) ? a.perm2[t0 + p] : -1;
-      __syncthreads();
-      if constexpr (D % 4 == 0) {
-        for (int e = tid; e < C::TPTS * (D / 4); e += blockDim.x) {
-          const int p = e / (D / 4), c = e - p * (D / 4);
-          const int idx = sidx[p];
-          const float4 v = (idx >= 0) ? __ldg(reinterpret_cast<const float4*>(a.x + (size_t)idx * D) + c)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(xs + p * C::DS + 4 * c) = v;
-        }
-      } else {
-        for (int e = tid; e < C::TPTS * D; e += blockDim.x) {
-          const int p = e / D, c = e - p * D;
-          const int idx = sidx[p];
-          xs[p * C::DS + c] = (idx >= 0) ? __ldg(a.x + (size_t)idx * D + c) : 0.f;
-        }
-      }
-      __syncthreads();
-      if (live)
+    prefetch(item, item.begin, 0);
+    int buf = 0;
+    for (int t0 = item.begin; t0 < item.end; t0 += C::TPTS, buf ^= 1) {
+      cp_async_wait_all();
+      __syncthreads();  // tile t0 has landed for everyone; everyone is done with the other buffer
+      if (t0 + C::TPTS < item.end) prefetch(item, t0 + C::TPTS, buf ^ 1);
+      if (live) {
+        const float* xs = xs_all + buf * C::TPTS * C::DS;
 #pragma unroll
-      for (int r = 0; r < C::R; ++r) {
-        const float* row = xs + (slice * 32 * C::R + r * 32 + lane) * C::DS;
-        float xi[BS], xj[BS];
-        if constexpr (C::VEC) {
+        for (int r = 0; r < C::R; ++r) {
+          const float* row = xs + (slice * 32 * C::R + r * 32 + lane) * C::DS;
+          float xi[BS];
+          f32x2_t xj[NQ];
+          if constexpr (C::VEC) {
 #pragma unroll
-          for (int q4 = 0; q4 < BS / 4; ++q4) {
-            const float4 vi = *reinterpret_cast<const float4*>(row + bi * BS + 4 * q4);
-            const float4 vj = *reinterpret_cast<const float4*>(row + bj * BS + 4 * q4);
-            xi[4 * q4] = vi.x; xi[4 * q4 + 1] = vi.y; xi[4 * q4 + 2] = vi.z; xi[4 * q4 + 3] = vi.w;
-            xj[4 * q4] = vj.x; xj[4 * q4 + 1] = vj.y; xj[4 * q4 + 2] = vj.z; xj[4 * q4 + 3] = vj.w;
+            for (int q4 = 0; q4 < BS / 4; ++q4) {
+              const float4 vi = *reinterpret_cast<const float4*>(row + bi * BS + 4 * q4);
+              const ulonglong2 vj = *reinterpret_cast<const ulonglong2*>(row + bj * BS + 4 * q4);
+              xi[4 * q4] = vi.x; xi[4 * q4 + 1] = vi.y; xi[4 * q4 + 2] = vi.z; xi[4 * q4 + 3] = vi.w;
+              xj[2 * q4] = vj.x; xj[2 * q4 + 1] = vj.y;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < BS; ++q) xi[q] = row[bi * BS + q];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) xj[q] = f2_pack(row[bj * BS + 2 * q], row[bj * BS + 2 * q + 1]);
           }
-        } else {
 #pragma unroll
-          for (int q = 0; q < BS; ++q) {
-            xi[q] = row[bi * BS + q];
-            xj[q] = row[bj * BS + q];
+          for (int p = 0; p < BS; ++p) {
+            const f32x2_t xip = f2_pack(xi[p], xi[p]);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) acc[p][q] = f2_fma(xip, xj[q], acc[p][q]);
           }
-        }
+          if (diag) {
 #pragma unroll
-        for (int p = 0; p < BS; ++p)
-#pragma unroll
-          for (int q = 0; q < BS; ++q) acc[p * BS + q] = fmaf(xi[p], xj[q], acc[p * BS + q]);
-        if (diag) {
-#pragma unroll
-          for (int p = 0; p < BS; ++p) sx[p] += xi[p];
+            for (int p = 0; p < BS; ++p) sx[p] += xi[p];
+          }
         }
       }
     }
     // ---- combine the 32 lanes and add to the key's Float64 accumulator ----
     if (!live) continue;
-    warp_transpose_reduce<C::EP>(acc, lane);
+    float accf[C::EP];
+#pragma unroll
+    for (int e = 0; e < C::EP; ++e) accf[e] = 0.f;
+#pragma unroll
+    for (int p = 0; p < BS; ++p)
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) f2_unpack(acc[p][q], accf[p * BSQ + 2 * q], accf[p * BSQ + 2 * q + 1]);
+    warp_transpose_reduce<C::EP>(accf, lane);
     double* dst = a.acc + (size_t)item.key * a.rec;
 #pragma unroll
     for (int j = 0; j < C::EP / 32; ++j) {
       const int e = warp_transpose_entry<C::EP>(lane, j);
       if (e < C::E) {
-        const int gi = bi * BS + e / BS, gj = bj * BS + e % BS;
-        if (gi < D && gj < D && gi <= gj) atomicAdd(dst + 1 + D + (size_t)gi * D + gj, (double)acc[j]);
+        const int gi = bi * BS + e / BSQ, gj = bj * BS + e % BSQ;
+        if (e % BSQ < BS && gi < D && gj < D && gi <= gj) atomicAdd(dst + 1 + D + (size_t)gi * D + gj, (double)accf[j]);
       }
     }
     if (diag) {
