@@ -260,6 +260,26 @@ static int env_int(const char* name, int dflt) {
 template <int D, int P>
 static int launch_gauss_label_p(dpmm_ctx* ctx, GaussLabelArgs a) {
   using C = GaussCfg<D>;
+  {
+    // warp-autonomous form: all K records resident + W private warp buffers
+    const size_t fixed = ((size_t)a.K * C::REC + ((a.K + 3) & ~3)) * 4;
+    const size_t perwarp = ((size_t)32 * P * C::DS + (size_t)a.K * 32 * P) * 4;
+    int W = fixed < (size_t)ctx->smem_optin ? (int)(((size_t)ctx->smem_optin - fixed) / perwarp) : 0;
+    W = std::min(W, 12);
+    W = env_int("DPMM_LABEL_W", W);
+    if (W >= 6 && env_int("DPMM_LABEL_FORM", 1) == 1) {
+      const size_t sm = fixed + (size_t)W * perwarp;
+      auto kern = gauss_label_warp_kernel<D, P>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      a.KC = a.K;
+      a.ntiles = (a.n + 32 * P - 1) / (32 * P);
+      const int64_t grid = std::min<int64_t>((a.ntiles + W - 1) / W, (int64_t)ctx->sm_count);
+      KernelTimer kt(ctx, TK_LABEL);
+      kern<<<(unsigned)grid, W * 32, sm, ctx->stream>>>(a);
+      CK(cudaGetLastError());
+      return 0;
+    }
+  }
   const size_t budget2 = 110 * 1024, budget1 = (size_t)ctx->smem_optin;
   int T = 128, KC = a.K;
   auto bytes = [&](int T_, int KC_) {

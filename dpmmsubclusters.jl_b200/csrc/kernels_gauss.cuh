@@ -255,6 +255,102 @@ __global__ void __launch_bounds__(128, 2) gauss_label_kernel(const GaussLabelArg
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1 (warp-autonomous form, used whenever all K cluster records fit in shared memory next to the
+// per-warp buffers): one persistent CTA per SM; every warp owns a private tile of 32*P points and
+// runs stage -> log-likelihood -> draw on its own, synchronising only with __syncwarp.  The warps of
+// an SM drift out of phase, so the FMA-bound likelihood loop of one warp overlaps the latency-bound
+// staging and draw phases of the others (the CTA-synchronous kernel above keeps all of its warps in
+// the same phase).  Shared memory:
+//   us [K][REC] cluster records (staged once) | hs [K] label histogram |
+//   per warp: xs [32P][DS] tile, rs [K][32P] slice of parr
+// ---------------------------------------------------------------------------------------------
+template <int D, int P>
+__global__ void __launch_bounds__(384, 1) gauss_label_warp_kernel(const GaussLabelArgs a) {
+  using C = GaussCfg<D>;
+  constexpr int TPW = 32 * P;  // points per warp tile
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+  float* us = smem;
+  int* hs = reinterpret_cast<int*>(us + (size_t)a.K * C::REC);
+  float* wbase = reinterpret_cast<float*>(hs + ((a.K + 3) & ~3));
+  float* xs = wbase + (size_t)warp * (TPW * C::DS + a.K * TPW);
+  float* rs = xs + TPW * C::DS;
+
+  for (int e = tid; e < a.K * (C::REC / 4); e += blockDim.x) {
+    const int kk = e / (C::REC / 4), c = e - kk * (C::REC / 4);
+    reinterpret_cast<float4*>(us)[e] = __ldg(reinterpret_cast<const float4*>(a.recs + (size_t)(3 * kk) * C::REC) + c);
+  }
+  for (int k = tid; k < a.K; k += blockDim.x) hs[k] = 0;
+  __syncthreads();
+
+  for (int64_t tile = (int64_t)blockIdx.x * W + warp; tile < a.ntiles; tile += (int64_t)gridDim.x * W) {
+    const int64_t base = tile * TPW;
+    const int npts = (int)min((int64_t)TPW, a.n - base);
+    __syncwarp();
+    // ---- stage the warp's tile: all loads in flight before the first store ----
+    if constexpr (C::VEC) {
+      constexpr int NLD = P * (D / 4);  // float4 per lane
+      const float4* src = reinterpret_cast<const float4*>(a.x + base * D);
+      const int nv = npts * (D / 4);
+      float4 v[NLD];
+#pragma unroll
+      for (int i = 0; i < NLD; ++i) {
+        const int e = lane + 32 * i;
+        v[i] = (e < nv) ? __ldg(src + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < NLD; ++i) {
+        const int e = lane + 32 * i;
+        const int p = e / (D / 4), c = e - p * (D / 4);
+        *reinterpret_cast<float4*>(xs + p * C::DS + 4 * c) = v[i];
+      }
+    } else {
+      const float* src = a.x + base * D;
+      const int nv = npts * D;
+      for (int e = lane; e < TPW * D; e += 32) {
+        const int p = e / D, c = e - p * D;
+        xs[p * C::DS + c] = (e < nv) ? __ldg(src + e) : 0.f;
+      }
+    }
+    __syncwarp();
+    // ---- log-likelihood under every cluster ----
+    for (int k = 0; k < a.K; ++k) {
+      float q[P];
+      gauss_quadform<D, P>(us + (size_t)k * C::REC,
+                           [&](int pp, int j0) { return gauss_row_load4<D>(xs + (lane + pp * 32) * C::DS, j0); }, q);
+      const float c = __ldg(a.cst + 3 * k), lw = __ldg(a.logw + k);
+#pragma unroll
+      for (int pp = 0; pp < P; ++pp) rs[k * TPW + lane + pp * 32] = gauss_finish(c, q[pp], lw);
+    }
+    // ---- draw (each lane only touches its own columns of rs) ----
+#pragma unroll
+    for (int pp = 0; pp < P; ++pp) {
+      const int p = lane + pp * 32;
+      if (p < npts) {
+        const int64_t i = base + p;
+        float* col = rs + p;
+        if (a.dump != nullptr)
+          for (int k = 0; k < a.K; ++k) a.dump[(size_t)k * a.n + i] = col[k * TPW];
+        int lab;
+        if (a.final_iter) {
+          lab = dpmm_draw_argmax(col, TPW, a.K);
+        } else if (a.sampler == 1) {
+          lab = dpmm_draw_gumbel(col, TPW, a.K, a.seed, a.call, (uint64_t)(a.goff + i));
+        } else {
+          const double u = dpmm_uniform(a.u_inj, i, a.seed, DPMM_STREAM_LABEL, a.call, (uint64_t)(a.goff + i));
+          lab = dpmm_draw_inverse_cdf(col, TPW, a.K, u);
+        }
+        a.labels[i] = lab;
+        atomicAdd(&hs[lab], 1);
+      }
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < a.K; k += blockDim.x)
+    if (hs[k] != 0) atomicAdd(&a.hist[k], hs[k]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K4: sub-label draw over the label-sorted permutation + partition of every label segment into
 // its left / right halves (feeds the statistics kernel).  One thread = one sorted position; lanes
 // of a warp almost always share the label, so the l/r records are read through the read-only path
