@@ -1,0 +1,467 @@
+"""Host side of the sampler: a Python mirror of the reference's MASTER functions, driving the sweep
+through the C ABI (GpuSweep) exactly where the reference crosses to its workers.
+
+Julia is not installed in this environment, so this module stands where the (unchanged) Julia host
+would stand: same function names, same control flow, same defaults, citing the reference lines:
+  fit / dp_parallel / run_model / calculate_posterior     src/dp-parallel-sampling.jl
+  group_step and the master "!"-functions                  src/local_clusters_actions.jl
+  sample_cluster_params / should_merge! / splits           src/shared_actions.jl
+Only the worker calls differ: every `@spawnat ... _worker!` becomes one GpuSweep call.
+"""
+from __future__ import annotations
+
+import copy
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+from scipy.special import gammaln
+
+from . import priors as P
+from .sweep import GpuSweep, NIW, MULTINOMIAL
+
+F32 = np.float32
+
+
+# ---------------------------------------------------------------- data structures (src/ds.jl) ----
+@dataclass
+class model_hyper_params:            # ds.jl:7-11
+    distribution_hyper_params: object
+    α: float
+    total_dim: int
+
+
+@dataclass
+class cluster_parameters:            # ds.jl:13-18
+    hyperparams: object
+    distribution: object
+    suff_statistics: object
+    posterior_hyperparams: object
+
+
+@dataclass
+class splittable_cluster_params:     # ds.jl:20-27
+    cluster_params: cluster_parameters
+    cluster_params_l: cluster_parameters
+    cluster_params_r: cluster_parameters
+    lr_weights: np.ndarray
+    splittable: bool
+    logsublikelihood_hist: np.ndarray
+
+
+@dataclass
+class local_cluster:                 # ds.jl:43-49
+    cluster_params: splittable_cluster_params
+    total_dim: int
+    points_count: int
+    l_count: int
+    r_count: int
+
+
+@dataclass
+class local_group:                   # ds.jl:51-58; points/labels/labels_subcluster live in the sweep
+    model_hyperparams: model_hyper_params
+    sweep: object
+    local_clusters: list = field(default_factory=list)
+    weights: np.ndarray = field(default_factory=lambda: np.zeros(0, F32))
+
+
+@dataclass
+class dp_parallel_sampling:          # ds.jl:76-79
+    model_hyperparams: model_hyper_params
+    group: local_group
+
+
+@dataclass
+class Settings:
+    """The module-level globals of the reference (src/global_params.jl, dp-parallel-sampling.jl:135-146)."""
+    iterations: int = 100
+    hard_clustering: bool = False
+    initial_clusters: int = 1
+    argmax_sample_stop: int = 5
+    split_stop: int = 5
+    burnout_period: int = 20
+    max_num_of_clusters: float = np.inf
+    outlier_mod: float = 0.0
+    use_verbose: bool = False
+    ground_truth: object = None
+
+
+# ---------------------------------------------------------------- shared_actions.jl --------------
+def _neg_inf_hist(cfg):
+    return np.full(cfg.burnout_period + 5, -np.inf)
+
+
+def create_splittable_from_params(params, α, cfg, rng):
+    """shared_actions.jl:2-9."""
+    params_l = copy.deepcopy(params)
+    params_l.distribution = P.sample_distribution(params.posterior_hyperparams, rng)
+    params_r = copy.deepcopy(params)
+    params_r.distribution = P.sample_distribution(params.posterior_hyperparams, rng)
+    lr_weights = rng.dirichlet([α / 2, α / 2])
+    return splittable_cluster_params(params, params_l, params_r, lr_weights, False, _neg_inf_hist(cfg))
+
+
+def merge_clusters_to_splittable(cpl, cpr, α, cfg, rng):
+    """shared_actions.jl:12-18."""
+    suff_stats = P.aggregate_suff_stats(cpl.suff_statistics, cpr.suff_statistics)
+    posterior = P.calc_posterior(cpl.hyperparams, suff_stats)
+    lr_weights = rng.dirichlet([cpl.suff_statistics.N + α / 2, cpr.suff_statistics.N + α / 2])
+    cp = cluster_parameters(cpl.hyperparams, cpl.distribution, suff_stats, posterior)
+    return splittable_cluster_params(cp, cpl, cpr, lr_weights, False, _neg_inf_hist(cfg))
+
+
+def should_merge(cpl, cpr, α, final, rng):
+    """shared_actions.jl:21-38."""
+    new_suff = P.aggregate_suff_stats(cpl.suff_statistics, cpr.suff_statistics)
+    post = P.calc_posterior(cpl.hyperparams, new_suff)
+    ll_l = P.log_marginal_likelihood(cpl.hyperparams, cpl.posterior_hyperparams, cpl.suff_statistics)
+    ll_r = P.log_marginal_likelihood(cpr.hyperparams, cpr.posterior_hyperparams, cpr.suff_statistics)
+    ll = P.log_marginal_likelihood(cpl.hyperparams, post, new_suff)
+    Nl, Nr, N = cpl.suff_statistics.N, cpr.suff_statistics.N, new_suff.N
+    log_HR = (-np.log(α) + gammaln(α) - 2 * gammaln(0.5 * α) + gammaln(N) - gammaln(N + α)
+              + gammaln(Nl + 0.5 * α) - gammaln(Nl) - gammaln(Nr) + gammaln(Nr + 0.5 * α) + ll - ll_l - ll_r)
+    return (log_HR > np.log(rng.random())) or (final and log_HR > np.log(0.1))
+
+
+def sample_cluster_params(params, α, first, cfg, rng):
+    """shared_actions.jl:41-66."""
+    for cp in (params.cluster_params, params.cluster_params_l, params.cluster_params_r):
+        cp.distribution = P.sample_distribution(cp.hyperparams if first else cp.posterior_hyperparams, rng)
+    pc = np.array([params.cluster_params_l.suff_statistics.N, params.cluster_params_r.suff_statistics.N], np.float64) + α / 2
+    params.lr_weights = rng.dirichlet(pc)
+    ll_l = P.log_marginal_likelihood(params.cluster_params_l.hyperparams, params.cluster_params_l.posterior_hyperparams,
+                                     params.cluster_params_l.suff_statistics)
+    ll_r = P.log_marginal_likelihood(params.cluster_params_r.hyperparams, params.cluster_params_r.posterior_hyperparams,
+                                     params.cluster_params_r.suff_statistics)
+    b = cfg.burnout_period
+    h = params.logsublikelihood_hist
+    h[0:b - 1] = h[1:b].copy()
+    h[b - 1] = ll_l + ll_r
+    with np.errstate(invalid="ignore"):
+        now = float(np.sum(h[:b] * (1 / (b - 0.1))))
+    if now != -np.inf and not np.isnan(now) and now - h[b - 1] < 1e-2:
+        params.splittable = True
+    return params
+
+
+# ---------------------------------------------------------------- local_clusters_actions.jl -------
+def create_first_local_cluster(group, cfg, rng):
+    """:1-20.  The worker call (split_first_cluster_worker!, :16-18) -> randomize_sublabels(all)."""
+    hyper = group.model_hyperparams.distribution_hyper_params
+    suff = P.empty_suff_stats(hyper)
+    dist = P.sample_distribution(hyper, rng)
+    cp = cluster_parameters(hyper, dist, suff, hyper)
+    cpl, cpr = copy.deepcopy(cp), copy.deepcopy(cp)
+    splittable = splittable_cluster_params(cp, cpl, cpr, np.array([0.5, 0.5]), False, _neg_inf_hist(cfg))
+    cp.suff_statistics.N = group.sweep.n
+    cluster = local_cluster(splittable, group.model_hyperparams.total_dim, group.sweep.n, 0, 0)
+    group.sweep.randomize_sublabels(None)
+    return cluster
+
+
+def update_suff_stats_posterior(group, indices=None):
+    """update_suff_stats_posterior! :206-254.  The fetch of the workers' dictionaries and their
+    aggregate_suff_stats reduction (:229-248) is one dpmm_suff_stats call (all-reduce inside)."""
+    if indices is None:
+        indices = list(range(1, len(group.local_clusters) + 1))
+    indices = [int(i) for i in indices]
+    if not indices:
+        return
+    hyper = group.model_hyperparams.distribution_hyper_params
+    counts, sum_x, sum_xx = group.sweep.suff_stats(indices)
+    for a, v in enumerate(indices):
+        cluster = group.local_clusters[v - 1]
+        sp = cluster.cluster_params
+        for s, cp in enumerate((sp.cluster_params, sp.cluster_params_l, sp.cluster_params_r)):
+            cp.suff_statistics = P.make_suff_stats(hyper, counts[a, s], sum_x[a, s], None if sum_xx is None else sum_xx[a, s])
+        cluster.points_count = int(counts[a, 0])                                   # :249
+        for cp in (sp.cluster_params, sp.cluster_params_l, sp.cluster_params_r):   # update_splittable_cluster_params! :137-147
+            cp.posterior_hyperparams = P.calc_posterior(cp.hyperparams, cp.suff_statistics)
+
+
+def sample_clusters(group, first, cfg, rng):
+    """sample_clusters! :417-437."""
+    α = group.model_hyperparams.α
+    points_count = []
+    for cluster in group.local_clusters:
+        cluster.cluster_params = sample_cluster_params(cluster.cluster_params, α, first, cfg, rng)
+        cluster.points_count = int(cluster.cluster_params.cluster_params.suff_statistics.N)
+        points_count.append(cluster.points_count)
+    points_count.append(α)
+    pc = np.maximum(np.asarray(points_count, np.float64), 1e-300)   # Dirichlet needs positive parameters
+    group.weights = (rng.dirichlet(pc)[:-1] * (1 - cfg.outlier_mod)).astype(F32)
+
+
+def broadcast_cluster_params(group):
+    """broadcast_cluster_params :518-549 with create_thin_cluster_params :439-444: pack the thin
+    parameters (3 distributions + lr_weights per cluster) and the weights into one upload."""
+    cl = group.local_clusters
+    K = len(cl)
+    lr = np.array([c.cluster_params.lr_weights for c in cl], F32).reshape(K, 2)
+    trip = [(c.cluster_params.cluster_params.distribution, c.cluster_params.cluster_params_l.distribution,
+             c.cluster_params.cluster_params_r.distribution) for c in cl]
+    w = np.asarray(group.weights, F32)
+    if isinstance(group.model_hyperparams.distribution_hyper_params, P.niw_hyperparams):
+        mu = np.array([[d.μ for d in t] for t in trip], F32)
+        inv = np.array([[d.invΣ for d in t] for t in trip], F32)
+        ld = np.array([[d.logdetΣ for d in t] for t in trip], F32)
+        group.sweep.set_params_niw(mu, inv, ld, w, lr)
+    else:
+        lp = np.array([[d.α for d in t] for t in trip], F32)
+        group.sweep.set_params_multinomial(lp, w, lr)
+
+
+def reset_bad_clusters(group, cfg):
+    """reset_bad_clusters! :501-516."""
+    bad = []
+    for i, c in enumerate(group.local_clusters, start=1):
+        if c.cluster_params.cluster_params_l.suff_statistics.N == 0 or c.cluster_params.cluster_params_r.suff_statistics.N == 0:
+            bad.append(i)
+            c.cluster_params.logsublikelihood_hist = _neg_inf_hist(cfg)
+            c.cluster_params.splittable = False
+    if bad:
+        group.sweep.randomize_sublabels(bad)           # reset_bad_clusters_worker! :481-488
+        update_suff_stats_posterior(group, bad)
+    return bad
+
+
+def should_split_local(cluster_params, α, final, rng):
+    """should_split_local! :318-343."""
+    cpl, cpr, cp = cluster_params.cluster_params_l, cluster_params.cluster_params_r, cluster_params.cluster_params
+    if final or cpl.suff_statistics.N == 0 or cpr.suff_statistics.N == 0:
+        return False
+    post = P.calc_posterior(cp.hyperparams, cp.suff_statistics)
+    lpost = P.calc_posterior(cp.hyperparams, cpl.suff_statistics)
+    rpost = P.calc_posterior(cp.hyperparams, cpr.suff_statistics)
+    ll_l = P.log_marginal_likelihood(cpl.hyperparams, lpost, cpl.suff_statistics)
+    ll_r = P.log_marginal_likelihood(cpr.hyperparams, rpost, cpr.suff_statistics)
+    ll = P.log_marginal_likelihood(cp.hyperparams, post, cp.suff_statistics)
+    log_HR = (np.log(α) + gammaln(cpl.suff_statistics.N) + ll_l + gammaln(cpr.suff_statistics.N) + ll_r
+              - (gammaln(cp.suff_statistics.N) + ll))
+    return log_HR > np.log(rng.random())
+
+
+def check_and_split(group, final, cfg, rng):
+    """check_and_split! :345-382 (+ split_cluster_local! :280-291)."""
+    α = group.model_hyperparams.α
+    K = len(group.local_clusters)
+    split = []
+    for index, cluster in enumerate(group.local_clusters, start=1):
+        if cfg.outlier_mod > 0 and index == 1:
+            continue
+        sp = cluster.cluster_params
+        if sp.splittable and sp.cluster_params.suff_statistics.N > 1 and should_split_local(sp, α, final, rng):
+            split.append(index)
+    indices, new_indices = [], []
+    new_index = K + 1
+    for i in split:
+        cluster = group.local_clusters[i - 1]
+        l_split = copy.deepcopy(cluster)
+        l_split.cluster_params = create_splittable_from_params(cluster.cluster_params.cluster_params_r, α, cfg, rng)
+        cluster.cluster_params = create_splittable_from_params(cluster.cluster_params.cluster_params_l, α, cfg, rng)
+        l_split.points_count = int(l_split.cluster_params.cluster_params.suff_statistics.N)
+        cluster.points_count = int(cluster.cluster_params.cluster_params.suff_statistics.N)
+        group.local_clusters.append(l_split)
+        indices.append(i)
+        new_indices.append(new_index)
+        new_index += 1
+    if indices:
+        group.sweep.apply_split(indices, new_indices)      # split_cluster_local_worker! :265-278
+    return indices + new_indices
+
+
+def check_and_merge(group, final, cfg, rng):
+    """check_and_merge! :385-413 (+ merge_clusters! :308-315)."""
+    α = group.model_hyperparams.α
+    cl = group.local_clusters
+    indices, new_indices = [], []
+    for i in range(len(cl)):
+        if cfg.outlier_mod > 0 and i == 0:
+            continue
+        for j in range(i + 1, len(cl)):
+            ci, cj = cl[i].cluster_params, cl[j].cluster_params
+            if (ci.splittable and cj.splittable and ci.cluster_params.suff_statistics.N > 0
+                    and cj.cluster_params.suff_statistics.N > 0
+                    and should_merge(ci.cluster_params, cj.cluster_params, α, final, rng)):
+                cl[i].cluster_params = merge_clusters_to_splittable(ci.cluster_params, cj.cluster_params, α, cfg, rng)
+                cl[i].points_count += cl[j].points_count
+                cl[j].points_count = 0
+                cl[j].cluster_params.cluster_params.suff_statistics.N = 0
+                cl[j].cluster_params.splittable = False
+                indices.append(i + 1)
+                new_indices.append(j + 1)
+    if indices:
+        group.sweep.apply_merge(indices, new_indices)      # merge_clusters_worker! :293-304
+    return indices
+
+
+def remove_empty_clusters(group, cfg):
+    """remove_empty_clusters! :457-471."""
+    new_vec, pts_count = [], []
+    n = len(group.local_clusters)
+    for index, cluster in enumerate(group.local_clusters, start=1):
+        pts_count.append(int(cluster.points_count))
+        if cluster.points_count > 0 or (cfg.outlier_mod > 0 and index == 1) or (cfg.outlier_mod > 0 and index == 2 and n == 2):
+            new_vec.append(cluster)
+    group.sweep.remove_empty(pts_count)                    # remove_empty_clusters_worker! :446-455
+    group.local_clusters = new_vec
+
+
+def group_step(group, no_more_splits, final, first, cfg, rng):
+    """group_step :658-673."""
+    sample_clusters(group, False, cfg, rng)
+    broadcast_cluster_params(group)
+    group.sweep.sample_labels(True if cfg.hard_clustering else final)   # sample_labels! :98-109
+    group.sweep.sample_sublabels()                                       # sample_sub_clusters! :64-68
+    update_suff_stats_posterior(group)
+    reset_bad_clusters(group, cfg)
+    if not no_more_splits:
+        indices = check_and_split(group, final, cfg, rng)
+        update_suff_stats_posterior(group, indices)
+        check_and_merge(group, final, cfg, rng)
+    remove_empty_clusters(group, cfg)
+
+
+# ---------------------------------------------------------------- dp-parallel-sampling.jl ---------
+def normalized_mutual_info(a, b):
+    """Clustering.mutualinfo(a, b; normed=true): 2 I(a;b) / (H(a) + H(b))."""
+    a = np.asarray(a).astype(np.int64)
+    b = np.asarray(b).astype(np.int64)
+    _, ai = np.unique(a, return_inverse=True)
+    _, bi = np.unique(b, return_inverse=True)
+    n = a.size
+    C = np.zeros((ai.max() + 1, bi.max() + 1))
+    np.add.at(C, (ai, bi), 1)
+    pa, pb, pab = C.sum(1) / n, C.sum(0) / n, C / n
+    nz = pab > 0
+    I = (pab[nz] * np.log(pab[nz] / (pa[:, None] * pb[None, :])[nz])).sum()
+    H = -(pa[pa > 0] * np.log(pa[pa > 0])).sum() - (pb[pb > 0] * np.log(pb[pb > 0])).sum()
+    return float(2 * I / H) if H > 0 else 1.0
+
+
+def calculate_posterior(model):
+    """calculate_posterior :458-470."""
+    α = model.model_hyperparams.α
+    lp = gammaln(α) - gammaln(model.group.sweep.n_total + α)
+    for c in model.group.local_clusters:
+        cp = c.cluster_params.cluster_params
+        if cp.suff_statistics.N == 0:
+            continue
+        lp += P.log_marginal_likelihood(cp.hyperparams, cp.posterior_hyperparams, cp.suff_statistics)
+        lp += np.log(α) + gammaln(cp.suff_statistics.N)
+    return float(lp)
+
+
+def init_model_from_data(all_data, hyper_params, α, cfg, seed, sweep_factory, shard):
+    """init_model_from_data :36-53: `distribute(all_data)` + random labels become dpmm_create +
+    dpmm_init_labels.  `shard` = (global_offset, n_total) when the points are one shard of many."""
+    all_data = np.asarray(all_data, F32)
+    kind = NIW if isinstance(hyper_params, P.niw_hyperparams) else MULTINOMIAL
+    goff, n_total = shard if shard is not None else (0, all_data.shape[1])
+    sweep_seed = int(seed) if seed is not None else int(np.random.default_rng().integers(2 ** 62))
+    sweep = sweep_factory(all_data, kind, sweep_seed, goff)
+    sweep.n_total = n_total
+    mh = model_hyper_params(hyper_params, float(F32(α)), all_data.shape[1])
+    sweep.init_labels(cfg.initial_clusters, cfg.outlier_mod > 0)
+    return dp_parallel_sampling(mh, local_group(mh, sweep))
+
+
+def init_first_clusters(dp_model, cfg, rng):
+    """init_first_clusters! :62-78."""
+    g = dp_model.group
+    for _ in range(cfg.initial_clusters):
+        g.local_clusters.append(create_first_local_cluster(g, cfg, rng))
+    update_suff_stats_posterior(g)
+    sample_clusters(g, False, cfg, rng)
+    g.weights = np.full(len(g.local_clusters), 1.0 / len(g.local_clusters), F32) if len(g.local_clusters) > 1 else np.ones(1, F32)
+    broadcast_cluster_params(g)
+
+
+def run_model(dp_model, first_iter, cfg, rng):
+    """run_model :336-404."""
+    iter_count, nmi_hist, ll_hist, k_hist = [], [], [], []
+    g = dp_model.group
+    for i in range(first_iter, cfg.iterations + 1):
+        final = i >= cfg.iterations - cfg.argmax_sample_stop
+        no_more_splits = (i >= cfg.iterations - cfg.split_stop) or (len(g.local_clusters) >= cfg.max_num_of_clusters)
+        t0 = time.perf_counter()
+        group_step(g, no_more_splits, final, i == 1, cfg, rng)
+        iter_count.append(time.perf_counter() - t0)
+        k_hist.append(len(g.local_clusters))
+        if cfg.ground_truth is not None:
+            nmi_hist.append(normalized_mutual_info(cfg.ground_truth, g.sweep.get_labels()))
+        else:
+            nmi_hist.append("no gt")
+        if cfg.use_verbose:
+            ll_hist.append(calculate_posterior(dp_model))
+            print(f"Iteration: {i} || Clusters count: {k_hist[-1]} || Log posterior: {ll_hist[-1]} || "
+                  f"NMI score: {nmi_hist[-1]} || Iter Time:{iter_count[-1]} || Total time:{sum(iter_count)}")
+        else:
+            ll_hist.append(1)
+    return dp_model, iter_count, nmi_hist, ll_hist, k_hist
+
+
+def _gpu_factory(device=0):
+    def make(x, kind, seed, goff):
+        return GpuSweep(x, kind, seed=seed, global_offset=goff, device=device)
+    return make
+
+
+def dp_parallel(all_data, local_hyper_params, α_param, iters=100, init_clusters=1, seed=None, verbose=True,
+                save_model=False, burnout=15, gt=None, max_clusters=np.inf, outlier_weight=0, outlier_params=None,
+                smart_splits=False, *, sweep_factory=None, shard=None, comm=None, device=0):
+    """dp_parallel :121-157.  `sweep_factory`, `shard`, `comm`, `device` have no reference counterpart:
+    they select the device / inject a test double / attach the multi-GPU communicator."""
+    if outlier_weight or smart_splits or save_model:
+        raise NotImplementedError("outlier component, smart splits and checkpoints are out of scope (DESIGN.md 6)")
+    cfg = Settings(iterations=int(iters), initial_clusters=int(init_clusters), burnout_period=int(burnout),
+                   max_num_of_clusters=max_clusters, use_verbose=bool(verbose), ground_truth=gt)
+    rng = np.random.default_rng(seed)
+    dp_model = init_model_from_data(all_data, local_hyper_params, α_param, cfg, seed,
+                                    sweep_factory or _gpu_factory(device), shard)
+    if comm is not None:
+        dp_model.group.sweep.comm_init(*comm)
+    init_first_clusters(dp_model, cfg, rng)
+    return run_model(dp_model, 1, cfg, rng)
+
+
+def fit(all_data, *args, iters=100, init_clusters=1, seed=None, verbose=False, save_model=False, burnout=20,
+        gt=None, max_clusters=np.inf, outlier_weight=0, outlier_params=None, smart_splits=False, **kw):
+    """fit(all_data, [local_hyper_params,] α_param; ...) :215-293.  Returns the reference's tuple:
+    (labels, clusters, weights, iter_count, nmi_score_history, likelihood_history, cluster_count_history,
+     sub_labels, dp_model)."""
+    all_data = np.asarray(all_data, F32)
+    if len(args) == 1:
+        D = all_data.shape[0]
+        hyper = P.niw_hyperparams(1.0, np.zeros(D), D + 3, np.eye(D))        # :272-274
+        α = args[0]
+    else:
+        hyper, α = args
+    dp_model, iter_count, nmi, ll, kh = dp_parallel(all_data, hyper, α, iters, init_clusters, seed, verbose,
+                                                    save_model, burnout, gt, max_clusters, outlier_weight,
+                                                    outlier_params, smart_splits, **kw)
+    g = dp_model.group
+    return (g.sweep.get_labels(), [c.cluster_params.cluster_params.distribution for c in g.local_clusters],
+            g.weights, iter_count, nmi, ll, kh, g.sweep.get_sublabels(), dp_model)
+
+
+def predict(dp_model, data):
+    """predict / predict_points :23-40, :532-537 (host-only; posterior predictive, hard labels + probs)."""
+    data = np.asarray(data, F32)
+    cl = dp_model.group.local_clusters
+    parr = np.zeros((data.shape[1], len(cl)), F32)
+    for k, c in enumerate(cl):
+        parr[:, k] = P.posterior_predictive(data, c.cluster_params.cluster_params.posterior_hyperparams)
+    with np.errstate(divide="ignore"):
+        parr += np.log(np.asarray(dp_model.group.weights, F32))[None, :]
+    lbls = np.argmax(parr, axis=1) + 1
+    parr = np.where(np.isnan(parr), -np.inf, parr)
+    parr = np.exp(parr - parr.max(axis=1, keepdims=True))
+    return lbls, parr / parr.sum(axis=1, keepdims=True)
+
+
+def get_labels_histogram(labels):
+    """utils.jl:39-48."""
+    v, c = np.unique(np.asarray(labels), return_counts=True)
+    return list(zip(v.tolist(), c.tolist()))

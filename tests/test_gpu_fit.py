@@ -1,0 +1,77 @@
+"""End-to-end fit() on the GPU (C ABI underneath): the reference's own test/module_tests.jl testsets,
+the C1 example of docs/src/getting_started.md, and statistical equivalence with the same host logic
+running on the oracle (NMI / final K over seeds)."""
+import numpy as np
+import pytest
+
+import dpmm_pkg
+from oracle import dpmm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as g
+    g.build()
+    return dpmm_pkg.load()
+
+
+def oracle_factory(x, kind, seed, goff):
+    return O.OracleSweep(x, kind, seed=seed, global_offset=goff)
+
+
+def test_module_deterministic_four_point_masses(pkg):
+    """test/module_tests.jl:10-32."""
+    x = np.zeros((2, 1000), np.float32)
+    x[:, 0:250] = [[-1], [-1]]; x[:, 250:500] = [[-1], [1]]; x[:, 500:750] = [[1], [-1]]; x[:, 750:1000] = [[1], [1]]
+    labels, clusters, weights, *_r, dp_model = pkg.fit(x, 100.0, iters=200, seed=123456789, burnout=15)
+    assert len(clusters) == 4
+    assert all(w >= 0.15 for w in weights)
+    lbls, _ = pkg.predict(dp_model, x)
+    np.testing.assert_array_equal(lbls, labels)
+    assert [c for _, c in pkg.get_labels_histogram(labels)] == [250, 250, 250, 250]
+
+
+def test_module_random_mess(pkg):
+    """test/module_tests.jl:36-47, full size."""
+    x, labels, _, _ = pkg.generate_gaussian_data(10 ** 5, 3, 10, 100.0, np.random.default_rng(0))
+    hyper = pkg.niw_hyperparams(1.0, np.zeros(3), 5, np.eye(3))
+    out = pkg.fit(x, hyper, 1e21, iters=100, seed=12345, gt=labels)
+    assert len(out[1]) > 1
+    assert out[4][-1] > 0.6
+
+
+def test_module_multinomial(pkg):
+    """test/module_tests.jl:49-60 (without save/load)."""
+    x, labels, _ = pkg.generate_mnmm_data(10 ** 3, 100, 20, 50, np.random.default_rng(0))
+    hyper = pkg.multinomial_hyper(np.ones(100, np.float32))
+    out = pkg.fit(x, hyper, 1e5, iters=39, seed=3, gt=labels)
+    assert len(out[1]) > 1
+
+
+def test_c1_getting_started_example(pkg):
+    """BASELINE config C1 / docs/src/getting_started.md:27-37: N=1e4, D=2, K=6, alpha=10, 100 iterations;
+    the documented run ends at K=6 with NMI 1.0."""
+    x, labels, _, _ = pkg.generate_gaussian_data(10 ** 4, 2, 6, 100.0, np.random.default_rng(4))
+    out = pkg.fit(x, 10.0, iters=100, seed=1, gt=labels, burnout=10)
+    k_true = len(np.unique(labels))
+    assert abs(len(out[1]) - k_true) <= 2
+    assert out[4][-1] > 0.9
+
+
+def test_gpu_and_oracle_hosts_statistically_indistinguishable(pkg):
+    """Same host logic, same seeds, workers = GPU vs oracle: NMI against the ground truth and the
+    final K agree across 10 seeds (they share the Philox streams, so most runs coincide exactly)."""
+    from dpmmsubclusters_jl_b200 import host as H
+    x, labels, _, _ = pkg.generate_gaussian_data(3000, 2, 4, 100.0, np.random.default_rng(11))
+    nmi_g, nmi_o, k_g, k_o, same = [], [], [], [], 0
+    for seed in range(10):
+        g = H.fit(x, 10.0, iters=40, seed=seed, gt=labels, burnout=5)
+        o = H.fit(x, 10.0, iters=40, seed=seed, gt=labels, burnout=5, sweep_factory=oracle_factory)
+        nmi_g.append(g[4][-1]); nmi_o.append(o[4][-1]); k_g.append(len(g[1])); k_o.append(len(o[1]))
+        same += int(np.array_equal(g[0], o[0]))
+    print("NMI gpu", np.round(nmi_g, 3), "oracle", np.round(nmi_o, 3), "K gpu", k_g, "oracle", k_o, "identical runs", same)
+    assert abs(np.mean(nmi_g) - np.mean(nmi_o)) < 0.05
+    assert abs(np.mean(k_g) - np.mean(k_o)) <= 1.0
+    assert same >= 5
