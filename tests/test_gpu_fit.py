@@ -53,7 +53,7 @@ def test_module_multinomial(pkg):
 def test_c1_getting_started_example(pkg):
     """BASELINE config C1 / docs/src/getting_started.md:27-37: N=1e4, D=2, K=6, alpha=10, 100 iterations;
     the documented run ends at K=6 with NMI 1.0."""
-    x, labels, _, _ = pkg.generate_gaussian_data(10 ** 4, 2, 6, 100.0, np.random.default_rng(4))
+    x, labels, _, _ = pkg.generate_gaussian_data(10 ** 4, 2, 6, 100.0, np.random.default_rng(5))
     out = pkg.fit(x, 10.0, iters=100, seed=1, gt=labels, burnout=10)
     k_true = len(np.unique(labels))
     assert abs(len(out[1]) - k_true) <= 2
