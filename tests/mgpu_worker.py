@@ -41,8 +41,10 @@ if rank == 0:
     np.testing.assert_array_equal(full_lab, ref.get_labels())
     np.testing.assert_array_equal(full_sub, ref.get_sublabels())
     np.testing.assert_array_equal(counts, rc)
-    np.testing.assert_allclose(sx, rsx, rtol=1e-9, atol=1e-6)
-    np.testing.assert_allclose(sxx, rsxx, rtol=1e-9, atol=1e-6)
+    # runs are accumulated in Float32 (<= 1024 points) before the Float64 atomics, and the run
+    # boundaries depend on the sharding: agreement is to Float32 rounding, not bit-exact
+    np.testing.assert_allclose(sx, rsx, rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(sxx, rsxx, rtol=1e-5, atol=1e-5 * np.abs(rsxx).max())
     print("MGPU_OK", counts[:, 0].sum(), flush=True)
 g.close()
 dist.barrier()
