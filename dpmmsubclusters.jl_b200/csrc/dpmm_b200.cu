@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "kernels_gauss.cuh"
+#include "kernels_gauss_tc.cuh"
 #include "kernels_mnm.cuh"
 #include "kernels_sort.cuh"
 #include "kernels_stats.cuh"
@@ -84,6 +85,15 @@ struct dpmm_ctx {
   float* cst = nullptr;   // [3K]
   float* logw = nullptr;  // [K]
   float* loglr = nullptr; // [2K]
+  // tensor-core label path (NIW, D == 32): stacked K-major factors, U mu, mu, |U|_F, TMA descriptor of X
+  float* tc_w = nullptr;
+  float* tc_b = nullptr;
+  float* tc_mu = nullptr;
+  float* tc_fro = nullptr;
+  int32_t* tc_stats = nullptr;
+  CUtensorMap tmap_x;
+  bool tc_ok = false;       // tensor map built
+  bool tc_params = false;   // tc_* describe the current parameters
   float* logp_t = nullptr;  // multinomial [D][KP]
   int KP = 0;
   int32_t* hist = nullptr;
@@ -213,6 +223,14 @@ static int ensure_k(dpmm_ctx* ctx, int K) {
   CK(dev_realloc(&ctx->logw, (size_t)cap));
   CK(dev_realloc(&ctx->loglr, (size_t)2 * cap));
   if (ctx->prior == DPMM_PRIOR_MULTINOMIAL) CK(dev_realloc(&ctx->logp_t, (size_t)D * (cap + MNM_KT)));
+  if (ctx->tc_ok) {
+    const int capc = std::min(cap, TC_MAX_K);
+    CK(dev_realloc(&ctx->tc_w, (size_t)((capc + TC_NCL - 1) / TC_NCL) * 256 * TC_D));
+    CK(dev_realloc(&ctx->tc_b, (size_t)capc * TC_D));
+    CK(dev_realloc(&ctx->tc_mu, (size_t)capc * TC_D));
+    CK(dev_realloc(&ctx->tc_fro, (size_t)capc));
+    ctx->tc_params = false;
+  }
   CK(dev_realloc(&ctx->hist, (size_t)cap));
   CK(dev_realloc(&ctx->seg_off, (size_t)cap + 1));
   CK(dev_realloc(&ctx->scat_cursor, (size_t)cap));
@@ -428,6 +446,26 @@ extern "C" int dpmm_create(dpmm_ctx** out, const float* x, int64_t n_local, int3
   CKC(cudaMemsetAsync(ctx->labels, 0, (size_t)n_local * sizeof(int32_t), ctx->stream));
   CKC(cudaMemsetAsync(ctx->sub, 0, (size_t)n_local, ctx->stream));
   CKC(cudaStreamSynchronize(ctx->stream));
+  if (prior_kind == DPMM_PRIOR_NIW && d == TC_D && n_local >= TC_TILE) {
+    // TMA descriptor of X as a [n][32] float tensor, 128-point boxes, 128B swizzle (K2 operand A)
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn != nullptr &&
+        qres == cudaDriverEntryPointSuccess) {
+      const cuuint64_t gdim[2] = {(cuuint64_t)TC_D, (cuuint64_t)n_local};
+      const cuuint64_t gstr[1] = {(cuuint64_t)TC_D * 4};
+      const cuuint32_t box[2] = {TC_D, TC_TILE};
+      const cuuint32_t estr[2] = {1, 1};
+      const CUresult r = ((EncodeFn)fn)(&ctx->tmap_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ctx->x, gdim, gstr, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      ctx->tc_ok = (r == CUDA_SUCCESS);
+    }
+    if (ctx->tc_ok) CKC(cudaMalloc((void**)&ctx->tc_stats, 2 * sizeof(int32_t)));
+  }
 #undef CKC
   ctx->chunk = 1024;
   *out = ctx;
@@ -445,7 +483,7 @@ extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
   }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   void* ptrs[] = {ctx->x, ctx->labels, ctx->sub, ctx->perm, ctx->perm2, ctx->u_label, ctx->u_sub, ctx->r_bits,
-                  ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->hist, ctx->seg_off,
+                  ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->tc_w, ctx->tc_b, ctx->tc_mu, ctx->tc_fro, ctx->tc_stats, ctx->hist, ctx->seg_off,
                   ctx->scat_cursor, ctx->lr_cursor, ctx->lut_l, ctx->lut_r, ctx->rule, ctx->wanted,
                   ctx->idx_list, ctx->acc, ctx->outbuf, ctx->items, ctx->item_ctr};
   for (void* p : ptrs)
@@ -755,7 +793,10 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
   if (rc) return rc;
   const int D = ctx->D, REC = ctx->rec_f, TRIP = gauss_col_off(D);
   const size_t nrec = (size_t)3 * K;
-  const size_t bytes = (nrec * REC + nrec + K + 2 * K) * sizeof(float);
+  const bool tcp = ctx->tc_ok && K <= TC_MAX_K;
+  const int nch = (K + TC_NCL - 1) / TC_NCL;
+  const size_t tc_floats = tcp ? (size_t)nch * 256 * TC_D + (size_t)2 * K * TC_D + K : 0;
+  const size_t bytes = (nrec * REC + nrec + K + 2 * K + tc_floats) * sizeof(float);
   rc = ensure_stage(ctx, bytes);
   if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));  // staging buffer reuse
@@ -763,6 +804,11 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
   float* h_cst = h_recs + nrec * REC;
   float* h_logw = h_cst + nrec;
   float* h_loglr = h_logw + K;
+  float* h_w = h_loglr + 2 * K;                       // [nch][256][32]
+  float* h_b = h_w + (tcp ? (size_t)nch * 256 * TC_D : 0);
+  float* h_mu = h_b + (tcp ? (size_t)K * TC_D : 0);
+  float* h_fro = h_mu + (tcp ? (size_t)K * TC_D : 0);
+  if (tcp) std::fill(h_w, h_w + (size_t)nch * 256 * TC_D, 0.f);
   std::vector<double> L((size_t)D * D);
   const float log2pi = (float)std::log(2.0 * M_PI);  // Float32(log(2pi)), mv_gaussian.jl:24
   for (size_t t = 0; t < nrec; ++t) {
@@ -792,12 +838,36 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
     }
     for (int j = 0; j < D; ++j) rec[TRIP + j] = mu[t * D + j];
     h_cst[t] = ((float)(D * D) * log2pi + logdet[t]) / 2.f;
+    if (tcp && t % 3 == 0) {  // K2 operands of the cluster distribution: rows of U, U mu, mu, |U|_F
+      const int k = (int)(t / 3);
+      double fro = 0.0;
+      for (int i = 0; i < D; ++i) {
+        double bi = 0.0;
+        for (int j = i; j < D; ++j) {
+          const float u = ok ? (float)L[(size_t)j * D + i] : NAN;
+          h_w[((size_t)k * D + i) * D + j] = u;
+          bi += (double)u * (double)mu[t * D + j];
+          fro += (double)u * (double)u;
+        }
+        h_b[(size_t)k * D + i] = (float)bi;
+        h_mu[(size_t)k * D + i] = mu[t * D + i];
+      }
+      h_fro[k] = (float)std::sqrt(fro);
+    }
   }
   common_weights(ctx, K, weights, lr_weights, h_logw, h_loglr);
   CK(cudaMemcpyAsync(ctx->recs, h_recs, nrec * REC * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->cst, h_cst, nrec * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->logw, h_logw, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->loglr, h_loglr, (size_t)2 * K * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->tc_params = false;
+  if (tcp) {
+    CK(cudaMemcpyAsync(ctx->tc_w, h_w, (size_t)nch * 256 * TC_D * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->tc_b, h_b, (size_t)K * TC_D * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->tc_mu, h_mu, (size_t)K * TC_D * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->tc_fro, h_fro, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->tc_params = true;
+  }
   ctx->K = K;
   ctx->params_set = true;
   return 0;
@@ -846,7 +916,23 @@ static int run_sample_labels(dpmm_ctx* ctx, int final_iter, float* dump) {
   const int K = ctx->K;
   ctx->call += 1;
   CK(cudaMemsetAsync(ctx->hist, 0, (size_t)K * 4, ctx->stream));
-  if (ctx->prior == DPMM_PRIOR_NIW) {
+  if (ctx->prior == DPMM_PRIOR_NIW && ctx->tc_params && dump == nullptr && ctx->sampler == DPMM_SAMPLER_INVERSE_CDF &&
+      env_int("DPMM_LABEL_TC", 1) != 0) {
+    // K2: tcgen05 TF32 screen + FP32 refine
+    GaussTcArgs a{};
+    a.n = ctx->n; a.K = K; a.wmat = ctx->tc_w; a.bvec = ctx->tc_b; a.mu = ctx->tc_mu; a.cst = ctx->cst; a.logw = ctx->logw;
+    a.fro = ctx->tc_fro; a.labels = ctx->labels; a.hist = ctx->hist; a.u_inj = ctx->u_label; a.seed = ctx->seed;
+    a.call = ctx->call; a.goff = ctx->goff; a.final_iter = final_iter; a.ntiles = (ctx->n + TC_TILE - 1) / TC_TILE;
+    a.stats = env_int("DPMM_TC_STATS", 0) ? ctx->tc_stats : nullptr;
+    const size_t sm = gauss_tc_smem_bytes(K);
+    NEED(sm <= (size_t)ctx->smem_optin, DPMM_ELIMIT, "internal: tensor-core label kernel does not fit shared memory");
+    CK(cudaFuncSetAttribute(gauss_label_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const int64_t grid = std::min<int64_t>((a.ntiles + 1) / 2, (int64_t)ctx->sm_count);
+    if (a.stats) CK(cudaMemsetAsync(ctx->tc_stats, 0, 8, ctx->stream));
+    KernelTimer kt(ctx, TK_LABEL);
+    gauss_label_tc_kernel<<<(unsigned)grid, TC_THREADS, sm, ctx->stream>>>(ctx->tmap_x, a);
+    CK(cudaGetLastError());
+  } else if (ctx->prior == DPMM_PRIOR_NIW) {
     GaussLabelArgs a{};
     a.x = ctx->x; a.n = ctx->n; a.K = K; a.recs = ctx->recs; a.cst = ctx->cst; a.logw = ctx->logw;
     a.labels = ctx->labels; a.hist = ctx->hist; a.u_inj = ctx->u_label; a.seed = ctx->seed; a.call = ctx->call;
@@ -1124,6 +1210,19 @@ extern "C" int dpmm_debug_loglik(dpmm_ctx* ctx, int32_t which, float* out) {
   }
   cudaFree(dump);
   return rc;
+}
+
+extern "C" int dpmm_debug_tc_stats(dpmm_ctx* ctx, int64_t* out2) {
+  NEED(ctx && out2, DPMM_EINVAL, "NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  out2[0] = out2[1] = 0;
+  if (ctx->tc_stats == nullptr) return 0;
+  int32_t h[2] = {0, 0};
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(h, ctx->tc_stats, 8, cudaMemcpyDeviceToHost));
+  out2[0] = h[0];
+  out2[1] = h[1];
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,407 @@
+// K2: tensor-core form of the fused Gaussian log-likelihood + label draw (D = 32).
+//
+//   sample_labels_worker!        src/local_clusters_actions.jl:112-134
+//   log_likelihood!(mv_gaussian) src/distributions/mv_gaussian.jl:21-25
+//   sample_log_cat_array!        src/utils.jl:19-31
+//
+// TF32 screen + FP32 refine (the "error-compensated TF32/FP32 split" of the north star, organised so
+// that every value that can influence a draw is an exact-FP32 reference value):
+//
+//  1. SCREEN on tcgen05: for a tile of 128 points (TMA, 128B-swizzled) and 8 clusters at a time,
+//     Y[128 x 256] = X[128 x 32] . W^T with W = the 8 upper-triangular factors U_k stacked K-major in
+//     shared memory, accumulated in TMEM (kind::tf32, 4 k-steps).  The epilogue warps read the
+//     accumulator with tcgen05.ld and form q~_k = |U_k x - U_k mu_k|^2 per (point, cluster).
+//     TF32 keeps 10 mantissa bits of x, so q~ carries an error that is BOUNDED per point:
+//       |y~ - y|_2 <= e_k := 2^-9 |U_k|_F |x|_2   =>   |q~_k - q_k| <= 2 sqrt(q~_k) e_k + e_k^2.
+//  2. REFINE on the FMA pipe: cluster k is a candidate of the point iff its upper bound reaches
+//     within DELTA = 30 of the best lower bound.  Only candidates (typically 1-2 of K) are evaluated
+//     exactly -- z = x - mu in Float32, |U z|^2 with packed FFMA2, r = -c - q/2 + log w, the
+//     reference's own operations -- and only they enter the draw.  A non-candidate has
+//     p_k < e^-30 ~ 1e-13 of the largest term; dropping it moves no cumulative boundary by more
+//     than 1e-13, eight orders of magnitude inside the documented near-tie band.
+//     Points with a NaN/Inf screen value fall back to "all clusters are candidates".
+//
+// Warp roles (one persistent CTA per SM, 320 threads): warps 0/1 = control warp of point-group
+// 0/1 (TMA producer + tcgen05.mma issuer), warps 2-5 / 6-9 = epilogue+refine+draw warps of group
+// 0/1 (thread = TMEM lane = point).  The two groups work on alternating tiles so that the tensor
+// pipe, the TMEM loads and the FMA-bound refinement of different tiles overlap.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels_gauss.cuh"
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "LAB_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LAB_DONE_%=;\n\t"
+      "bra LAB_WAIT_%=;\n\t"
+      "LAB_DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] . B[smem]^T, both operands K-major, TF32 inputs, FP32 accumulate.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread = lane).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand stored as rows of 128 bytes with the 128B swizzle
+// (8-row groups 1024 B apart): start address, LBO = 1 (ignored), SBO = 1024 B, version 1, SWIZZLE_128B.
+__device__ __forceinline__ uint64_t smem_desc_k128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// Instruction descriptor: FP32 accumulator, TF32 A and B, both K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+}  // namespace tc
+
+#define TC_D 32
+#define TC_TILE 128                 // points per tile = TMEM lanes
+#define TC_NCL 8                    // clusters per MMA chunk (8 * 32 = 256 accumulator columns)
+#define TC_CHUNK_BYTES (256 * TC_D * 4)
+#define TC_STAGE_BYTES (TC_TILE * TC_D * 4)
+#define TC_THREADS 320
+#define TC_MAX_K 24
+#define TC_DELTA 30.0f
+
+struct GaussTcArgs {
+  int64_t n;
+  int K;
+  const float* wmat;   // [NCH][256][32] factors U_k, rows (k_local, i), zero padded
+  const float* bvec;   // [K][32]  U_k mu_k
+  const float* mu;     // [K][32]
+  const float* cst;    // [3K]   c of every distribution (cluster dist = 3k)
+  const float* logw;   // [K]
+  const float* fro;    // [K]    |U_k|_F
+  int32_t* labels;
+  int32_t* hist;
+  const double* u_inj;
+  uint64_t seed;
+  uint32_t call;
+  int64_t goff;
+  int final_iter;
+  int64_t ntiles;
+  int32_t* stats;      // optional [2]: #points, #candidate evaluations (diagnostics)
+};
+
+static inline size_t gauss_tc_smem_bytes(int K) {
+  const int nch = (K + TC_NCL - 1) / TC_NCL;
+  size_t b = 1024;                                   // alignment slack
+  b += (size_t)nch * TC_CHUNK_BYTES;                 // W
+  b += 4 * (size_t)TC_STAGE_BYTES;                   // X stages (2 per group)
+  b += (size_t)K * TC_D * 4 * 2;                     // b, mu
+  b += (size_t)K * 4 * 4;                            // c, log w, |U|_F, (pad)
+  b += 2 * (size_t)K * TC_TILE * 4;                  // rs per group
+  b += (size_t)((K + 3) & ~3) * 4;                   // hist
+  b += 16 * 8 + 16;                                  // barriers + tmem pointer
+  return b;
+}
+
+// exact q = |U_k (x - mu_k)|^2 from the K-major (row = i) swizzled factor rows in shared memory
+__device__ __forceinline__ float gauss_tc_exact_q(const float* wk, const float* mu, const float (&x)[TC_D]) {
+  f32x2_t z2[TC_D / 2];
+#pragma unroll
+  for (int c = 0; c < TC_D / 4; ++c) {
+    const float4 m = *reinterpret_cast<const float4*>(mu + 4 * c);
+    z2[2 * c] = f2_pack(x[4 * c] - m.x, x[4 * c + 1] - m.y);
+    z2[2 * c + 1] = f2_pack(x[4 * c + 2] - m.z, x[4 * c + 3] - m.w);
+  }
+  float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < TC_D; ++i) {
+    const float* row = wk + i * TC_D;
+    f32x2_t acc = 0ull;
+#pragma unroll
+    for (int c = i >> 2; c < TC_D / 4; ++c) {
+      const ulonglong2 u = *reinterpret_cast<const ulonglong2*>(row + ((c ^ (i & 7)) << 2));
+      acc = f2_fma(u.x, z2[2 * c], acc);
+      acc = f2_fma(u.y, z2[2 * c + 1], acc);
+    }
+    float lo, hi;
+    f2_unpack(acc, lo, hi);
+    const float y = lo + hi;
+    if (i & 1) q1 = fmaf(y, y, q1); else q0 = fmaf(y, y, q0);
+  }
+  return q0 + q1;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int K = a.K;
+  const int nch = (K + TC_NCL - 1) / TC_NCL;
+  float* wsm = reinterpret_cast<float*>(base);
+  uint8_t* stage0 = base + (size_t)nch * TC_CHUNK_BYTES;
+  float* bsm = reinterpret_cast<float*>(stage0 + 4 * TC_STAGE_BYTES);
+  float* musm = bsm + K * TC_D;
+  float* csm = musm + K * TC_D;       // c_k
+  float* lwsm = csm + K;              // log w_k
+  float* frosm = lwsm + K;            // |U_k|_F
+  float* rs_all = frosm + 2 * K;      // [2][K][128]
+  int* hs = reinterpret_cast<int*>(rs_all + 2 * K * TC_TILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hs + ((K + 3) & ~3));
+  uint64_t* full = bars;              // [4]  TMA landed
+  uint64_t* empty = bars + 4;         // [4]  stage released by its 128 consumers
+  uint64_t* tfull = bars + 8;         // [2]  accumulator chunk ready
+  uint64_t* tempty = bars + 10;       // [2]  accumulator chunk drained
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) {
+      tc::mbar_init(&full[i], 1);
+      tc::mbar_init(&empty[i], 128);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&tfull[i], 1);
+      tc::mbar_init(&tempty[i], 128);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
+  // ---- stage the factors once per CTA, applying the 128B swizzle the MMA descriptor expects ----
+  for (int e = tid; e < nch * 256 * (TC_D / 4); e += TC_THREADS) {
+    const int r = e >> 3, c = e & 7;  // row (within the stacked chunks), 16-byte chunk
+    const float4 v = __ldg(reinterpret_cast<const float4*>(a.wmat) + e);
+    *reinterpret_cast<float4*>(wsm + (size_t)r * TC_D + ((c ^ (r & 7)) << 2)) = v;
+  }
+  for (int e = tid; e < K * TC_D; e += TC_THREADS) {
+    bsm[e] = __ldg(a.bvec + e);
+    musm[e] = __ldg(a.mu + e);
+  }
+  for (int k = tid; k < K; k += TC_THREADS) {
+    csm[k] = __ldg(a.cst + 3 * k);
+    lwsm[k] = __ldg(a.logw + k);
+    frosm[k] = __ldg(a.fro + k);
+    hs[k] = 0;
+  }
+  tc::fence_proxy_async();  // generic-proxy writes of W must be visible to the tensor core's async proxy
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < 2) {
+    // =============================== control warp of group g ===============================
+    const int g = warp;
+    if (lane == 0) {
+      const uint32_t tmem_d = tmem_base + g * 256;
+      int li = 0;
+      uint32_t tcount = 0;
+      int64_t tile = (int64_t)blockIdx.x + (int64_t)g * gridDim.x;
+      const int64_t tstep = 2 * (int64_t)gridDim.x;
+      if (tile < a.ntiles) {  // prologue: first tile of this group
+        tc::mbar_arrive_expect_tx(&full[g * 2], TC_STAGE_BYTES);
+        tc::tma_load_2d(stage0 + (size_t)(g * 2) * TC_STAGE_BYTES, &tmap_x, &full[g * 2], 0, (int)(tile * TC_TILE));
+      }
+      for (; tile < a.ntiles; tile += tstep, ++li) {
+        const int s = g * 2 + (li & 1);
+        tc::mbar_wait(&full[s], (li >> 1) & 1);
+        tc::tc_fence_after();
+        const uint64_t adesc = tc::smem_desc_k128(tc::smem_u32(stage0 + (size_t)s * TC_STAGE_BYTES));
+        for (int c = 0; c < nch; ++c, ++tcount) {
+          tc::mbar_wait(&tempty[g], (tcount & 1) ^ 1);   // epilogue drained the previous chunk
+          tc::tc_fence_after();
+          const int ncl = min(TC_NCL, K - c * TC_NCL);
+          const uint64_t bdesc = tc::smem_desc_k128(tc::smem_u32(wsm) + c * TC_CHUNK_BYTES);
+          const uint32_t idesc = tc::idesc_tf32(ncl * TC_D);
+#pragma unroll
+          for (int ks = 0; ks < TC_D / 8; ++ks)   // 32-byte k-steps inside the 128-byte swizzled rows
+            tc::umma_tf32(tmem_d, adesc + ks * 2, bdesc + ks * 2, idesc, ks > 0 ? 1u : 0u);
+          tc::umma_commit(&tfull[g]);
+        }
+        // prefetch this group's next tile into its other stage (freed when tile li-1 was finished)
+        const int64_t nt = tile + tstep;
+        if (nt < a.ntiles) {
+          const int ns = g * 2 + ((li + 1) & 1);
+          tc::mbar_wait(&empty[ns], (((li + 1) >> 1) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(&full[ns], TC_STAGE_BYTES);
+          tc::tma_load_2d(stage0 + (size_t)ns * TC_STAGE_BYTES, &tmap_x, &full[ns], 0, (int)(nt * TC_TILE));
+        }
+      }
+    }
+  } else {
+    // ======================= epilogue + refine + draw warps of group g =======================
+    const int g = (warp - 2) >> 2;
+    const int row = ((warp & 3) << 5) | lane;              // TMEM lane == point within the tile
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) << 5) << 16) + g * 256;
+    float* rs = rs_all + (size_t)g * K * TC_TILE + row;    // element k at rs[k * 128]
+    int li = 0;
+    uint32_t tcount = 0;
+    int ncand_total = 0, npts_total = 0;
+    for (int64_t tile = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; tile < a.ntiles; tile += 2 * (int64_t)gridDim.x, ++li) {
+      const int s = g * 2 + (li & 1);
+      // ---- screen: q~_k for every cluster from the TMEM accumulators ----
+      for (int c = 0; c < nch; ++c, ++tcount) {
+        tc::mbar_wait(&tfull[g], tcount & 1);
+        tc::tc_fence_after();
+        const int ncl = min(TC_NCL, K - c * TC_NCL);
+        for (int kl = 0; kl < ncl; ++kl) {
+          uint32_t v[32];
+          tc::tmem_ld32(tmem_row + kl * TC_D, v);
+          tc::tmem_ld_wait();
+          const float* bk = bsm + (c * TC_NCL + kl) * TC_D;
+          f32x2_t acc = 0ull;
+#pragma unroll
+          for (int j = 0; j < TC_D / 4; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bk + 4 * j);
+            const float d0 = __uint_as_float(v[4 * j]) - b4.x, d1 = __uint_as_float(v[4 * j + 1]) - b4.y;
+            const float d2 = __uint_as_float(v[4 * j + 2]) - b4.z, d3 = __uint_as_float(v[4 * j + 3]) - b4.w;
+            const f32x2_t p0 = f2_pack(d0, d1), p1 = f2_pack(d2, d3);
+            acc = f2_fma(p0, p0, acc);
+            acc = f2_fma(p1, p1, acc);
+          }
+          float lo, hi;
+          f2_unpack(acc, lo, hi);
+          rs[(c * TC_NCL + kl) * TC_TILE] = lo + hi;
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(&tempty[g]);
+      }
+      // ---- the point itself (the TMA wrote it with the 128B swizzle) ----
+      tc::mbar_wait(&full[s], (li >> 1) & 1);
+      const int64_t i = tile * TC_TILE + row;
+      const bool valid = i < a.n;
+      float x[TC_D];
+      {
+        const float* xrow = reinterpret_cast<const float*>(stage0 + (size_t)s * TC_STAGE_BYTES) + row * TC_D;
+        float xn = 0.f;
+#pragma unroll
+        for (int c = 0; c < TC_D / 4; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(xrow + ((c ^ (row & 7)) << 2));
+          x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+          xn = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, xn))));
+        }
+        // ---- candidates: upper bound of r_k within DELTA of the best lower bound ----
+        const float xnorm = sqrtf(xn) * (1.f / 512.f);   // 2^-9 |x|
+        float best_lo = -CUDART_INF_F;
+        bool weird = false;
+        for (int k = 0; k < K; ++k) {
+          const float qt = rs[k * TC_TILE];
+          const float e = xnorm * frosm[k];
+          const float dr = 0.5f * (2.f * sqrtf(fmaxf(qt, 0.f)) * e + e * e) + 0.01f;
+          const float rt = lwsm[k] - csm[k] - 0.5f * qt;
+          weird |= !(fabsf(rt) < CUDART_INF_F) || !(dr < CUDART_INF_F);
+          best_lo = fmaxf(best_lo, rt - dr);
+        }
+        uint32_t mask = 0;
+        for (int k = 0; k < K; ++k) {
+          const float qt = rs[k * TC_TILE];
+          const float e = xnorm * frosm[k];
+          const float dr = 0.5f * (2.f * sqrtf(fmaxf(qt, 0.f)) * e + e * e) + 0.01f;
+          const float rt = lwsm[k] - csm[k] - 0.5f * qt;
+          if (weird || rt + dr >= best_lo - TC_DELTA) mask |= 1u << k;
+        }
+        if (!valid) mask = 0;
+        // ---- refine: exact Float32 reference value for every candidate, -Inf for the rest ----
+        for (int k = 0; k < K; ++k) {
+          const bool mine = (mask >> k) & 1u;
+          if (__any_sync(0xffffffffu, mine)) {
+            float r = -CUDART_INF_F;
+            if (mine) {
+              const float q = gauss_tc_exact_q(wsm + (size_t)k * TC_D * TC_D, musm + k * TC_D, x);
+              r = gauss_finish(csm[k], q, lwsm[k]);
+              ++ncand_total;
+            }
+            rs[k * TC_TILE] = r;
+          } else {
+            rs[k * TC_TILE] = -CUDART_INF_F;
+          }
+        }
+      }
+      // the stage can be refilled now: x lives in registers
+      tc::mbar_arrive(&empty[s]);
+      // ---- draw ----
+      if (valid) {
+        int lab;
+        if (a.final_iter) {
+          lab = dpmm_draw_argmax(rs, TC_TILE, K);
+        } else {
+          const double u = dpmm_uniform(a.u_inj, i, a.seed, DPMM_STREAM_LABEL, a.call, (uint64_t)(a.goff + i));
+          lab = dpmm_draw_inverse_cdf(rs, TC_TILE, K, u);
+        }
+        a.labels[i] = lab;
+        atomicAdd(&hs[lab], 1);
+        ++npts_total;
+      }
+    }
+    if (a.stats != nullptr) {
+      atomicAdd(&a.stats[0], npts_total);
+      atomicAdd(&a.stats[1], ncand_total);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+  for (int k = tid; k < K; k += TC_THREADS)
+    if (hs[k] != 0) atomicAdd(&a.hist[k], hs[k]);
+}

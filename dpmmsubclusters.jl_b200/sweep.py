@@ -190,6 +190,11 @@ class GpuSweep:
         self._ck(self.lib.dpmm_debug_loglik(self.h, int(which), _ptr(out, C.c_float)))
         return np.ascontiguousarray(out.T)  # n x cols, as the reference's parr
 
+    def tc_stats(self):
+        out = np.zeros(2, np.int64)
+        self._ck(self.lib.dpmm_debug_tc_stats(self.h, _ptr(out, C.c_int64)))
+        return int(out[0]), int(out[1])
+
     def timing_enable(self, on=True):
         self._ck(self.lib.dpmm_timing_enable(self.h, 1 if on else 0))
 

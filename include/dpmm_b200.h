@@ -144,6 +144,9 @@ int dpmm_set_uniforms(dpmm_ctx* ctx, const double* u_label, const double* u_sub,
  * which=1: out float32 [n_local x 2] = the l/r matrix of create_subclusters_labels! (:89-93) under
  * each point's current label. */
 int dpmm_debug_loglik(dpmm_ctx* ctx, int32_t which, float* out);
+/* Tensor-core label path diagnostics (set DPMM_TC_STATS=1): out[0] = points drawn, out[1] = exact
+ * (FP32-refined) cluster evaluations of the last dpmm_sample_labels; both 0 when the FMA path ran. */
+int dpmm_debug_tc_stats(dpmm_ctx* ctx, int64_t* out2);
 /* Per-kernel device timing (CUDA events around every launch) for roofline reporting. */
 int dpmm_timing_enable(dpmm_ctx* ctx, int32_t on);
 int dpmm_timing_kinds(void);
