@@ -225,7 +225,7 @@ static int ensure_k(dpmm_ctx* ctx, int K) {
   if (ctx->prior == DPMM_PRIOR_MULTINOMIAL) CK(dev_realloc(&ctx->logp_t, (size_t)D * (cap + MNM_KT)));
   if (ctx->tc_ok) {
     const int capc = std::min(cap, TC_MAX_K);
-    CK(dev_realloc(&ctx->tc_w, (size_t)((capc + TC_NCL - 1) / TC_NCL) * 256 * TC_D));
+    CK(dev_realloc(&ctx->tc_w, (size_t)((capc + TC_NCL - 1) / TC_NCL) * TC_NCL * TC_D * TC_D));
     CK(dev_realloc(&ctx->tc_b, (size_t)capc * TC_D));
     CK(dev_realloc(&ctx->tc_mu, (size_t)capc * TC_D));
     CK(dev_realloc(&ctx->tc_fro, (size_t)capc));
@@ -795,7 +795,8 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
   const size_t nrec = (size_t)3 * K;
   const bool tcp = ctx->tc_ok && K <= TC_MAX_K;
   const int nch = (K + TC_NCL - 1) / TC_NCL;
-  const size_t tc_floats = tcp ? (size_t)nch * 256 * TC_D + (size_t)2 * K * TC_D + K : 0;
+  const size_t wfl = (size_t)nch * TC_NCL * TC_D * TC_D;   // factor floats incl. zero padding
+  const size_t tc_floats = tcp ? wfl + (size_t)2 * K * TC_D + K : 0;
   const size_t bytes = (nrec * REC + nrec + K + 2 * K + tc_floats) * sizeof(float);
   rc = ensure_stage(ctx, bytes);
   if (rc) return rc;
@@ -804,11 +805,11 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
   float* h_cst = h_recs + nrec * REC;
   float* h_logw = h_cst + nrec;
   float* h_loglr = h_logw + K;
-  float* h_w = h_loglr + 2 * K;                       // [nch][256][32]
-  float* h_b = h_w + (tcp ? (size_t)nch * 256 * TC_D : 0);
+  float* h_w = h_loglr + 2 * K;                       // [nch * 4][32][32]
+  float* h_b = h_w + (tcp ? wfl : 0);
   float* h_mu = h_b + (tcp ? (size_t)K * TC_D : 0);
   float* h_fro = h_mu + (tcp ? (size_t)K * TC_D : 0);
-  if (tcp) std::fill(h_w, h_w + (size_t)nch * 256 * TC_D, 0.f);
+  if (tcp) std::fill(h_w, h_w + wfl, 0.f);
   std::vector<double> L((size_t)D * D);
   const float log2pi = (float)std::log(2.0 * M_PI);  // Float32(log(2pi)), mv_gaussian.jl:24
   for (size_t t = 0; t < nrec; ++t) {
@@ -862,7 +863,7 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
   CK(cudaMemcpyAsync(ctx->loglr, h_loglr, (size_t)2 * K * 4, cudaMemcpyHostToDevice, ctx->stream));
   ctx->tc_params = false;
   if (tcp) {
-    CK(cudaMemcpyAsync(ctx->tc_w, h_w, (size_t)nch * 256 * TC_D * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->tc_w, h_w, wfl * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->tc_b, h_b, (size_t)K * TC_D * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->tc_mu, h_mu, (size_t)K * TC_D * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->tc_fro, h_fro, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -924,7 +925,7 @@ static int run_sample_labels(dpmm_ctx* ctx, int final_iter, float* dump) {
     a.fro = ctx->tc_fro; a.labels = ctx->labels; a.hist = ctx->hist; a.u_inj = ctx->u_label; a.seed = ctx->seed;
     a.call = ctx->call; a.goff = ctx->goff; a.final_iter = final_iter; a.ntiles = (ctx->n + TC_TILE - 1) / TC_TILE;
     a.stats = env_int("DPMM_TC_STATS", 0) ? ctx->tc_stats : nullptr;
-    const size_t sm = gauss_tc_smem_bytes(K);
+    const size_t sm = GaussTcSmem(K).total;
     NEED(sm <= (size_t)ctx->smem_optin, DPMM_ELIMIT, "internal: tensor-core label kernel does not fit shared memory");
     CK(cudaFuncSetAttribute(gauss_label_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const int64_t grid = std::min<int64_t>((a.ntiles + 1) / 2, (int64_t)ctx->sm_count);

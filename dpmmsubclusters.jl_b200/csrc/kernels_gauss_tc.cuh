@@ -124,8 +124,8 @@ __device__ __forceinline__ uint32_t idesc_tf32(int n) {
 
 #define TC_D 32
 #define TC_TILE 128                 // points per tile = TMEM lanes
-#define TC_NCL 8                    // clusters per MMA chunk (8 * 32 = 256 accumulator columns)
-#define TC_CHUNK_BYTES (256 * TC_D * 4)
+#define TC_NCL 4                    // clusters per MMA chunk (4 * 32 = 128 accumulator columns)
+#define TC_CHUNK_BYTES (TC_NCL * TC_D * TC_D * 4)
 #define TC_STAGE_BYTES (TC_TILE * TC_D * 4)
 #define TC_THREADS 320
 #define TC_MAX_K 24
@@ -134,7 +134,7 @@ __device__ __forceinline__ uint32_t idesc_tf32(int n) {
 struct GaussTcArgs {
   int64_t n;
   int K;
-  const float* wmat;   // [NCH][256][32] factors U_k, rows (k_local, i), zero padded
+  const float* wmat;   // [K padded to a multiple of 4][32][32] factors U_k, rows (k, i), zero padded
   const float* bvec;   // [K][32]  U_k mu_k
   const float* mu;     // [K][32]
   const float* cst;    // [3K]   c of every distribution (cluster dist = 3k)
@@ -151,18 +151,28 @@ struct GaussTcArgs {
   int32_t* stats;      // optional [2]: #points, #candidate evaluations (diagnostics)
 };
 
-static inline size_t gauss_tc_smem_bytes(int K) {
-  const int nch = (K + TC_NCL - 1) / TC_NCL;
-  size_t b = 1024;                                   // alignment slack
-  b += (size_t)nch * TC_CHUNK_BYTES;                 // W
-  b += 4 * (size_t)TC_STAGE_BYTES;                   // X stages (2 per group)
-  b += (size_t)K * TC_D * 4 * 2;                     // b, mu
-  b += (size_t)K * 4 * 4;                            // c, log w, |U|_F, (pad)
-  b += 2 * (size_t)K * TC_TILE * 4;                  // rs per group
-  b += (size_t)((K + 3) & ~3) * 4;                   // hist
-  b += 16 * 8 + 16;                                  // barriers + tmem pointer
-  return b;
-}
+// shared-memory carve-up (bytes), shared by host and device
+struct GaussTcSmem {
+  int nch;
+  size_t w, stages, bvec, mu, consts, rs, pairs, cnt, hist, bars, total;
+  __host__ __device__ explicit GaussTcSmem(int K) {
+    nch = (K + TC_NCL - 1) / TC_NCL;
+    size_t o = 0;
+    w = o;       o += (size_t)nch * TC_CHUNK_BYTES;          // factors (1024-aligned chunks)
+    stages = o;  o += 4 * (size_t)TC_STAGE_BYTES;            // X stages, 2 per group
+    bvec = o;    o += (size_t)K * TC_D * 4;
+    mu = o;      o += (size_t)K * TC_D * 4;
+    consts = o;  o += (size_t)4 * K * 4;                     // c, log w, |U|_F, pad
+    rs = o;      o += 2 * (size_t)K * TC_TILE * 4;           // per group [K][128]
+    pairs = o;   o += 2 * (size_t)K * TC_TILE * 2;           // per group candidate (row, k) list, uint16
+    o = (o + 15) & ~(size_t)15;
+    cnt = o;     o += 2 * 2 * 32 * 4;                        // per group: counts[32], offsets[32]
+    hist = o;    o += (size_t)((K + 3) & ~3) * 4;
+    o = (o + 15) & ~(size_t)15;
+    bars = o;    o += 16 * 8 + 16;
+    total = o;
+  }
+};
 
 // exact q = |U_k (x - mu_k)|^2 from the K-major (row = i) swizzled factor rows in shared memory
 __device__ __forceinline__ float gauss_tc_exact_q(const float* wk, const float* mu, const float (&x)[TC_D]) {
@@ -192,27 +202,49 @@ __device__ __forceinline__ float gauss_tc_exact_q(const float* wk, const float* 
   return q0 + q1;
 }
 
+// q~ = sum_i (acc_i - b_i)^2 over the 32 accumulator columns of one cluster
+__device__ __forceinline__ float gauss_tc_screen_q(const uint32_t (&v)[32], const float* bk) {
+  f32x2_t acc = 0ull;
+#pragma unroll
+  for (int j = 0; j < TC_D / 4; ++j) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bk + 4 * j);
+    const float d0 = __uint_as_float(v[4 * j]) - b4.x, d1 = __uint_as_float(v[4 * j + 1]) - b4.y;
+    const float d2 = __uint_as_float(v[4 * j + 2]) - b4.z, d3 = __uint_as_float(v[4 * j + 3]) - b4.w;
+    const f32x2_t p0 = f2_pack(d0, d1), p1 = f2_pack(d2, d3);
+    acc = f2_fma(p0, p0, acc);
+    acc = f2_fma(p1, p1, acc);
+  }
+  float lo, hi;
+  f2_unpack(acc, lo, hi);
+  return lo + hi;
+}
+
+__device__ __forceinline__ void group_barrier(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  uint8_t* const smem = tc_smem;
   const int K = a.K;
-  const int nch = (K + TC_NCL - 1) / TC_NCL;
-  float* wsm = reinterpret_cast<float*>(base);
-  uint8_t* stage0 = base + (size_t)nch * TC_CHUNK_BYTES;
-  float* bsm = reinterpret_cast<float*>(stage0 + 4 * TC_STAGE_BYTES);
-  float* musm = bsm + K * TC_D;
-  float* csm = musm + K * TC_D;       // c_k
-  float* lwsm = csm + K;              // log w_k
-  float* frosm = lwsm + K;            // |U_k|_F
-  float* rs_all = frosm + 2 * K;      // [2][K][128]
-  int* hs = reinterpret_cast<int*>(rs_all + 2 * K * TC_TILE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(hs + ((K + 3) & ~3));
-  uint64_t* full = bars;              // [4]  TMA landed
-  uint64_t* empty = bars + 4;         // [4]  stage released by its 128 consumers
-  uint64_t* tfull = bars + 8;         // [2]  accumulator chunk ready
-  uint64_t* tempty = bars + 10;       // [2]  accumulator chunk drained
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  const GaussTcSmem L(K);
+  const int nch = L.nch;
+  float* wsm = reinterpret_cast<float*>(smem + L.w);
+  uint8_t* stage0 = smem + L.stages;
+  float* bsm = reinterpret_cast<float*>(smem + L.bvec);
+  float* musm = reinterpret_cast<float*>(smem + L.mu);
+  float* csm = reinterpret_cast<float*>(smem + L.consts);  // c_k
+  float* lwsm = csm + K;                                   // log w_k
+  float* frosm = lwsm + K;                                 // |U_k|_F
+  float* rs_all = reinterpret_cast<float*>(smem + L.rs);
+  uint16_t* pairs_all = reinterpret_cast<uint16_t*>(smem + L.pairs);
+  int* cnt_all = reinterpret_cast<int*>(smem + L.cnt);
+  int* hs = reinterpret_cast<int*>(smem + L.hist);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* full = bars;              // [4]     TMA landed in stage s
+  uint64_t* empty = bars + 4;         // [4]     stage s released by its 128 consumers
+  uint64_t* tfull = bars + 8;         // [2][2]  accumulator buffer (group, b) ready
+  uint64_t* tempty = bars + 12;       // [2][2]  accumulator buffer (group, b) drained
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -220,8 +252,6 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
     for (int i = 0; i < 4; ++i) {
       tc::mbar_init(&full[i], 1);
       tc::mbar_init(&empty[i], 128);
-    }
-    for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&tfull[i], 1);
       tc::mbar_init(&tempty[i], 128);
     }
@@ -229,8 +259,8 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
   // ---- stage the factors once per CTA, applying the 128B swizzle the MMA descriptor expects ----
-  for (int e = tid; e < nch * 256 * (TC_D / 4); e += TC_THREADS) {
-    const int r = e >> 3, c = e & 7;  // row (within the stacked chunks), 16-byte chunk
+  for (int e = tid; e < nch * TC_NCL * TC_D * (TC_D / 4); e += TC_THREADS) {
+    const int r = e >> 3, c = e & 7;  // row (k * 32 + i), 16-byte chunk
     const float4 v = __ldg(reinterpret_cast<const float4*>(a.wmat) + e);
     *reinterpret_cast<float4*>(wsm + (size_t)r * TC_D + ((c ^ (r & 7)) << 2)) = v;
   }
@@ -254,9 +284,8 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
     // =============================== control warp of group g ===============================
     const int g = warp;
     if (lane == 0) {
-      const uint32_t tmem_d = tmem_base + g * 256;
       int li = 0;
-      uint32_t tcount = 0;
+      uint32_t cc = 0;  // chunk counter of this group
       int64_t tile = (int64_t)blockIdx.x + (int64_t)g * gridDim.x;
       const int64_t tstep = 2 * (int64_t)gridDim.x;
       if (tile < a.ntiles) {  // prologue: first tile of this group
@@ -265,20 +294,6 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
       }
       for (; tile < a.ntiles; tile += tstep, ++li) {
         const int s = g * 2 + (li & 1);
-        tc::mbar_wait(&full[s], (li >> 1) & 1);
-        tc::tc_fence_after();
-        const uint64_t adesc = tc::smem_desc_k128(tc::smem_u32(stage0 + (size_t)s * TC_STAGE_BYTES));
-        for (int c = 0; c < nch; ++c, ++tcount) {
-          tc::mbar_wait(&tempty[g], (tcount & 1) ^ 1);   // epilogue drained the previous chunk
-          tc::tc_fence_after();
-          const int ncl = min(TC_NCL, K - c * TC_NCL);
-          const uint64_t bdesc = tc::smem_desc_k128(tc::smem_u32(wsm) + c * TC_CHUNK_BYTES);
-          const uint32_t idesc = tc::idesc_tf32(ncl * TC_D);
-#pragma unroll
-          for (int ks = 0; ks < TC_D / 8; ++ks)   // 32-byte k-steps inside the 128-byte swizzled rows
-            tc::umma_tf32(tmem_d, adesc + ks * 2, bdesc + ks * 2, idesc, ks > 0 ? 1u : 0u);
-          tc::umma_commit(&tfull[g]);
-        }
         // prefetch this group's next tile into its other stage (freed when tile li-1 was finished)
         const int64_t nt = tile + tstep;
         if (nt < a.ntiles) {
@@ -287,58 +302,70 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
           tc::mbar_arrive_expect_tx(&full[ns], TC_STAGE_BYTES);
           tc::tma_load_2d(stage0 + (size_t)ns * TC_STAGE_BYTES, &tmap_x, &full[ns], 0, (int)(nt * TC_TILE));
         }
+        tc::mbar_wait(&full[s], (li >> 1) & 1);
+        tc::tc_fence_after();
+        const uint64_t adesc = tc::smem_desc_k128(tc::smem_u32(stage0 + (size_t)s * TC_STAGE_BYTES));
+        for (int c = 0; c < nch; ++c, ++cc) {
+          const int b = cc & 1;
+          tc::mbar_wait(&tempty[g * 2 + b], ((cc >> 1) & 1) ^ 1);   // epilogue drained this buffer
+          tc::tc_fence_after();
+          const int ncl = min(TC_NCL, K - c * TC_NCL);
+          const uint64_t bdesc = tc::smem_desc_k128(tc::smem_u32(wsm) + c * TC_CHUNK_BYTES);
+          const uint32_t idesc = tc::idesc_tf32(ncl * TC_D);
+          const uint32_t tmem_d = tmem_base + g * 256 + b * 128;
+#pragma unroll
+          for (int ks = 0; ks < TC_D / 8; ++ks)   // 32-byte k-steps inside the 128-byte swizzled rows
+            tc::umma_tf32(tmem_d, adesc + ks * 2, bdesc + ks * 2, idesc, ks > 0 ? 1u : 0u);
+          tc::umma_commit(&tfull[g * 2 + b]);
+        }
       }
     }
   } else {
     // ======================= epilogue + refine + draw warps of group g =======================
     const int g = (warp - 2) >> 2;
+    const int gt = tid - 64 - g * 128;                     // thread index within the group
     const int row = ((warp & 3) << 5) | lane;              // TMEM lane == point within the tile
     const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) << 5) << 16) + g * 256;
-    float* rs = rs_all + (size_t)g * K * TC_TILE + row;    // element k at rs[k * 128]
+    float* rsg = rs_all + (size_t)g * K * TC_TILE;         // [K][128]
+    float* rs = rsg + row;                                 // this point's column: element k at rs[k * 128]
+    uint16_t* pairs = pairs_all + (size_t)g * K * TC_TILE;
+    int* cnt = cnt_all + g * 64;                           // [0..31] counts -> cursors, [32] total
     int li = 0;
-    uint32_t tcount = 0;
+    uint32_t cc = 0;
     int ncand_total = 0, npts_total = 0;
     for (int64_t tile = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; tile < a.ntiles; tile += 2 * (int64_t)gridDim.x, ++li) {
       const int s = g * 2 + (li & 1);
       // ---- screen: q~_k for every cluster from the TMEM accumulators ----
-      for (int c = 0; c < nch; ++c, ++tcount) {
-        tc::mbar_wait(&tfull[g], tcount & 1);
+      for (int c = 0; c < nch; ++c, ++cc) {
+        const int b = cc & 1;
+        tc::mbar_wait(&tfull[g * 2 + b], (cc >> 1) & 1);
         tc::tc_fence_after();
         const int ncl = min(TC_NCL, K - c * TC_NCL);
-        for (int kl = 0; kl < ncl; ++kl) {
-          uint32_t v[32];
-          tc::tmem_ld32(tmem_row + kl * TC_D, v);
+        const uint32_t taddr = tmem_row + b * 128;
+        for (int kl = 0; kl < ncl; kl += 2) {
+          uint32_t v0[32], v1[32];
+          tc::tmem_ld32(taddr + kl * TC_D, v0);
+          if (kl + 1 < ncl) tc::tmem_ld32(taddr + (kl + 1) * TC_D, v1);
           tc::tmem_ld_wait();
-          const float* bk = bsm + (c * TC_NCL + kl) * TC_D;
-          f32x2_t acc = 0ull;
-#pragma unroll
-          for (int j = 0; j < TC_D / 4; ++j) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bk + 4 * j);
-            const float d0 = __uint_as_float(v[4 * j]) - b4.x, d1 = __uint_as_float(v[4 * j + 1]) - b4.y;
-            const float d2 = __uint_as_float(v[4 * j + 2]) - b4.z, d3 = __uint_as_float(v[4 * j + 3]) - b4.w;
-            const f32x2_t p0 = f2_pack(d0, d1), p1 = f2_pack(d2, d3);
-            acc = f2_fma(p0, p0, acc);
-            acc = f2_fma(p1, p1, acc);
-          }
-          float lo, hi;
-          f2_unpack(acc, lo, hi);
-          rs[(c * TC_NCL + kl) * TC_TILE] = lo + hi;
+          const int k = c * TC_NCL + kl;
+          rs[k * TC_TILE] = gauss_tc_screen_q(v0, bsm + k * TC_D);
+          if (kl + 1 < ncl) rs[(k + 1) * TC_TILE] = gauss_tc_screen_q(v1, bsm + (k + 1) * TC_D);
         }
         tc::tc_fence_before();
-        tc::mbar_arrive(&tempty[g]);
+        tc::mbar_arrive(&tempty[g * 2 + b]);
       }
       // ---- the point itself (the TMA wrote it with the 128B swizzle) ----
       tc::mbar_wait(&full[s], (li >> 1) & 1);
+      const float* stage = reinterpret_cast<const float*>(stage0 + (size_t)s * TC_STAGE_BYTES);
       const int64_t i = tile * TC_TILE + row;
       const bool valid = i < a.n;
-      float x[TC_D];
+      uint32_t mask = 0;
       {
-        const float* xrow = reinterpret_cast<const float*>(stage0 + (size_t)s * TC_STAGE_BYTES) + row * TC_D;
+        const float* xrow = stage + row * TC_D;
         float xn = 0.f;
 #pragma unroll
         for (int c = 0; c < TC_D / 4; ++c) {
           const float4 v = *reinterpret_cast<const float4*>(xrow + ((c ^ (row & 7)) << 2));
-          x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
           xn = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, xn))));
         }
         // ---- candidates: upper bound of r_k within DELTA of the best lower bound ----
@@ -353,32 +380,54 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
           weird |= !(fabsf(rt) < CUDART_INF_F) || !(dr < CUDART_INF_F);
           best_lo = fmaxf(best_lo, rt - dr);
         }
-        uint32_t mask = 0;
         for (int k = 0; k < K; ++k) {
           const float qt = rs[k * TC_TILE];
           const float e = xnorm * frosm[k];
           const float dr = 0.5f * (2.f * sqrtf(fmaxf(qt, 0.f)) * e + e * e) + 0.01f;
           const float rt = lwsm[k] - csm[k] - 0.5f * qt;
-          if (weird || rt + dr >= best_lo - TC_DELTA) mask |= 1u << k;
-        }
-        if (!valid) mask = 0;
-        // ---- refine: exact Float32 reference value for every candidate, -Inf for the rest ----
-        for (int k = 0; k < K; ++k) {
-          const bool mine = (mask >> k) & 1u;
-          if (__any_sync(0xffffffffu, mine)) {
-            float r = -CUDART_INF_F;
-            if (mine) {
-              const float q = gauss_tc_exact_q(wsm + (size_t)k * TC_D * TC_D, musm + k * TC_D, x);
-              r = gauss_finish(csm[k], q, lwsm[k]);
-              ++ncand_total;
-            }
-            rs[k * TC_TILE] = r;
-          } else {
-            rs[k * TC_TILE] = -CUDART_INF_F;
-          }
+          const bool cand = valid && (weird || rt + dr >= best_lo - TC_DELTA);
+          if (cand) mask |= 1u << k;
+          else rs[k * TC_TILE] = -CUDART_INF_F;   // exactly-zero weight in the draw
         }
       }
-      // the stage can be refilled now: x lives in registers
+      // ---- regroup the (point, cluster) candidates by cluster so that a warp refines one cluster ----
+      // (counting sort over <= 24 keys in shared memory: count, prefix, scatter)
+      if (gt < 32) cnt[gt] = 0;
+      group_barrier(g);
+      for (uint32_t m = mask; m; m &= m - 1) atomicAdd(&cnt[__ffs(m) - 1], 1);
+      group_barrier(g);
+      if (gt == 0) {
+        int run = 0;
+        for (int k = 0; k < K; ++k) {
+          const int c = cnt[k];
+          cnt[k] = run;        // becomes the scatter cursor of cluster k
+          run += c;
+        }
+        cnt[32] = run;
+      }
+      group_barrier(g);
+      for (uint32_t m = mask; m; m &= m - 1) {
+        const int k = __ffs(m) - 1;
+        pairs[atomicAdd(&cnt[k], 1)] = (uint16_t)((row << 5) | k);
+      }
+      group_barrier(g);
+      const int npairs = cnt[32];
+      for (int idx = gt; idx < npairs; idx += 128) {
+        const uint32_t pr = pairs[idx];
+        const int prow = pr >> 5, k = pr & 31;
+        float x[TC_D];
+        const float* xrow = stage + prow * TC_D;
+#pragma unroll
+        for (int c = 0; c < TC_D / 4; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(xrow + ((c ^ (prow & 7)) << 2));
+          x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+        }
+        const float q = gauss_tc_exact_q(wsm + (size_t)k * TC_D * TC_D, musm + k * TC_D, x);
+        rsg[k * TC_TILE + prow] = gauss_finish(csm[k], q, lwsm[k]);
+        ++ncand_total;
+      }
+      group_barrier(g);
+      // the stage can be refilled now
       tc::mbar_arrive(&empty[s]);
       // ---- draw ----
       if (valid) {
