@@ -322,6 +322,7 @@ def main():
     assert int(out[0][:, 0].sum()) == case["n"] * world, "statistics do not cover every point"
 
     # ---- per-kernel durations (CUDA events around every launch) for the roofline ----
+    os.environ["DPMM_TC_STATS"] = "1"   # diagnostics of the tensor-core label path (which path ran, refinements/point)
     flush = None
     if case["n"] * D * 4 <= 126e6:
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
@@ -333,6 +334,8 @@ def main():
         sweep_device()
     tim = g.timing_read()
     g.timing_enable(False)
+    tc_pts, tc_cand = g.tc_stats()
+    os.environ.pop("DPMM_TC_STATS", None)
     work = algorithmic_work(case)
     pk = peaks()
     tf32_peak = pk["bf16_tflops"] / 2.0
@@ -354,11 +357,16 @@ def main():
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(case["name"], {}).get("label")
     if "mu" in case:
-        roofline = {"kernel": "gauss_label_kernel (fused log-likelihood + label draw)", "bound": "tensor",
+        on_tc = tc_pts > 0
+        roofline = {"kernel": ("gauss_label_tc_kernel (tcgen05 TF32 screen + FP32 refine + label draw)" if on_tc else
+                               "gauss_label_warp_kernel (fused FP32 log-likelihood + label draw)"),
+                    "bound": "tensor",
                     "achieved": stages["label"]["algorithmic_tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
                     "frac": stages["label"]["algorithmic_tflops"] / tf32_peak, "traffic": traffic,
                     "peak_source": f"TF32 dense = 1/2 x bf16 {pk['bf16_tflops']} TFLOP/s, {pk['source']}",
-                    "pipe": "fp32 FFMA (triangular |U z|^2, issues half the algorithmic flops)",
+                    "pipe": ("tcgen05.mma kind::tf32 (M=128,N=128,K=8) fed by TMA; candidates refined on the FP32 FMA pipe"
+                             if on_tc else "fp32 FFMA2 (triangular |U z|^2, issues half the algorithmic flops)"),
+                    "refined_clusters_per_point": (tc_cand / tc_pts) if on_tc else None,
                     "algorithmic_flops_per_launch": work["label_flops"]}
     else:
         roofline = {"kernel": "mnm_label_kernel (fused log-likelihood + label draw)", "bound": "hbm",

@@ -146,6 +146,40 @@ __device__ __forceinline__ int dpmm_draw_inverse_cdf(float* rs, int stride, int 
   return i;
 }
 
+// The same draw when only the clusters in `mask` (bit k) carry weight and every other entry is
+// exactly -Inf (weight exactly 0): identical arithmetic in identical order -- zeros added to the
+// left-to-right sums do not change them -- but only the masked entries are touched.  Requires all
+// masked entries to be finite or -Inf (callers route NaN rows to the general routine).
+__device__ __forceinline__ int dpmm_draw_inverse_cdf_masked(float* rs, int stride, int K, uint32_t mask, double u) {
+  float mx = -CUDART_INF_F;
+  for (uint32_t m = mask; m; m &= m - 1) mx = fmaxf(mx, rs[(__ffs(m) - 1) * stride]);
+  float s = 0.f;
+  for (uint32_t m = mask; m; m &= m - 1) {
+    const int k = __ffs(m) - 1;
+    const float e = expf(rs[k * stride] - mx);
+    rs[k * stride] = e;
+    s = __fadd_rn(s, e);
+  }
+  const bool s_regular = (s > 0.f) && (s < CUDART_INF_F);
+  float cw = 0.f;
+  for (uint32_t m = mask; m; m &= m - 1) {
+    const int k = __ffs(m) - 1;
+    const float e = rs[k * stride];
+    const bool zero = (e < 1.17549435e-38f) && s_regular;
+    const float quo = __fdiv_rn(zero ? 1.f : e, s);
+    cw = __fadd_rn(cw, zero ? 0.f : quo);
+    rs[k * stride] = cw;
+  }
+  const double t = u * (double)cw;
+  if (!(0.0 < t) && !(mask & 1u)) return 0;   // cw_1 = w_1 = 0 is not < t: the walk stops at i = 1
+  for (uint32_t m = mask; m; m &= m - 1) {
+    const int k = __ffs(m) - 1;
+    if (k >= K - 1) break;
+    if (!((double)rs[k * stride] < t)) return k;
+  }
+  return K - 1;
+}
+
 // mapslices(argmax, parr, dims=[2]) (local_clusters_actions.jl:130): first maximal element, NaN
 // counts as maximal (Julia's argmax); no NaN sanitising on this branch.
 __device__ __forceinline__ int dpmm_draw_argmax(const float* rs, int stride, int K) {

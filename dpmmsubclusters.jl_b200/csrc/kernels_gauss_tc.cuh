@@ -360,6 +360,7 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
       const int64_t i = tile * TC_TILE + row;
       const bool valid = i < a.n;
       uint32_t mask = 0;
+      bool weird = false;   // a NaN / Inf screen value: every cluster is refined, general draw
       {
         const float* xrow = stage + row * TC_D;
         float xn = 0.f;
@@ -371,23 +372,22 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
         // ---- candidates: upper bound of r_k within DELTA of the best lower bound ----
         const float xnorm = sqrtf(xn) * (1.f / 512.f);   // 2^-9 |x|
         float best_lo = -CUDART_INF_F;
-        bool weird = false;
         for (int k = 0; k < K; ++k) {
           const float qt = rs[k * TC_TILE];
           const float e = xnorm * frosm[k];
-          const float dr = 0.5f * (2.f * sqrtf(fmaxf(qt, 0.f)) * e + e * e) + 0.01f;
+          float sq;
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(fmaxf(qt, 0.f)));
+          const float dr = fmaf(1.01f * sq, e, fmaf(0.5f * e, e, 0.01f));   // |r~ - r| <= sqrt(q~) e + e^2/2
           const float rt = lwsm[k] - csm[k] - 0.5f * qt;
           weird |= !(fabsf(rt) < CUDART_INF_F) || !(dr < CUDART_INF_F);
           best_lo = fmaxf(best_lo, rt - dr);
+          rs[k * TC_TILE] = rt + dr;                     // upper bound
         }
+        const float thr = best_lo - TC_DELTA;
         for (int k = 0; k < K; ++k) {
-          const float qt = rs[k * TC_TILE];
-          const float e = xnorm * frosm[k];
-          const float dr = 0.5f * (2.f * sqrtf(fmaxf(qt, 0.f)) * e + e * e) + 0.01f;
-          const float rt = lwsm[k] - csm[k] - 0.5f * qt;
-          const bool cand = valid && (weird || rt + dr >= best_lo - TC_DELTA);
+          const bool cand = valid && (weird || rs[k * TC_TILE] >= thr);
           if (cand) mask |= 1u << k;
-          else rs[k * TC_TILE] = -CUDART_INF_F;   // exactly-zero weight in the draw
+          else rs[k * TC_TILE] = -CUDART_INF_F;          // exactly-zero weight in the draw
         }
       }
       // ---- regroup the (point, cluster) candidates by cluster so that a warp refines one cluster ----
@@ -436,7 +436,7 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
           lab = dpmm_draw_argmax(rs, TC_TILE, K);
         } else {
           const double u = dpmm_uniform(a.u_inj, i, a.seed, DPMM_STREAM_LABEL, a.call, (uint64_t)(a.goff + i));
-          lab = dpmm_draw_inverse_cdf(rs, TC_TILE, K, u);
+          lab = weird ? dpmm_draw_inverse_cdf(rs, TC_TILE, K, u) : dpmm_draw_inverse_cdf_masked(rs, TC_TILE, K, mask, u);
         }
         a.labels[i] = lab;
         atomicAdd(&hs[lab], 1);
