@@ -115,6 +115,11 @@ __device__ __forceinline__ uint64_t smem_desc_k128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
+// K-major operand of one 8-element k-step without swizzle: 8-row x 16-byte core matrices, the two core
+// matrices of the k-step LBO = 128 B apart, 8-row groups SBO = 256 B apart.
+__device__ __forceinline__ uint64_t smem_desc_k_noswz(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
+}
 // Instruction descriptor: FP32 accumulator, TF32 A and B, both K-major, M = 128, N = n.
 __device__ __forceinline__ uint32_t idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -128,7 +133,7 @@ __device__ __forceinline__ uint32_t idesc_tf32(int n) {
 #define TC_CHUNK_BYTES (TC_NCL * TC_D * TC_D * 4)
 #define TC_STAGE_BYTES (TC_TILE * TC_D * 4)
 #define TC_THREADS 320
-#define TC_MAX_K 24
+#define TC_MAX_K 23
 #define TC_DELTA 30.0f
 
 struct GaussTcArgs {
@@ -160,7 +165,7 @@ struct GaussTcSmem {
     size_t o = 0;
     w = o;       o += (size_t)nch * TC_CHUNK_BYTES;          // factors (1024-aligned chunks)
     stages = o;  o += 4 * (size_t)TC_STAGE_BYTES;            // X stages, 2 per group
-    bvec = o;    o += (size_t)K * TC_D * 4;
+    bvec = o;    o += 4096 + (size_t)nch * 4096;            // bias k-step: A_aug [128 x 8], B_aug [nch][128 x 8]
     mu = o;      o += (size_t)K * TC_D * 4;
     consts = o;  o += (size_t)4 * K * 4;                     // c, log w, |U|_F, pad
     rs = o;      o += 2 * (size_t)K * TC_TILE * 4;           // per group [K][128]
@@ -202,21 +207,20 @@ __device__ __forceinline__ float gauss_tc_exact_q(const float* wk, const float* 
   return q0 + q1;
 }
 
-// q~ = sum_i (acc_i - b_i)^2 over the 32 accumulator columns of one cluster
-__device__ __forceinline__ float gauss_tc_screen_q(const uint32_t (&v)[32], const float* bk) {
-  f32x2_t acc = 0ull;
+// q~ = sum_i y_i^2 over the 32 accumulator columns of one cluster (y = U x - U mu from the MMA)
+__device__ __forceinline__ float gauss_tc_screen_q(const uint32_t (&v)[32]) {
+  f32x2_t acc0 = 0ull, acc1 = 0ull;
 #pragma unroll
   for (int j = 0; j < TC_D / 4; ++j) {
-    const float4 b4 = *reinterpret_cast<const float4*>(bk + 4 * j);
-    const float d0 = __uint_as_float(v[4 * j]) - b4.x, d1 = __uint_as_float(v[4 * j + 1]) - b4.y;
-    const float d2 = __uint_as_float(v[4 * j + 2]) - b4.z, d3 = __uint_as_float(v[4 * j + 3]) - b4.w;
-    const f32x2_t p0 = f2_pack(d0, d1), p1 = f2_pack(d2, d3);
-    acc = f2_fma(p0, p0, acc);
-    acc = f2_fma(p1, p1, acc);
+    const f32x2_t p0 = f2_pack(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]));
+    const f32x2_t p1 = f2_pack(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    acc0 = f2_fma(p0, p0, acc0);
+    acc1 = f2_fma(p1, p1, acc1);
   }
-  float lo, hi;
-  f2_unpack(acc, lo, hi);
-  return lo + hi;
+  float a0, a1, b0, b1;
+  f2_unpack(acc0, a0, a1);
+  f2_unpack(acc1, b0, b1);
+  return (a0 + a1) + (b0 + b1);
 }
 
 __device__ __forceinline__ void group_barrier(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
@@ -230,7 +234,8 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
   const int nch = L.nch;
   float* wsm = reinterpret_cast<float*>(smem + L.w);
   uint8_t* stage0 = smem + L.stages;
-  float* bsm = reinterpret_cast<float*>(smem + L.bvec);
+  float* aaug = reinterpret_cast<float*>(smem + L.bvec);            // [128 rows][8]: (1, 1, 0, ...)
+  float* baug = aaug + 1024;                                        // [nch][128 rows][8]: (-b_hi, -b_lo, 0, ...)
   float* musm = reinterpret_cast<float*>(smem + L.mu);
   float* csm = reinterpret_cast<float*>(smem + L.consts);  // c_k
   float* lwsm = csm + K;                                   // log w_k
@@ -264,9 +269,27 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
     const float4 v = __ldg(reinterpret_cast<const float4*>(a.wmat) + e);
     *reinterpret_cast<float4*>(wsm + (size_t)r * TC_D + ((c ^ (r & 7)) << 2)) = v;
   }
+  // bias k-step: Y -= U mu is folded into the MMA as one more k-step whose A operand is the constant
+  // (1, 1, 0, ..) and whose B operand holds -b split into a TF32-exact high part and the remainder
+  for (int e = tid; e < 1024 + nch * 1024; e += TC_THREADS) aaug[e] = 0.f;
+  __syncthreads();
+  for (int r = tid; r < TC_TILE; r += TC_THREADS) {
+    float* p = aaug + (r >> 3) * 64 + (r & 7) * 4;   // (r/8)*256 B + (r%8)*16 B
+    p[0] = 1.f;
+    p[1] = 1.f;
+  }
   for (int e = tid; e < K * TC_D; e += TC_THREADS) {
-    bsm[e] = __ldg(a.bvec + e);
     musm[e] = __ldg(a.mu + e);
+    const float b = __ldg(a.bvec + e);
+    uint32_t ub = __float_as_uint(b);
+    ub += 0xFFFu + ((ub >> 13) & 1u);
+    ub &= 0xFFFFE000u;                                // round to TF32 (10 explicit mantissa bits)
+    const float bhi = (b == b && fabsf(b) < CUDART_INF_F) ? __uint_as_float(ub) : b;
+    const float blo = b - bhi;
+    const int c = e / (TC_NCL * TC_D), rl = e - c * (TC_NCL * TC_D);   // chunk, row within the chunk
+    float* p = baug + c * 1024 + (rl >> 3) * 64 + (rl & 7) * 4;
+    p[0] = -bhi;
+    p[1] = -blo;
   }
   for (int k = tid; k < K; k += TC_THREADS) {
     csm[k] = __ldg(a.cst + 3 * k);
@@ -316,6 +339,8 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
 #pragma unroll
           for (int ks = 0; ks < TC_D / 8; ++ks)   // 32-byte k-steps inside the 128-byte swizzled rows
             tc::umma_tf32(tmem_d, adesc + ks * 2, bdesc + ks * 2, idesc, ks > 0 ? 1u : 0u);
+          tc::umma_tf32(tmem_d, tc::smem_desc_k_noswz(tc::smem_u32(aaug)),
+                        tc::smem_desc_k_noswz(tc::smem_u32(baug) + c * 4096), idesc, 1u);   // Y -= U mu
           tc::umma_commit(&tfull[g * 2 + b]);
         }
       }
@@ -348,8 +373,8 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
           if (kl + 1 < ncl) tc::tmem_ld32(taddr + (kl + 1) * TC_D, v1);
           tc::tmem_ld_wait();
           const int k = c * TC_NCL + kl;
-          rs[k * TC_TILE] = gauss_tc_screen_q(v0, bsm + k * TC_D);
-          if (kl + 1 < ncl) rs[(k + 1) * TC_TILE] = gauss_tc_screen_q(v1, bsm + (k + 1) * TC_D);
+          rs[k * TC_TILE] = gauss_tc_screen_q(v0);
+          if (kl + 1 < ncl) rs[(k + 1) * TC_TILE] = gauss_tc_screen_q(v1);
         }
         tc::tc_fence_before();
         tc::mbar_arrive(&tempty[g * 2 + b]);
