@@ -467,7 +467,7 @@ extern "C" int dpmm_create(dpmm_ctx** out, const float* x, int64_t n_local, int3
     if (ctx->tc_ok) CKC(cudaMalloc((void**)&ctx->tc_stats, 2 * sizeof(int32_t)));
   }
 #undef CKC
-  ctx->chunk = 1024;
+  ctx->chunk = 1024;  // <= StatsCfg::MAX_CHUNK
   *out = ctx;
   return 0;
 }

@@ -110,7 +110,9 @@ struct StatsCfg {
   static constexpr int WARPS = WPG * NS;
   static constexpr int R = (NS >= 8) ? 2 : 4;            // points per lane per tile
   static constexpr int TPTS = 32 * NS * R;               // points per shared-memory tile
-  static constexpr int SMEM_BYTES = 2 * TPTS * DS * 4;   // double-buffered tile
+  static constexpr int STAGES = 4;                       // cp.async ring depth (tiles in flight)
+  static constexpr int MAX_CHUNK = 2048;                 // longest run (points) of one work item
+  static constexpr int SMEM_BYTES = STAGES * TPTS * DS * 4 + MAX_CHUNK * 4;
   static constexpr int MIN_CTAS = (WARPS * 32 <= 320) ? 2 : 1;
 };
 
@@ -135,6 +137,8 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // K5: NIW.  Warp w of a CTA owns upper block u = g*WPG + w % WPG of S (g = block group of the work
 // unit; G > 1 only when S has more than 16 upper blocks, i.e. D > 40) and point slice w / WPG; lane l
@@ -147,27 +151,31 @@ __global__ void __launch_bounds__(StatsCfg<D>::WARPS * 32, StatsCfg<D>::MIN_CTAS
 niw_stats_kernel(const StatsArgs a) {
   using C = StatsCfg<D>;
   constexpr int BS = C::BS, BSQ = C::BSQ, NQ = C::BSQ / 2;
-  extern __shared__ __align__(16) float xs_all[];  // [2][TPTS][DS]
+  extern __shared__ __align__(16) float xs_all[];  // [STAGES][TPTS][DS] | sidx [MAX_CHUNK]
+  int32_t* sidx = reinterpret_cast<int32_t*>(xs_all + C::STAGES * C::TPTS * C::DS);
   __shared__ int s_item;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slice = warp / C::WPG;
-  for (int e = tid; e < 2 * C::TPTS * C::DS; e += blockDim.x) xs_all[e] = 0.f;  // padding columns stay 0
+  for (int e = tid; e < C::STAGES * C::TPTS * C::DS; e += blockDim.x) xs_all[e] = 0.f;  // padding columns stay 0
 
+  // gather tile [t0, t0 + TPTS) of the run into ring slot `buf`; the run's point indices were staged
+  // in sidx when the item was fetched, so issuing the copies never waits on a global load
   auto prefetch = [&](const StatsItem& item, int t0, int buf) {
     float* xs = xs_all + buf * C::TPTS * C::DS;
     const int tn = min(C::TPTS, item.end - t0);
+    const int32_t* ix = sidx + (t0 - item.begin);
     if constexpr (D % 4 == 0) {
       for (int e = tid; e < C::TPTS * (D / 4); e += blockDim.x) {
         const int p = e / (D / 4), c = e - p * (D / 4);
         const bool ok = p < tn;
-        const int idx = ok ? __ldg(a.perm2 + t0 + p) : 0;
+        const int idx = ok ? ix[p] : 0;
         cp_async16(xs + p * C::DS + 4 * c, a.x + (size_t)idx * D + 4 * c, ok ? 16 : 0);
       }
     } else {
       for (int e = tid; e < C::TPTS * D; e += blockDim.x) {
         const int p = e / D, c = e - p * D;
         const bool ok = p < tn;
-        const int idx = ok ? __ldg(a.perm2 + t0 + p) : 0;
+        const int idx = ok ? ix[p] : 0;
         cp_async4(xs + p * C::DS + c, a.x + (size_t)idx * D + c, ok ? 4 : 0);
       }
     }
@@ -181,6 +189,8 @@ niw_stats_kernel(const StatsArgs a) {
     const int it = s_item;
     if (it >= *a.n_items * C::G) break;
     const StatsItem item = a.items[it / C::G];
+    for (int e = tid; e < item.end - item.begin; e += blockDim.x) sidx[e] = __ldg(a.perm2 + item.begin + e);
+    __syncthreads();
     const int u = (it % C::G) * C::WPG + warp % C::WPG;
     const bool live = u < C::NU;
     int bi = 0, bj = 0;
@@ -202,12 +212,21 @@ niw_stats_kernel(const StatsArgs a) {
       for (int q = 0; q < NQ; ++q) acc[p][q] = 0ull;
     }
 
-    prefetch(item, item.begin, 0);
-    int buf = 0;
-    for (int t0 = item.begin; t0 < item.end; t0 += C::TPTS, buf ^= 1) {
-      cp_async_wait_all();
-      __syncthreads();  // tile t0 has landed for everyone; everyone is done with the other buffer
-      if (t0 + C::TPTS < item.end) prefetch(item, t0 + C::TPTS, buf ^ 1);
+    // cp.async ring: STAGES-1 tiles in flight ahead of the one being accumulated (a commit group is
+    // issued every step, empty past the end of the run, so that wait_group<STAGES-2> always means
+    // "the tile of this step has landed")
+    const int ntl = (item.end - item.begin + C::TPTS - 1) / C::TPTS;
+#pragma unroll
+    for (int j = 0; j < C::STAGES - 1; ++j) {
+      if (j < ntl) prefetch(item, item.begin + j * C::TPTS, j);
+      else cp_async_commit();
+    }
+    for (int t = 0; t < ntl; ++t) {
+      const int buf = t % C::STAGES;
+      cp_async_wait_group<C::STAGES - 2>();
+      __syncthreads();  // tile t has landed for everyone; everyone is done with tile t-1's buffer
+      if (t + C::STAGES - 1 < ntl) prefetch(item, item.begin + (t + C::STAGES - 1) * C::TPTS, (t + C::STAGES - 1) % C::STAGES);
+      else cp_async_commit();
       if (live) {
         const float* xs = xs_all + buf * C::TPTS * C::DS;
 #pragma unroll
