@@ -351,6 +351,22 @@ static int launch_gauss_label(dpmm_ctx* ctx, GaussLabelArgs a) {
 
 template <int D>
 static int launch_gauss_sublabel(dpmm_ctx* ctx, const SubLabelArgs& a, bool sample) {
+  if constexpr (D % 4 == 0 && D >= 16 && D <= 48) {
+    if (sample && env_int("DPMM_SUBLABEL_P2", 1)) {
+      using C = GaussCfg<D>;
+      const size_t sm = ((size_t)2 * 256 * C::DS + (size_t)SUBLABEL_SPAN * 2 * C::REC + a.K + 4) * 4;
+      auto kern = gauss_sublabel2_kernel<D>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      int occ = 1;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, sm));
+      const int64_t ntiles = (a.n + 255) / 256;
+      const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * std::max(occ, 1));
+      KernelTimer kt(ctx, TK_SUBLABEL);
+      kern<<<grid, 128, sm, ctx->stream>>>(a);
+      CK(cudaGetLastError());
+      return 0;
+    }
+  }
   const int T = 128;
   const unsigned grid = (unsigned)((a.n + T - 1) / T);
   KernelTimer kt(ctx, TK_SUBLABEL);
@@ -1016,6 +1032,7 @@ static int run_sublabels(dpmm_ctx* ctx, bool sample, float* dump) {
   SubLabelArgs a{};
   a.x = ctx->x; a.n = ctx->n; a.K = ctx->K; a.recs = ctx->recs; a.cst = ctx->cst; a.loglr = ctx->loglr;
   a.labels = ctx->labels; a.sub = ctx->sub; a.perm = ctx->perm; a.perm2 = ctx->perm2; a.cursor = ctx->lr_cursor;
+  a.seg_off = ctx->seg_off;
   a.u_inj = ctx->u_sub; a.seed = ctx->seed; a.call = ctx->call; a.goff = ctx->goff; a.dump = dump; a.D = ctx->D;
   if (ctx->prior == DPMM_PRIOR_NIW) {
     rc = DPMM_ELIMIT;

@@ -369,6 +369,7 @@ struct SubLabelArgs {
   const int32_t* perm;    // [n] positions sorted by label
   int32_t* perm2;         // [n] out: label segments partitioned left | right
   int* cursor;            // [2K] cursor[2k] grows up from seg_off[k], cursor[2k+1] down from seg_off[k+1]
+  const int32_t* seg_off; // [K+1] label segment offsets in perm
   const double* u_inj;
   uint64_t seed;
   uint32_t call;
@@ -488,4 +489,171 @@ __global__ void gauss_sublabel_kernel(const SubLabelArgs a) {
     __syncthreads();
   }
   sublabel_partition(a, active, k, side, idx, s_cnt, s_base, s_first);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4, two points per thread: thread t owns the ADJACENT label-sorted positions 2t and 2t+1 of a
+// 256-position tile, which share their label except at a segment boundary, so one pass of factor
+// loads serves two points (the one-point form above is bound by the shared-memory pipe: 144
+// LDS.128 per 288 FFMA2).  The tile's rows are gathered into shared memory with cp.async.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sl_cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) gauss_sublabel2_kernel(const SubLabelArgs a) {
+  using C = GaussCfg<D>;
+  static_assert(C::VEC, "two-point sub-label kernel needs D % 4 == 0");
+  constexpr int T = 128, TP = 256;
+  extern __shared__ __align__(16) float sl_smem[];
+  float* xs_all = sl_smem;                              // [2][TP][DS]  double-buffered gathered rows
+  float* us = xs_all + 2 * TP * C::DS;                  // [SPAN][l, r][REC]
+  int* segs = reinterpret_cast<int*>(us + SUBLABEL_SPAN * 2 * C::REC);   // [K+1] label segment offsets
+  __shared__ int s_cnt[2 * TP];
+  __shared__ int s_base[2 * TP];
+  const int tid = threadIdx.x;
+  const int K = a.K;
+  for (int e = tid; e <= K; e += T) segs[e] = __ldg(a.seg_off + e);
+  __syncthreads();
+  // label of a sorted position = the segment that contains it (positions are sorted by label)
+  auto label_of = [&](int64_t pos) {
+    int lo = 0, hi = K;                                  // segs[lo] <= pos < segs[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (segs[mid] <= pos) lo = mid; else hi = mid;
+    }
+    return lo;
+  };
+  const int64_t ntiles = (a.n + TP - 1) / TP;
+  auto load_perm = [&](int64_t tile, int32_t (&idx)[2]) {
+    const int64_t p = tile * TP + 2 * tid;
+    idx[0] = (tile < ntiles && p < a.n) ? __ldg(a.perm + p) : -1;
+    idx[1] = (tile < ntiles && p + 1 < a.n) ? __ldg(a.perm + p + 1) : -1;
+  };
+  auto gather = [&](int buf, const int32_t (&idx)[2]) {
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) {
+      float* dst = xs_all + (size_t)buf * TP * C::DS + (2 * tid + pp) * C::DS;
+      const bool ok = idx[pp] >= 0;
+      const float* src = a.x + (size_t)(ok ? idx[pp] : 0) * D;
+#pragma unroll
+      for (int c = 0; c < D / 4; ++c) sl_cp_async16(dst + 4 * c, src + 4 * c, ok ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // software pipeline over this CTA's tiles: the permutation entries are loaded two tiles ahead and
+  // the rows one tile ahead of the tile being evaluated
+  int32_t idx[2], idx_n[2], idx_nn[2];
+  int64_t tile = blockIdx.x;
+  load_perm(tile, idx);
+  load_perm(tile + gridDim.x, idx_n);
+  gather(0, idx);
+  int cached_first = -1, cached_last = -2;
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const float* xs = xs_all + (size_t)buf * TP * C::DS;
+    load_perm(tile + 2 * (int64_t)gridDim.x, idx_nn);
+    gather(buf ^ 1, idx_n);                               // rows of the next tile (a no-op group past the end)
+    const int64_t pos0 = tile * TP;
+    const int nact = (int)min((int64_t)TP, a.n - pos0);
+    const int kfirst = label_of(pos0), klast = label_of(pos0 + nact - 1);
+    int k[2], side[2] = {0, 0};
+    bool act[2];
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) {
+      act[pp] = idx[pp] >= 0;
+      // most tiles lie inside one label segment: only boundary tiles search per point
+      k[pp] = (act[pp] && kfirst != klast) ? label_of(pos0 + 2 * tid + pp) : kfirst;
+    }
+    for (int j = tid; j < 2 * TP; j += T) s_cnt[j] = 0;
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's rows have landed
+    __syncthreads();
+    float rl[2] = {0.f, 0.f}, rr[2] = {0.f, 0.f};
+    for (int kb = kfirst; kb <= klast; kb += SUBLABEL_SPAN) {
+      const int nk = min(SUBLABEL_SPAN, klast - kb + 1);
+      const bool reuse = (kb == kfirst) && (kfirst == cached_first) && (klast == cached_last) && (klast - kfirst < SUBLABEL_SPAN);
+      if (!reuse) {
+        if (kb != kfirst) __syncthreads();
+        for (int e = tid; e < nk * 2 * (C::REC / 4); e += T) {
+          const int r = e / (C::REC / 4), c = e - r * (C::REC / 4);
+          const int kk = kb + (r >> 1), s = 1 + (r & 1);
+          reinterpret_cast<float4*>(us)[e] = __ldg(reinterpret_cast<const float4*>(a.recs + (size_t)(3 * kk + s) * C::REC) + c);
+        }
+        __syncthreads();
+      }
+      // pass 0 evaluates both points under the first point's label, pass 1 (only at a segment
+      // boundary) both under the second point's label
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const int kk = pass == 0 ? k[0] : k[1];
+        const bool inchunk = kk >= kb && kk < kb + nk;
+        const bool need = pass == 0 ? (act[0] && inchunk) || (act[1] && k[1] == k[0] && inchunk)
+                                    : (act[1] && k[1] != k[0] && inchunk);
+        if (need) {
+          float ql[2], qr[2];
+          auto ld = [&](int pp, int j0) { return *reinterpret_cast<const float4*>(xs + (2 * tid + pp) * C::DS + j0); };
+          gauss_quadform<D, 2>(us + (size_t)((kk - kb) * 2) * C::REC, ld, ql);
+          gauss_quadform<D, 2>(us + (size_t)((kk - kb) * 2 + 1) * C::REC, ld, qr);
+          const float cl = __ldg(a.cst + 3 * kk + 1), cr = __ldg(a.cst + 3 * kk + 2);
+          const float wl = __ldg(a.loglr + 2 * kk), wr = __ldg(a.loglr + 2 * kk + 1);
+#pragma unroll
+          for (int pp = 0; pp < 2; ++pp)
+            if (k[pp] == kk) {
+              rl[pp] = gauss_finish(cl, ql[pp], wl);
+              rr[pp] = gauss_finish(cr, qr[pp], wr);
+            }
+        }
+      }
+    }
+    cached_first = kfirst;
+    cached_last = (klast - kfirst < SUBLABEL_SPAN) ? klast : -2;   // only a single-pass staging stays valid
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp)
+      if (act[pp]) {
+        if (a.dump != nullptr) {
+          a.dump[idx[pp]] = rl[pp];
+          a.dump[a.n + idx[pp]] = rr[pp];
+        }
+        const double u = dpmm_uniform(a.u_inj, idx[pp], a.seed, DPMM_STREAM_SUBLABEL, a.call, (uint64_t)(a.goff + idx[pp]));
+        side[pp] = dpmm_draw_two(rl[pp], rr[pp], u);
+        a.sub[idx[pp]] = (uint8_t)side[pp];
+      }
+    // ---- partition every label segment of the tile into left | right (as sublabel_partition) ----
+    const int span = klast - kfirst + 1;
+    if (span <= TP) {
+      int rank[2] = {0, 0}, local[2] = {0, 0};
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp)
+        if (act[pp]) {
+          local[pp] = (k[pp] - kfirst) * 2 + side[pp];
+          rank[pp] = atomicAdd(&s_cnt[local[pp]], 1);
+        }
+      __syncthreads();
+      for (int j = tid; j < 2 * span; j += T) {
+        const int c = s_cnt[j];
+        if (c > 0) {
+          const int key = 2 * kfirst + j;
+          s_base[j] = (j & 1) ? atomicSub(&a.cursor[key], c) - c : atomicAdd(&a.cursor[key], c);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp)
+        if (act[pp]) a.perm2[s_base[local[pp]] + rank[pp]] = idx[pp];
+    } else {
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp)
+        if (act[pp]) {
+          const int key = 2 * k[pp] + side[pp];
+          const int dst = side[pp] ? atomicSub(&a.cursor[key], 1) - 1 : atomicAdd(&a.cursor[key], 1);
+          a.perm2[dst] = idx[pp];
+        }
+    }
+    __syncthreads();   // s_cnt / s_base / xs[buf] are reused by the next tile
+    idx[0] = idx_n[0]; idx[1] = idx_n[1];
+    idx_n[0] = idx_nn[0]; idx_n[1] = idx_nn[1];
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
