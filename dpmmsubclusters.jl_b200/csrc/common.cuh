@@ -150,20 +150,20 @@ __device__ __forceinline__ int dpmm_draw_inverse_cdf(float* rs, int stride, int 
 // exactly -Inf (weight exactly 0): identical arithmetic in identical order -- zeros added to the
 // left-to-right sums do not change them -- but only the masked entries are touched.  Requires all
 // masked entries to be finite or -Inf (callers route NaN rows to the general routine).
-__device__ __forceinline__ int dpmm_draw_inverse_cdf_masked(float* rs, int stride, int K, uint32_t mask, double u) {
+__device__ __forceinline__ int dpmm_draw_inverse_cdf_masked(float* rs, int stride, int K, uint64_t mask, double u) {
   float mx = -CUDART_INF_F;
-  for (uint32_t m = mask; m; m &= m - 1) mx = fmaxf(mx, rs[(__ffs(m) - 1) * stride]);
+  for (uint64_t m = mask; m; m &= m - 1) mx = fmaxf(mx, rs[(__ffsll((long long)m) - 1) * stride]);
   float s = 0.f;
-  for (uint32_t m = mask; m; m &= m - 1) {
-    const int k = __ffs(m) - 1;
+  for (uint64_t m = mask; m; m &= m - 1) {
+    const int k = __ffsll((long long)m) - 1;
     const float e = expf(rs[k * stride] - mx);
     rs[k * stride] = e;
     s = __fadd_rn(s, e);
   }
   const bool s_regular = (s > 0.f) && (s < CUDART_INF_F);
   float cw = 0.f;
-  for (uint32_t m = mask; m; m &= m - 1) {
-    const int k = __ffs(m) - 1;
+  for (uint64_t m = mask; m; m &= m - 1) {
+    const int k = __ffsll((long long)m) - 1;
     const float e = rs[k * stride];
     const bool zero = (e < 1.17549435e-38f) && s_regular;
     const float quo = __fdiv_rn(zero ? 1.f : e, s);
@@ -171,13 +171,37 @@ __device__ __forceinline__ int dpmm_draw_inverse_cdf_masked(float* rs, int strid
     rs[k * stride] = cw;
   }
   const double t = u * (double)cw;
-  if (!(0.0 < t) && !(mask & 1u)) return 0;   // cw_1 = w_1 = 0 is not < t: the walk stops at i = 1
-  for (uint32_t m = mask; m; m &= m - 1) {
-    const int k = __ffs(m) - 1;
+  if (!(0.0 < t) && !(mask & 1ull)) return 0;   // cw_1 = w_1 = 0 is not < t: the walk stops at i = 1
+  for (uint64_t m = mask; m; m &= m - 1) {
+    const int k = __ffsll((long long)m) - 1;
     if (k >= K - 1) break;
     if (!((double)rs[k * stride] < t)) return k;
   }
   return K - 1;
+}
+
+// Entry point used by the FMA-pipe label kernels: for K <= 64 first find the row maximum and the
+// clusters whose weight is not exactly zero (exp(r - max) underflows to +0 in Float32 below -103.98,
+// so everything under max - 104 contributes an exact 0 to every sum of the reference), then run the
+// masked draw on those few; otherwise (or when the row holds a NaN / has no finite maximum) the
+// general routine.  Both produce the same labels.
+__device__ __forceinline__ int dpmm_draw_inverse_cdf_screened(float* rs, int stride, int K, double u) {
+  if (K > 64) return dpmm_draw_inverse_cdf(rs, stride, K, u);
+  float mx = -CUDART_INF_F;
+  bool has_nan = false;
+  for (int k = 0; k < K; ++k) {
+    const float v = rs[k * stride];
+    has_nan |= (v != v);
+    mx = fmaxf(mx, v);
+  }
+  if (has_nan || !(mx > -CUDART_INF_F) || !(mx < CUDART_INF_F)) return dpmm_draw_inverse_cdf(rs, stride, K, u);
+  const float thr = mx - 104.f;
+  uint64_t mask = 0;
+  for (int k = 0; k < K; ++k)
+    if (rs[k * stride] >= thr) mask |= 1ull << k;
+  // with most clusters in play the unrolled general routine is the faster of the two
+  if (2 * __popcll(mask) > K) return dpmm_draw_inverse_cdf(rs, stride, K, u);
+  return dpmm_draw_inverse_cdf_masked(rs, stride, K, mask, u);
 }
 
 // mapslices(argmax, parr, dims=[2]) (local_clusters_actions.jl:130): first maximal element, NaN

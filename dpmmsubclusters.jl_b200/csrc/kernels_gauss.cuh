@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(128, 2) gauss_label_kernel(const GaussLabelArg
           lab = dpmm_draw_gumbel(col, TP, a.K, a.seed, a.call, (uint64_t)(a.goff + i));
         } else {
           const double u = dpmm_uniform(a.u_inj, i, a.seed, DPMM_STREAM_LABEL, a.call, (uint64_t)(a.goff + i));
-          lab = dpmm_draw_inverse_cdf(col, TP, a.K, u);
+          lab = dpmm_draw_inverse_cdf_screened(col, TP, a.K, u);
         }
         a.labels[i] = lab;
         atomicAdd(&hs[lab], 1);
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(384, 1) gauss_label_warp_kernel(const GaussLab
           lab = dpmm_draw_gumbel(col, TPW, a.K, a.seed, a.call, (uint64_t)(a.goff + i));
         } else {
           const double u = dpmm_uniform(a.u_inj, i, a.seed, DPMM_STREAM_LABEL, a.call, (uint64_t)(a.goff + i));
-          lab = dpmm_draw_inverse_cdf(col, TPW, a.K, u);
+          lab = dpmm_draw_inverse_cdf_screened(col, TPW, a.K, u);
         }
         a.labels[i] = lab;
         atomicAdd(&hs[lab], 1);

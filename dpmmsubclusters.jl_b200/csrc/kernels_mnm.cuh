@@ -94,7 +94,7 @@ __global__ void mnm_label_kernel(const MnmLabelArgs a) {
         lab = dpmm_draw_gumbel(col, T, a.K, a.seed, a.call, (uint64_t)(a.goff + i));
       } else {
         const double u = dpmm_uniform(a.u_inj, i, a.seed, DPMM_STREAM_LABEL, a.call, (uint64_t)(a.goff + i));
-        lab = dpmm_draw_inverse_cdf(col, T, a.K, u);
+        lab = dpmm_draw_inverse_cdf_screened(col, T, a.K, u);
       }
       a.labels[i] = lab;
       atomicAdd(&hs[lab], 1);
