@@ -483,7 +483,9 @@ extern "C" int dpmm_create(dpmm_ctx** out, const float* x, int64_t n_local, int3
     if (ctx->tc_ok) CKC(cudaMalloc((void**)&ctx->tc_stats, 2 * sizeof(int32_t)));
   }
 #undef CKC
-  ctx->chunk = 1024;  // <= StatsCfg::MAX_CHUNK
+  // work-item length of the statistics kernels: NIW <= StatsCfg::MAX_CHUNK (a CTA per item);
+  // multinomial items are taken by single warps, so they are shorter
+  ctx->chunk = prior_kind == DPMM_PRIOR_NIW ? 1024 : 256;
   *out = ctx;
   return 0;
 }
@@ -1046,7 +1048,9 @@ static int run_sublabels(dpmm_ctx* ctx, bool sample, float* dump) {
     const int T = 128;
     const unsigned grid = (unsigned)((a.n + T - 1) / T);
     KernelTimer kt(ctx, TK_SUBLABEL);
-    if (sample)
+    if (sample && ctx->D <= 128)
+      mnm_sublabel2_kernel<<<grid, T, 0, ctx->stream>>>(a);
+    else if (sample)
       mnm_sublabel_kernel<true><<<grid, T, 0, ctx->stream>>>(a);
     else
       mnm_sublabel_kernel<false><<<grid, T, 0, ctx->stream>>>(a);
@@ -1134,15 +1138,11 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
     }
     if (rc) return rc;
   } else {
-    const int DPAD = (D + 31) & ~31;
-    const int T = std::max(256, DPAD);
-    const size_t sm = (size_t)MNM_STATS_TPTS * (D | 1) * 4;
-    CK(cudaFuncSetAttribute(mnm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mnm_stats_kernel, T, sm));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mnm_stats_kernel, 256, 0));
     occ = std::max(occ, 1);
     KernelTimer kt(ctx, TK_STATS);
-    mnm_stats_kernel<<<ctx->sm_count * occ, T, sm, ctx->stream>>>(sa);
+    mnm_stats_kernel<<<ctx->sm_count * occ, 256, 0, ctx->stream>>>(sa);
     CK(cudaGetLastError());
   }
   {

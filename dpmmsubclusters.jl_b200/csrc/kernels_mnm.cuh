@@ -144,3 +144,81 @@ __global__ void mnm_sublabel_kernel(const SubLabelArgs a) {
   }
   sublabel_partition(a, active, k, side, idx, s_cnt, s_base, s_first);
 }
+
+// Sub-label draw, D <= 128: a warp evaluates its 32 label-sorted positions one point at a time with
+// lanes <-> features (each point is read as coalesced 128-byte segments; the l/r log-probability
+// vectors of the current label sit in registers and are reloaded only when the label changes), then
+// every lane draws and partitions its own point.
+__global__ void __launch_bounds__(128) mnm_sublabel2_kernel(const SubLabelArgs a) {
+  __shared__ int s_cnt[2 * 128];
+  __shared__ int s_base[2 * 128];
+  __shared__ int s_first[2];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int D = a.D;
+  const int64_t pos = (int64_t)blockIdx.x * blockDim.x + tid;
+  const bool active = pos < a.n;
+  int32_t idx = -1;
+  int k = 0, side = 0;
+  if (active) {
+    idx = a.perm[pos];
+    k = a.labels[idx];
+  }
+  float my_sl = 0.f, my_sr = 0.f;
+  float al[4], ar[4];
+  int cur = -1;
+#pragma unroll 1
+  for (int j0 = 0; j0 < 32; j0 += 4) {
+    int pi[4], pk[4];
+    float xv[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pi[j] = __shfl_sync(0xffffffffu, idx, j0 + j);
+      pk[j] = __shfl_sync(0xffffffffu, k, j0 + j);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int d = lane + 32 * r;
+        xv[j][r] = (pi[j] >= 0 && d < D) ? __ldg(a.x + (size_t)pi[j] * D + d) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (pi[j] < 0) continue;                       // warp-uniform
+      if (pk[j] != cur) {
+        cur = pk[j];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int d = lane + 32 * r;
+          al[r] = d < D ? __ldg(a.recs + (size_t)(3 * cur + 1) * D + d) : 0.f;
+          ar[r] = d < D ? __ldg(a.recs + (size_t)(3 * cur + 2) * D + d) : 0.f;
+        }
+      }
+      float sl = 0.f, sr = 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        sl = fmaf(al[r], xv[j][r], sl);
+        sr = fmaf(ar[r], xv[j][r], sr);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sl += __shfl_xor_sync(0xffffffffu, sl, o);
+        sr += __shfl_xor_sync(0xffffffffu, sr, o);
+      }
+      if (lane == j0 + j) {
+        my_sl = sl;
+        my_sr = sr;
+      }
+    }
+  }
+  if (active) {
+    const float rl = __fadd_rn(my_sl, __ldg(a.loglr + 2 * k));
+    const float rr = __fadd_rn(my_sr, __ldg(a.loglr + 2 * k + 1));
+    if (a.dump != nullptr) {
+      a.dump[idx] = rl;
+      a.dump[a.n + idx] = rr;
+    }
+    const double u = dpmm_uniform(a.u_inj, idx, a.seed, DPMM_STREAM_SUBLABEL, a.call, (uint64_t)(a.goff + idx));
+    side = dpmm_draw_two(rl, rr, u);
+    a.sub[idx] = (uint8_t)side;
+  }
+  sublabel_partition(a, active, k, side, idx, s_cnt, s_base, s_first);
+}

@@ -292,41 +292,69 @@ niw_stats_kernel(const StatsArgs a) {
   }
 }
 
-// K6: multinomial.  sum x per key; thread = (feature d, point slice).
-#define MNM_STATS_TPTS 64
-__global__ void mnm_stats_kernel(const StatsArgs a) {
-  extern __shared__ __align__(16) float xsm[];  // [TPTS][DS]
-  __shared__ int32_t sidx[MNM_STATS_TPTS];
-  __shared__ int s_item;
+// K6: multinomial.  sum x per key.  One warp per work item (a run of points with one (label, side)
+// key); lane l owns the features l, l+32, ... so every point is read as fully coalesced 128-byte
+// segments straight from global memory (no staging), with MNM_STATS_UNROLL points in flight per
+// warp, and the per-lane Float32 partial sums (exact: small integer counts) are added to the key's
+// Float64 accumulator once per item.
+#define MNM_STATS_NREG 32      // features per lane: supports D <= 1024
+#define MNM_STATS_UNROLL 8
+__global__ void __launch_bounds__(256) mnm_stats_kernel(const StatsArgs a) {
   const int D = a.D;
-  const int DS = D | 1;
-  const int tid = threadIdx.x, T = blockDim.x;
-  const int DPAD = (D + 31) & ~31;
-  const int NSL = T / DPAD;  // point slices (host guarantees >= 1)
-  const int d = tid % DPAD, sl = tid / DPAD;
+  const int lane = threadIdx.x & 31;
+  const int nreg = (D + 31) >> 5;
+  const int n_items = *a.n_items;
   for (;;) {
-    __syncthreads();
-    if (tid == 0) s_item = atomicAdd(a.next_item, 1);
-    __syncthreads();
-    const int it = s_item;
-    if (it >= *a.n_items) break;
+    int it = 0;
+    if (lane == 0) it = atomicAdd(a.next_item, 1);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= n_items) break;
     const StatsItem item = a.items[it];
-    float s = 0.f;
-    for (int t0 = item.begin; t0 < item.end; t0 += MNM_STATS_TPTS) {
-      const int tn = min(MNM_STATS_TPTS, item.end - t0);
-      __syncthreads();
-      for (int p = tid; p < MNM_STATS_TPTS; p += T) sidx[p] = (p < tn) ? a.perm2[t0 + p] : -1;
-      __syncthreads();
-      for (int e = tid; e < MNM_STATS_TPTS * D; e += T) {
-        const int p = e / D, c = e - p * D;
-        const int idx = sidx[p];
-        xsm[p * DS + c] = (idx >= 0) ? __ldg(a.x + (size_t)idx * D + c) : 0.f;
+    float acc[MNM_STATS_NREG];
+#pragma unroll
+    for (int r = 0; r < MNM_STATS_NREG; ++r) acc[r] = 0.f;
+    int idx_n[MNM_STATS_UNROLL];
+#pragma unroll
+    for (int j = 0; j < MNM_STATS_UNROLL; ++j) idx_n[j] = (item.begin + j < item.end) ? __ldg(a.perm2 + item.begin + j) : -1;
+    for (int p0 = item.begin; p0 < item.end; p0 += MNM_STATS_UNROLL) {
+      int idx[MNM_STATS_UNROLL];
+#pragma unroll
+      for (int j = 0; j < MNM_STATS_UNROLL; ++j) {
+        idx[j] = idx_n[j];                                   // indices were fetched one batch ahead
+        const int pn = p0 + MNM_STATS_UNROLL + j;
+        idx_n[j] = (pn < item.end) ? __ldg(a.perm2 + pn) : -1;
       }
-      __syncthreads();
-      if (d < D && sl < NSL)
-        for (int p = sl; p < tn; p += NSL) s += xsm[p * DS + d];
+      if (nreg <= 4) {  // common case (D <= 128): all loads of the batch in flight at once
+        float v[MNM_STATS_UNROLL][4];
+#pragma unroll
+        for (int j = 0; j < MNM_STATS_UNROLL; ++j)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int d = lane + 32 * r;
+            v[j][r] = (idx[j] >= 0 && d < D) ? __ldg(a.x + (size_t)idx[j] * D + d) : 0.f;
+          }
+#pragma unroll
+        for (int j = 0; j < MNM_STATS_UNROLL; ++j)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[r] += v[j][r];
+      } else {
+#pragma unroll
+        for (int j = 0; j < MNM_STATS_UNROLL; ++j)
+          if (idx[j] >= 0) {
+#pragma unroll
+            for (int r = 0; r < MNM_STATS_NREG; ++r) {
+              const int d = lane + 32 * r;
+              if (r < nreg && d < D) acc[r] += __ldg(a.x + (size_t)idx[j] * D + d);
+            }
+          }
+      }
     }
-    if (d < D && sl < NSL && s != 0.f) atomicAdd(a.acc + (size_t)item.key * a.rec + 1 + d, (double)s);
+    double* dst = a.acc + (size_t)item.key * a.rec + 1;
+#pragma unroll
+    for (int r = 0; r < MNM_STATS_NREG; ++r) {
+      const int d = lane + 32 * r;
+      if (r < nreg && d < D && acc[r] != 0.f) atomicAdd(dst + d, (double)acc[r]);
+    }
   }
 }
 
