@@ -18,6 +18,7 @@
 #include "kernels_gauss.cuh"
 #include "kernels_gauss_tc.cuh"
 #include "kernels_mnm.cuh"
+#include "kernels_mnm_tc.cuh"
 #include "kernels_sort.cuh"
 #include "kernels_stats.cuh"
 
@@ -92,6 +93,9 @@ struct dpmm_ctx {
   float* tc_fro = nullptr;
   int32_t* tc_stats = nullptr;
   CUtensorMap tmap_x;
+  float* mtc_w = nullptr;   // multinomial tensor-core path: TF32-exact 3-way split of the log-probabilities
+  bool mtc_ok = false;      // multinomial: tensor map built and the counts are TF32-exact
+  bool mtc_params = false;
   bool tc_ok = false;       // tensor map built
   bool tc_params = false;   // tc_* describe the current parameters
   float* logp_t = nullptr;  // multinomial [D][KP]
@@ -223,6 +227,10 @@ static int ensure_k(dpmm_ctx* ctx, int K) {
   CK(dev_realloc(&ctx->logw, (size_t)cap));
   CK(dev_realloc(&ctx->loglr, (size_t)2 * cap));
   if (ctx->prior == DPMM_PRIOR_MULTINOMIAL) CK(dev_realloc(&ctx->logp_t, (size_t)D * (cap + MNM_KT)));
+  if (ctx->mtc_ok) {
+    CK(dev_realloc(&ctx->mtc_w, (size_t)3 * ((D + 31) / 32) * MTC_N * 32));
+    ctx->mtc_params = false;
+  }
   if (ctx->tc_ok) {
     const int capc = std::min(cap, TC_MAX_K);
     CK(dev_realloc(&ctx->tc_w, (size_t)((capc + TC_NCL - 1) / TC_NCL) * TC_NCL * TC_D * TC_D));
@@ -482,6 +490,31 @@ extern "C" int dpmm_create(dpmm_ctx** out, const float* x, int64_t n_local, int3
     }
     if (ctx->tc_ok) CKC(cudaMalloc((void**)&ctx->tc_stats, 2 * sizeof(int32_t)));
   }
+  if (prior_kind == DPMM_PRIOR_MULTINOMIAL && d % 4 == 0 && d <= MTC_MAX_D && n_local >= MTC_TILE) {
+    // the tensor-core likelihood is exact only for TF32-exact counts: integral, |x| < 2^11
+    bool exact = true;
+    const size_t tot = (size_t)n_local * d;
+    for (size_t e = 0; e < tot && exact; ++e) {
+      const float v = x[e];
+      exact = (v == (float)(int)v) && v > -2048.f && v < 2048.f;
+    }
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (exact && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        fn != nullptr && qres == cudaDriverEntryPointSuccess) {
+      const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)n_local};
+      const cuuint64_t gstr[1] = {(cuuint64_t)d * 4};
+      const cuuint32_t box[2] = {32, MTC_TILE};
+      const cuuint32_t estr[2] = {1, 1};
+      const CUresult r = ((EncodeFn)fn)(&ctx->tmap_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ctx->x, gdim, gstr, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      ctx->mtc_ok = (r == CUDA_SUCCESS);
+    }
+  }
 #undef CKC
   // work-item length of the statistics kernels: NIW <= StatsCfg::MAX_CHUNK (a CTA per item);
   // multinomial items are taken by single warps, so they are shorter
@@ -501,7 +534,7 @@ extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
   }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   void* ptrs[] = {ctx->x, ctx->labels, ctx->sub, ctx->perm, ctx->perm2, ctx->u_label, ctx->u_sub, ctx->r_bits,
-                  ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->tc_w, ctx->tc_b, ctx->tc_mu, ctx->tc_fro, ctx->tc_stats, ctx->hist, ctx->seg_off,
+                  ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->tc_w, ctx->tc_b, ctx->tc_mu, ctx->tc_fro, ctx->tc_stats, ctx->mtc_w, ctx->hist, ctx->seg_off,
                   ctx->scat_cursor, ctx->lr_cursor, ctx->lut_l, ctx->lut_r, ctx->rule, ctx->wanted,
                   ctx->idx_list, ctx->acc, ctx->outbuf, ctx->items, ctx->item_ctr};
   for (void* p : ptrs)
@@ -904,7 +937,10 @@ extern "C" int dpmm_set_params_multinomial(dpmm_ctx* ctx, int32_t K, const float
   const int D = ctx->D;
   const int KP = (K + MNM_KT - 1) / MNM_KT * MNM_KT;
   const size_t nrec = (size_t)3 * K;
-  const size_t bytes = (nrec * D + (size_t)D * KP + K + 2 * K) * sizeof(float);
+  const bool mtc = ctx->mtc_ok && K <= MTC_MAX_K;
+  const int NP = (D + 31) / 32;
+  const size_t wfl = mtc ? (size_t)3 * NP * MTC_N * 32 : 0;
+  const size_t bytes = (nrec * D + (size_t)D * KP + K + 2 * K + wfl) * sizeof(float);
   rc = ensure_stage(ctx, bytes);
   if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
@@ -912,11 +948,40 @@ extern "C" int dpmm_set_params_multinomial(dpmm_ctx* ctx, int32_t K, const float
   float* h_t = h_recs + nrec * D;
   float* h_logw = h_t + (size_t)D * KP;
   float* h_loglr = h_logw + K;
+  float* h_ws = h_loglr + 2 * K;
   memcpy(h_recs, log_p, nrec * D * 4);
   std::fill(h_t, h_t + (size_t)D * KP, 0.f);
   for (int k = 0; k < K; ++k)
     for (int d = 0; d < D; ++d) h_t[(size_t)d * KP + k] = log_p[(size_t)(3 * k) * D + d];
   common_weights(ctx, K, weights, lr_weights, h_logw, h_loglr);
+  ctx->mtc_params = false;
+  if (mtc) {
+    // alpha = a_hi + a_lo + a_lolo, every term exact in TF32 (10 explicit mantissa bits)
+    auto tf32 = [](float v) {
+      if (!std::isfinite(v)) return v;
+      uint32_t u;
+      memcpy(&u, &v, 4);
+      u += 0xFFFu + ((u >> 13) & 1u);
+      u &= 0xFFFFE000u;
+      float r;
+      memcpy(&r, &u, 4);
+      return r;
+    };
+    std::fill(h_ws, h_ws + wfl, 0.f);
+    for (int k = 0; k < K; ++k)
+      for (int dd = 0; dd < D; ++dd) {
+        const float al = log_p[(size_t)(3 * k) * D + dd];
+        const float hi = tf32(al);
+        const float r1 = std::isfinite(al) ? al - hi : 0.f;
+        const float lo = tf32(r1);
+        const float lolo = r1 - lo;
+        const int p = dd >> 5, c = dd & 31;
+        const float parts[3] = {hi, lo, lolo};
+        for (int sp = 0; sp < 3; ++sp) h_ws[(((size_t)sp * NP + p) * MTC_N + k) * 32 + c] = parts[sp];
+      }
+    CK(cudaMemcpyAsync(ctx->mtc_w, h_ws, wfl * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->mtc_params = true;
+  }
   CK(cudaMemcpyAsync(ctx->recs, h_recs, nrec * D * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->logp_t, h_t, (size_t)D * KP * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->logw, h_logw, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -963,6 +1028,19 @@ static int run_sample_labels(dpmm_ctx* ctx, int final_iter, float* dump) {
 #undef X
     }
     if (rc) return rc;
+  } else if (ctx->mtc_params && dump == nullptr && env_int("DPMM_LABEL_TC", 1) != 0) {
+    // K3 on tcgen05: exact TF32 3-way split GEMM of counts x log-probabilities
+    MnmTcArgs a{};
+    a.n = ctx->n; a.D = ctx->D; a.K = K; a.NP = (ctx->D + 31) / 32; a.wsplit = ctx->mtc_w; a.logw = ctx->logw;
+    a.labels = ctx->labels; a.hist = ctx->hist; a.u_inj = ctx->u_label; a.seed = ctx->seed; a.call = ctx->call;
+    a.goff = ctx->goff; a.final_iter = final_iter; a.sampler = ctx->sampler; a.ntiles = (ctx->n + MTC_TILE - 1) / MTC_TILE;
+    const size_t sm = MnmTcSmem(K, a.NP).total;
+    NEED(sm <= (size_t)ctx->smem_optin, DPMM_ELIMIT, "internal: multinomial tensor-core kernel does not fit shared memory");
+    CK(cudaFuncSetAttribute(mnm_label_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const int64_t grid = std::min<int64_t>(a.ntiles, (int64_t)ctx->sm_count);
+    KernelTimer kt(ctx, TK_LABEL);
+    mnm_label_tc_kernel<<<(unsigned)grid, MTC_THREADS, sm, ctx->stream>>>(ctx->tmap_x, a);
+    CK(cudaGetLastError());
   } else {
     MnmLabelArgs a{};
     a.x = ctx->x; a.n = ctx->n; a.D = ctx->D; a.DS = ctx->D | 1; a.K = K; a.KP = ctx->KP; a.logp_t = ctx->logp_t;
