@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(384, 1) gauss_label_warp_kernel(const GaussLab
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
   float* us = smem;
   int* hs = reinterpret_cast<int*>(us + (size_t)a.K * C::REC);
-  float* wbase = reinterpret_cast<float*>(hs + ((a.K + 3) & ~3));
+  float* csm = reinterpret_cast<float*>(hs + ((a.K + 3) & ~3));   // [K] c_k, [K] log w_k
+  float* wbase = csm + 2 * ((a.K + 3) & ~3);
   float* xs = wbase + (size_t)warp * (TPW * C::DS + a.K * TPW);
   float* rs = xs + TPW * C::DS;
 
@@ -280,7 +281,11 @@ __global__ void __launch_bounds__(384, 1) gauss_label_warp_kernel(const GaussLab
     const int kk = e / (C::REC / 4), c = e - kk * (C::REC / 4);
     reinterpret_cast<float4*>(us)[e] = __ldg(reinterpret_cast<const float4*>(a.recs + (size_t)(3 * kk) * C::REC) + c);
   }
-  for (int k = tid; k < a.K; k += blockDim.x) hs[k] = 0;
+  for (int k = tid; k < a.K; k += blockDim.x) {
+    hs[k] = 0;
+    csm[k] = __ldg(a.cst + 3 * k);
+    csm[a.K + k] = __ldg(a.logw + k);
+  }
   __syncthreads();
 
   for (int64_t tile = (int64_t)blockIdx.x * W + warp; tile < a.ntiles; tile += (int64_t)gridDim.x * W) {
@@ -314,13 +319,30 @@ __global__ void __launch_bounds__(384, 1) gauss_label_warp_kernel(const GaussLab
     }
     __syncwarp();
     // ---- log-likelihood under every cluster ----
-    for (int k = 0; k < a.K; ++k) {
-      float q[P];
-      gauss_quadform<D, P>(us + (size_t)k * C::REC,
-                           [&](int pp, int j0) { return gauss_row_load4<D>(xs + (lane + pp * 32) * C::DS, j0); }, q);
-      const float c = __ldg(a.cst + 3 * k), lw = __ldg(a.logw + k);
+    if constexpr (D <= 8) {
+      // low-dimensional points live in registers for the whole cluster loop (re-reading them from
+      // shared memory per cluster would cost more than the D(D+1)/2 FMAs of the quadratic form)
+      float4 xr[P][C::DP4 / 4];
 #pragma unroll
-      for (int pp = 0; pp < P; ++pp) rs[k * TPW + lane + pp * 32] = gauss_finish(c, q[pp], lw);
+      for (int pp = 0; pp < P; ++pp)
+#pragma unroll
+        for (int j4 = 0; j4 < C::DP4 / 4; ++j4) xr[pp][j4] = gauss_row_load4<D>(xs + (lane + pp * 32) * C::DS, 4 * j4);
+      for (int k = 0; k < a.K; ++k) {
+        float q[P];
+        gauss_quadform<D, P>(us + (size_t)k * C::REC, [&](int pp, int j0) { return xr[pp][j0 >> 2]; }, q);
+        const float c = csm[k], lw = csm[a.K + k];
+#pragma unroll
+        for (int pp = 0; pp < P; ++pp) rs[k * TPW + lane + pp * 32] = gauss_finish(c, q[pp], lw);
+      }
+    } else {
+      for (int k = 0; k < a.K; ++k) {
+        float q[P];
+        gauss_quadform<D, P>(us + (size_t)k * C::REC,
+                             [&](int pp, int j0) { return gauss_row_load4<D>(xs + (lane + pp * 32) * C::DS, j0); }, q);
+        const float c = csm[k], lw = csm[a.K + k];
+#pragma unroll
+        for (int pp = 0; pp < P; ++pp) rs[k * TPW + lane + pp * 32] = gauss_finish(c, q[pp], lw);
+      }
     }
     // ---- draw (each lane only touches its own columns of rs) ----
 #pragma unroll
