@@ -1,0 +1,209 @@
+// Context, error plumbing and per-launch timing shared by the translation units of libdpmm_b200.so.
+#pragma once
+#include "../../include/dpmm_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+struct StatsItem;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+enum TimingKind {
+  TK_LABEL = 0,     // fused log-likelihood + label draw
+  TK_SORT,          // histogram / scan / scatter
+  TK_SUBLABEL,      // sub-label draw + left/right partition
+  TK_STATS,         // segmented sufficient statistics
+  TK_STATS_AUX,     // work list + finalise/pack
+  TK_RELABEL,       // LUT relabel / init
+  TK_ALLREDUCE,     // NCCL all-reduce of the packed statistics
+  TK_COUNT
+};
+static const char* const kTimingNames[TK_COUNT] = {"label", "sort", "sublabel", "stats", "stats_aux", "relabel", "allreduce"};
+
+struct TimedEvent {
+  cudaEvent_t a, b;
+  int kind;
+};
+
+struct UidBlob {  // layout of ncclUniqueId (128 opaque bytes, passed by value)
+  char b[128];
+};
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, UidBlob, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+struct dpmm_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  int64_t n = 0;
+  int D = 0;
+  int prior = 0;
+  uint64_t seed = 0;
+  int64_t goff = 0;
+  uint32_t call = 0;
+  int sampler = 0;
+  std::string err;
+
+  float* x = nullptr;
+  int32_t* labels = nullptr;
+  uint8_t* sub = nullptr;
+  int32_t* perm = nullptr;
+  int32_t* perm2 = nullptr;
+  double* u_label = nullptr;
+  double* u_sub = nullptr;
+  uint8_t* r_bits = nullptr;
+
+  // K-sized state
+  int K = 0, Kcap = 0;    // K = number of clusters of the last set_params
+  int label_bound = 1;    // every label value is < label_bound (0-based)
+  bool params_set = false;
+  int rec_f = 0;          // floats per distribution record (NIW) / D (multinomial)
+  float* recs = nullptr;  // [3K][rec_f]
+  float* cst = nullptr;   // [3K]
+  float* logw = nullptr;  // [K]
+  float* loglr = nullptr; // [2K]
+  // tensor-core label path (NIW, D == 32): stacked K-major factors, U mu, mu, |U|_F, TMA descriptor of X
+  float* tc_w = nullptr;
+  float* tc_b = nullptr;
+  float* tc_mu = nullptr;
+  float* tc_fro = nullptr;
+  int32_t* tc_stats = nullptr;
+  CUtensorMap tmap_x;
+  float* mtc_w = nullptr;   // multinomial tensor-core path: TF32-exact 3-way split of the log-probabilities
+  bool mtc_ok = false;      // multinomial: tensor map built and the counts are TF32-exact
+  bool mtc_params = false;
+  bool tc_ok = false;       // tensor map built
+  bool tc_params = false;   // tc_* describe the current parameters
+  float* logp_t = nullptr;  // multinomial [D][KP]
+  int KP = 0;
+  int32_t* hist = nullptr;
+  int32_t* seg_off = nullptr;
+  int32_t* scat_cursor = nullptr;
+  int32_t* lr_cursor = nullptr;
+  int32_t* lut_l = nullptr;
+  int32_t* lut_r = nullptr;
+  uint8_t* rule = nullptr;
+  uint8_t* wanted = nullptr;
+  int32_t* idx_list = nullptr;
+  int stats_rec = 0;
+  double* acc = nullptr;
+  double* outbuf = nullptr;
+  StatsItem* items = nullptr;
+  int64_t items_cap = 0;
+  int32_t* item_ctr = nullptr;  // [0]=n_items [1]=next_item
+  int chunk = 1024;
+
+  // pinned staging
+  void* hstage = nullptr;
+  size_t hstage_bytes = 0;
+
+  bool hist_valid = false, sorted = false, partitioned = false;
+  bool cursors_fresh = false;  // lr_cursor still holds the segment bounds (not yet consumed by a partition)
+  int64_t launches = 0;
+  bool timing = false;
+  std::vector<TimedEvent> tev;
+  std::vector<cudaEvent_t> ev_pool;
+  double t_ms[TK_COUNT] = {0};
+  int64_t t_n[TK_COUNT] = {0};
+
+  NcclApi nccl;
+  void* comm = nullptr;
+  int world = 1, rank = 0;
+};
+
+inline thread_local std::string g_err;
+
+inline int fail(dpmm_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(ctx, DPMM_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+  } while (0)
+#define NEED(cond, code, msg) \
+  do {                        \
+    if (!(cond)) return fail(ctx, code, msg); \
+  } while (0)
+
+struct KernelTimer {
+  dpmm_ctx* c;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int kind;
+  KernelTimer(dpmm_ctx* c_, int kind_, int nlaunch = 1) : c(c_), kind(kind_) {
+    c->launches += nlaunch;
+    if (c->timing) {
+      auto get = [&]() {
+        cudaEvent_t e;
+        if (!c->ev_pool.empty()) {
+          e = c->ev_pool.back();
+          c->ev_pool.pop_back();
+        } else {
+          cudaEventCreate(&e);
+        }
+        return e;
+      };
+      a = get();
+      b = get();
+      cudaEventRecord(a, c->stream);
+    }
+  }
+  ~KernelTimer() {
+    if (a) {
+      cudaEventRecord(b, c->stream);
+      c->tev.push_back(TimedEvent{a, b, kind});
+      c->t_n[kind] += 1;
+    }
+  }
+};
+
+inline int ensure_stage(dpmm_ctx* ctx, size_t bytes) {
+  if (ctx->hstage_bytes >= bytes) return 0;
+  if (ctx->hstage) cudaFreeHost(ctx->hstage);
+  ctx->hstage = nullptr;
+  ctx->hstage_bytes = 0;
+  size_t want = std::max(bytes, (size_t)1 << 20);
+  CK(cudaMallocHost(&ctx->hstage, want));
+  ctx->hstage_bytes = want;
+  return 0;
+}
+
+template <typename T>
+inline cudaError_t dev_realloc(T** p, size_t count) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+}
+
+// number of label values any K-sized table must cover
+inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// NIW feature dimensions with instantiated kernels, grouped into the translation units
+// launch_niw.cu is compiled into (DPMM_DIMSET = 0..5)
+#define DPMM_NIW_NSETS 6
+int niw_launch_label(dpmm_ctx* ctx, const struct GaussLabelArgs& a);
+int niw_launch_sublabel(dpmm_ctx* ctx, const struct SubLabelArgs& a, bool sample);
+int niw_launch_stats(dpmm_ctx* ctx, const struct StatsArgs& a);

@@ -2,9 +2,7 @@
 // One context = one GPU = one shard of points = one "worker" of the reference
 // (src/local_clusters_actions.jl *_worker! functions).  No CPU fallback exists: every entry point
 // needs a CUDA device and reports DPMM_ECUDA otherwise.
-#include "../../include/dpmm_b200.h"
 
-#include <cuda_runtime.h>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -22,187 +20,7 @@
 #include "kernels_sort.cuh"
 #include "kernels_stats.cuh"
 
-// ------------------------------------------------------------------------------------------------
-// context
-// ------------------------------------------------------------------------------------------------
-enum TimingKind {
-  TK_LABEL = 0,     // fused log-likelihood + label draw
-  TK_SORT,          // histogram / scan / scatter
-  TK_SUBLABEL,      // sub-label draw + left/right partition
-  TK_STATS,         // segmented sufficient statistics
-  TK_STATS_AUX,     // work list + finalise/pack
-  TK_RELABEL,       // LUT relabel / init
-  TK_ALLREDUCE,     // NCCL all-reduce of the packed statistics
-  TK_COUNT
-};
-static const char* kTimingNames[TK_COUNT] = {"label", "sort", "sublabel", "stats", "stats_aux", "relabel", "allreduce"};
-
-struct TimedEvent {
-  cudaEvent_t a, b;
-  int kind;
-};
-
-struct UidBlob {  // layout of ncclUniqueId (128 opaque bytes, passed by value)
-  char b[128];
-};
-struct NcclApi {
-  void* handle = nullptr;
-  int (*GetUniqueId)(void*) = nullptr;
-  int (*CommInitRank)(void**, int, UidBlob, int) = nullptr;
-  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
-  int (*CommDestroy)(void*) = nullptr;
-  const char* (*GetErrorString)(int) = nullptr;
-};
-struct dpmm_ctx {
-  int device = 0;
-  int sm_count = 148;
-  int smem_optin = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = true;
-  int64_t n = 0;
-  int D = 0;
-  int prior = 0;
-  uint64_t seed = 0;
-  int64_t goff = 0;
-  uint32_t call = 0;
-  int sampler = 0;
-  std::string err;
-
-  float* x = nullptr;
-  int32_t* labels = nullptr;
-  uint8_t* sub = nullptr;
-  int32_t* perm = nullptr;
-  int32_t* perm2 = nullptr;
-  double* u_label = nullptr;
-  double* u_sub = nullptr;
-  uint8_t* r_bits = nullptr;
-
-  // K-sized state
-  int K = 0, Kcap = 0;    // K = number of clusters of the last set_params
-  int label_bound = 1;    // every label value is < label_bound (0-based)
-  bool params_set = false;
-  int rec_f = 0;          // floats per distribution record (NIW) / D (multinomial)
-  float* recs = nullptr;  // [3K][rec_f]
-  float* cst = nullptr;   // [3K]
-  float* logw = nullptr;  // [K]
-  float* loglr = nullptr; // [2K]
-  // tensor-core label path (NIW, D == 32): stacked K-major factors, U mu, mu, |U|_F, TMA descriptor of X
-  float* tc_w = nullptr;
-  float* tc_b = nullptr;
-  float* tc_mu = nullptr;
-  float* tc_fro = nullptr;
-  int32_t* tc_stats = nullptr;
-  CUtensorMap tmap_x;
-  float* mtc_w = nullptr;   // multinomial tensor-core path: TF32-exact 3-way split of the log-probabilities
-  bool mtc_ok = false;      // multinomial: tensor map built and the counts are TF32-exact
-  bool mtc_params = false;
-  bool tc_ok = false;       // tensor map built
-  bool tc_params = false;   // tc_* describe the current parameters
-  float* logp_t = nullptr;  // multinomial [D][KP]
-  int KP = 0;
-  int32_t* hist = nullptr;
-  int32_t* seg_off = nullptr;
-  int32_t* scat_cursor = nullptr;
-  int32_t* lr_cursor = nullptr;
-  int32_t* lut_l = nullptr;
-  int32_t* lut_r = nullptr;
-  uint8_t* rule = nullptr;
-  uint8_t* wanted = nullptr;
-  int32_t* idx_list = nullptr;
-  int stats_rec = 0;
-  double* acc = nullptr;
-  double* outbuf = nullptr;
-  StatsItem* items = nullptr;
-  int64_t items_cap = 0;
-  int32_t* item_ctr = nullptr;  // [0]=n_items [1]=next_item
-  int chunk = 1024;
-
-  // pinned staging
-  void* hstage = nullptr;
-  size_t hstage_bytes = 0;
-
-  bool hist_valid = false, sorted = false, partitioned = false;
-  bool cursors_fresh = false;  // lr_cursor still holds the segment bounds (not yet consumed by a partition)
-  int64_t launches = 0;
-  bool timing = false;
-  std::vector<TimedEvent> tev;
-  std::vector<cudaEvent_t> ev_pool;
-  double t_ms[TK_COUNT] = {0};
-  int64_t t_n[TK_COUNT] = {0};
-
-  NcclApi nccl;
-  void* comm = nullptr;
-  int world = 1, rank = 0;
-};
-
-static thread_local std::string g_err;
-
-static int fail(dpmm_ctx* c, int code, const std::string& msg) {
-  if (c) c->err = msg;
-  g_err = msg;
-  return code;
-}
-#define CK(call)                                                                                   \
-  do {                                                                                             \
-    cudaError_t e__ = (call);                                                                      \
-    if (e__ != cudaSuccess)                                                                        \
-      return fail(ctx, DPMM_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
-  } while (0)
-#define NEED(cond, code, msg) \
-  do {                        \
-    if (!(cond)) return fail(ctx, code, msg); \
-  } while (0)
-
-struct KernelTimer {
-  dpmm_ctx* c;
-  cudaEvent_t a = nullptr, b = nullptr;
-  int kind;
-  KernelTimer(dpmm_ctx* c_, int kind_, int nlaunch = 1) : c(c_), kind(kind_) {
-    c->launches += nlaunch;
-    if (c->timing) {
-      auto get = [&]() {
-        cudaEvent_t e;
-        if (!c->ev_pool.empty()) {
-          e = c->ev_pool.back();
-          c->ev_pool.pop_back();
-        } else {
-          cudaEventCreate(&e);
-        }
-        return e;
-      };
-      a = get();
-      b = get();
-      cudaEventRecord(a, c->stream);
-    }
-  }
-  ~KernelTimer() {
-    if (a) {
-      cudaEventRecord(b, c->stream);
-      c->tev.push_back(TimedEvent{a, b, kind});
-      c->t_n[kind] += 1;
-    }
-  }
-};
-
-static int ensure_stage(dpmm_ctx* ctx, size_t bytes) {
-  if (ctx->hstage_bytes >= bytes) return 0;
-  if (ctx->hstage) cudaFreeHost(ctx->hstage);
-  ctx->hstage = nullptr;
-  ctx->hstage_bytes = 0;
-  size_t want = std::max(bytes, (size_t)1 << 20);
-  CK(cudaMallocHost(&ctx->hstage, want));
-  ctx->hstage_bytes = want;
-  return 0;
-}
-
-template <typename T>
-static cudaError_t dev_realloc(T** p, size_t count) {
-  if (*p) cudaFree(*p);
-  *p = nullptr;
-  return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
-}
-
-// number of label values any K-sized table must cover
+#include "ctx.cuh"
 static int keff(const dpmm_ctx* c) { return std::max(std::max(c->K, c->label_bound), 1); }
 
 static int nrec_floats(const dpmm_ctx* c) {
@@ -258,14 +76,9 @@ static int ensure_k(dpmm_ctx* ctx, int K) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// template dispatch over the feature dimension (NIW)
+// dispatch over the feature dimension (NIW): the kernels live in launch_niw.cu, one object per set
 // ------------------------------------------------------------------------------------------------
 #define DPMM_NIW_DIMS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(12) X(16) X(24) X(32) X(48) X(64)
-
-template <int D>
-struct LabelP {  // points per thread of the label kernel
-  static constexpr int P = (D <= 16) ? 4 : (D <= 32 ? 2 : 1);
-};
 
 static bool niw_dim_supported(int D) {
   switch (D) {
@@ -278,126 +91,37 @@ static bool niw_dim_supported(int D) {
   }
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
-}
+#define DECL_SET(n)                                                                              \
+  int niw_set_label_##n(dpmm_ctx*, const GaussLabelArgs&, int, int*);                            \
+  int niw_set_sublabel_##n(dpmm_ctx*, const SubLabelArgs&, bool, int, int*);                     \
+  int niw_set_stats_##n(dpmm_ctx*, const StatsArgs&, int, int*);
+DECL_SET(0) DECL_SET(1) DECL_SET(2) DECL_SET(3) DECL_SET(4) DECL_SET(5)
+#undef DECL_SET
 
-template <int D, int P>
-static int launch_gauss_label_p(dpmm_ctx* ctx, GaussLabelArgs a) {
-  using C = GaussCfg<D>;
-  {
-    // warp-autonomous form: all K records resident + W private warp buffers
-    const size_t fixed = ((size_t)a.K * C::REC + ((a.K + 3) & ~3)) * 4;
-    const size_t perwarp = ((size_t)32 * P * C::DS + (size_t)a.K * 32 * P) * 4;
-    int W = fixed < (size_t)ctx->smem_optin ? (int)(((size_t)ctx->smem_optin - fixed) / perwarp) : 0;
-    W = std::min(W, 12);
-    W = env_int("DPMM_LABEL_W", W);
-    if (W >= 6 && env_int("DPMM_LABEL_FORM", 1) == 1) {
-      const size_t sm = fixed + (size_t)W * perwarp;
-      auto kern = gauss_label_warp_kernel<D, P>;
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      a.KC = a.K;
-      a.ntiles = (a.n + 32 * P - 1) / (32 * P);
-      const int64_t grid = std::min<int64_t>((a.ntiles + W - 1) / W, (int64_t)ctx->sm_count);
-      KernelTimer kt(ctx, TK_LABEL);
-      kern<<<(unsigned)grid, W * 32, sm, ctx->stream>>>(a);
-      CK(cudaGetLastError());
-      return 0;
-    }
-  }
-  const size_t budget2 = 110 * 1024, budget1 = (size_t)ctx->smem_optin;
-  int T = 128, KC = a.K;
-  auto bytes = [&](int T_, int KC_) {
-    return ((size_t)T_ * P * C::DS + (size_t)a.K * T_ * P + (size_t)KC_ * C::REC) * 4 + (size_t)a.K * 4;
-  };
-  // prefer two CTAs per SM; shrink the staged-cluster chunk first, then the tile
-  bool ok = false;
-  for (size_t budget : {budget2, budget1}) {
-    for (int T_ : {128, 64, 32}) {
-      if (bytes(T_, 1) > budget) continue;
-      T = T_;
-      KC = a.K;
-      while (bytes(T, KC) > budget) KC = (KC + 1) / 2;
-      ok = true;
-      break;
-    }
-    if (ok) break;
-  }
-  if (!ok) return fail(ctx, DPMM_ELIMIT, "K too large for the label kernel's shared-memory slice");
-  // development overrides (tools/): DPMM_LABEL_T / DPMM_LABEL_KC
-  T = env_int("DPMM_LABEL_T", T);
-  KC = std::min(a.K, env_int("DPMM_LABEL_KC", KC));
-  if (bytes(T, KC) > budget1) return fail(ctx, DPMM_ELIMIT, "label kernel override exceeds shared memory");
-  a.KC = KC;
-  const int TP = T * P;
-  a.ntiles = (a.n + TP - 1) / TP;
-  const size_t sm = bytes(T, KC);
-  auto kern = gauss_label_kernel<D, P>;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  int occ = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, sm));
-  occ = std::max(occ, 1);
-  const int64_t grid = std::min<int64_t>(a.ntiles, (int64_t)ctx->sm_count * occ);
-  KernelTimer kt(ctx, TK_LABEL);
-  kern<<<(unsigned)grid, T, sm, ctx->stream>>>(a);
-  CK(cudaGetLastError());
-  return 0;
+int niw_launch_label(dpmm_ctx* ctx, const GaussLabelArgs& a) {
+  int rc = DPMM_ELIMIT;
+  const int D = ctx->D;
+  if (niw_set_label_0(ctx, a, D, &rc) && niw_set_label_1(ctx, a, D, &rc) && niw_set_label_2(ctx, a, D, &rc) &&
+      niw_set_label_3(ctx, a, D, &rc) && niw_set_label_4(ctx, a, D, &rc) && niw_set_label_5(ctx, a, D, &rc))
+    return fail(ctx, DPMM_ELIMIT, "NIW: no kernel instantiated for this D");
+  return rc;
 }
-
-template <int D>
-static int launch_gauss_label(dpmm_ctx* ctx, GaussLabelArgs a) {
-#ifdef DPMM_EXPERIMENT
-  if constexpr (D == 32) {
-    const int p = env_int("DPMM_LABEL_P", LabelP<D>::P);
-    if (p == 1) return launch_gauss_label_p<D, 1>(ctx, a);
-    if (p == 4) return launch_gauss_label_p<D, 4>(ctx, a);
-  }
-#endif
-  return launch_gauss_label_p<D, LabelP<D>::P>(ctx, a);
+int niw_launch_sublabel(dpmm_ctx* ctx, const SubLabelArgs& a, bool sample) {
+  int rc = DPMM_ELIMIT;
+  const int D = ctx->D;
+  if (niw_set_sublabel_0(ctx, a, sample, D, &rc) && niw_set_sublabel_1(ctx, a, sample, D, &rc) &&
+      niw_set_sublabel_2(ctx, a, sample, D, &rc) && niw_set_sublabel_3(ctx, a, sample, D, &rc) &&
+      niw_set_sublabel_4(ctx, a, sample, D, &rc) && niw_set_sublabel_5(ctx, a, sample, D, &rc))
+    return fail(ctx, DPMM_ELIMIT, "NIW: no kernel instantiated for this D");
+  return rc;
 }
-
-template <int D>
-static int launch_gauss_sublabel(dpmm_ctx* ctx, const SubLabelArgs& a, bool sample) {
-  if constexpr (D % 4 == 0 && D >= 16 && D <= 48) {
-    if (sample && env_int("DPMM_SUBLABEL_P2", 1)) {
-      using C = GaussCfg<D>;
-      const size_t sm = ((size_t)2 * 256 * C::DS + (size_t)SUBLABEL_SPAN * 2 * C::REC + a.K + 4) * 4;
-      auto kern = gauss_sublabel2_kernel<D>;
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      int occ = 1;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, sm));
-      const int64_t ntiles = (a.n + 255) / 256;
-      const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * std::max(occ, 1));
-      KernelTimer kt(ctx, TK_SUBLABEL);
-      kern<<<grid, 128, sm, ctx->stream>>>(a);
-      CK(cudaGetLastError());
-      return 0;
-    }
-  }
-  const int T = 128;
-  const unsigned grid = (unsigned)((a.n + T - 1) / T);
-  KernelTimer kt(ctx, TK_SUBLABEL);
-  if (sample)
-    gauss_sublabel_kernel<D, true><<<grid, T, 0, ctx->stream>>>(a);
-  else
-    gauss_sublabel_kernel<D, false><<<grid, T, 0, ctx->stream>>>(a);
-  CK(cudaGetLastError());
-  return 0;
-}
-
-template <int D>
-static int launch_niw_stats(dpmm_ctx* ctx, const StatsArgs& a) {
-  using C = StatsCfg<D>;
-  auto kern = niw_stats_kernel<D>;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  int occ = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::WARPS * 32, C::SMEM_BYTES));
-  occ = std::max(occ, 1);
-  KernelTimer kt(ctx, TK_STATS);
-  kern<<<ctx->sm_count * occ, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(a);
-  CK(cudaGetLastError());
-  return 0;
+int niw_launch_stats(dpmm_ctx* ctx, const StatsArgs& a) {
+  int rc = DPMM_ELIMIT;
+  const int D = ctx->D;
+  if (niw_set_stats_0(ctx, a, D, &rc) && niw_set_stats_1(ctx, a, D, &rc) && niw_set_stats_2(ctx, a, D, &rc) &&
+      niw_set_stats_3(ctx, a, D, &rc) && niw_set_stats_4(ctx, a, D, &rc) && niw_set_stats_5(ctx, a, D, &rc))
+    return fail(ctx, DPMM_ELIMIT, "NIW: no kernel instantiated for this D");
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1021,12 +745,7 @@ static int run_sample_labels(dpmm_ctx* ctx, int final_iter, float* dump) {
     a.x = ctx->x; a.n = ctx->n; a.K = K; a.recs = ctx->recs; a.cst = ctx->cst; a.logw = ctx->logw;
     a.labels = ctx->labels; a.hist = ctx->hist; a.u_inj = ctx->u_label; a.seed = ctx->seed; a.call = ctx->call;
     a.goff = ctx->goff; a.final_iter = final_iter; a.sampler = ctx->sampler; a.dump = dump;
-    int rc = DPMM_ELIMIT;
-    switch (ctx->D) {
-#define X(d) case d: rc = launch_gauss_label<d>(ctx, a); break;
-      DPMM_NIW_DIMS(X)
-#undef X
-    }
+    int rc = niw_launch_label(ctx, a);
     if (rc) return rc;
   } else if (ctx->mtc_params && dump == nullptr && env_int("DPMM_LABEL_TC", 1) != 0) {
     // K3 on tcgen05: exact TF32 3-way split GEMM of counts x log-probabilities
@@ -1115,12 +834,7 @@ static int run_sublabels(dpmm_ctx* ctx, bool sample, float* dump) {
   a.seg_off = ctx->seg_off;
   a.u_inj = ctx->u_sub; a.seed = ctx->seed; a.call = ctx->call; a.goff = ctx->goff; a.dump = dump; a.D = ctx->D;
   if (ctx->prior == DPMM_PRIOR_NIW) {
-    rc = DPMM_ELIMIT;
-    switch (ctx->D) {
-#define X(d) case d: rc = launch_gauss_sublabel<d>(ctx, a, sample); break;
-      DPMM_NIW_DIMS(X)
-#undef X
-    }
+    rc = niw_launch_sublabel(ctx, a, sample);
     if (rc) return rc;
   } else {
     const int T = 128;
@@ -1208,12 +922,7 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
   sa.x = ctx->x; sa.D = D; sa.perm2 = ctx->perm2; sa.items = ctx->items; sa.n_items = ctx->item_ctr;
   sa.next_item = ctx->item_ctr + 1; sa.acc = ctx->acc; sa.rec = rec;
   if (ctx->prior == DPMM_PRIOR_NIW) {
-    rc = DPMM_ELIMIT;
-    switch (D) {
-#define X(d) case d: rc = launch_niw_stats<d>(ctx, sa); break;
-      DPMM_NIW_DIMS(X)
-#undef X
-    }
+    rc = niw_launch_stats(ctx, sa);
     if (rc) return rc;
   } else {
     int occ = 1;

@@ -20,6 +20,7 @@ struct StatsItem {
   int32_t end;
 };
 
+#ifndef DPMM_TEMPLATES_ONLY
 // Builds the work list: for every wanted cluster k, its left run [seg_off[k], lr_cursor[2k]) and
 // right run [lr_cursor[2k], seg_off[k+1]) cut into chunks of `chunk` points.  Single CTA.
 __global__ void stats_worklist_kernel(const int32_t* __restrict__ seg_off, const int32_t* __restrict__ lr_cursor,
@@ -58,6 +59,8 @@ __global__ void stats_worklist_kernel(const int32_t* __restrict__ seg_off, const
     for (int s = b; s < e; s += chunk) items[o++] = StatsItem{key, s, min(e, s + chunk)};
   }
 }
+
+#endif  // DPMM_TEMPLATES_ONLY
 
 // Transposed warp reduction: on entry every lane holds EP partial sums v[0..EP); on exit lane l
 // holds in v[0..EP/32) the warp totals of entries  e = (bits of l, MSB first) * (EP/2, EP/4, ...) + j.
@@ -292,6 +295,7 @@ niw_stats_kernel(const StatsArgs a) {
   }
 }
 
+#ifndef DPMM_TEMPLATES_ONLY
 // K6: multinomial.  sum x per key.  One warp per work item (a run of points with one (label, side)
 // key); lane l owns the features l, l+32, ... so every point is read as fully coalesced 128-byte
 // segments straight from global memory (no staging), with MNM_STATS_UNROLL points in flight per
@@ -394,3 +398,5 @@ __global__ void stats_finalize_kernel(const double* __restrict__ acc, const int3
     o[2 * rec + e] = r;
   }
 }
+
+#endif  // DPMM_TEMPLATES_ONLY
