@@ -240,6 +240,7 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
   float* csm = reinterpret_cast<float*>(smem + L.consts);  // c_k
   float* lwsm = csm + K;                                   // log w_k
   float* frosm = lwsm + K;                                 // |U_k|_F
+  float* ccsm = frosm + K;                                 // log w_k - c_k
   float* rs_all = reinterpret_cast<float*>(smem + L.rs);
   uint16_t* pairs_all = reinterpret_cast<uint16_t*>(smem + L.pairs);
   int* cnt_all = reinterpret_cast<int*>(smem + L.cnt);
@@ -295,6 +296,7 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
     csm[k] = __ldg(a.cst + 3 * k);
     lwsm[k] = __ldg(a.logw + k);
     frosm[k] = __ldg(a.fro + k);
+    ccsm[k] = __ldg(a.logw + k) - __ldg(a.cst + 3 * k);
     hs[k] = 0;
   }
   tc::fence_proxy_async();  // generic-proxy writes of W must be visible to the tensor core's async proxy
@@ -360,24 +362,32 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
     int ncand_total = 0, npts_total = 0;
     for (int64_t tile = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; tile < a.ntiles; tile += 2 * (int64_t)gridDim.x, ++li) {
       const int s = g * 2 + (li & 1);
-      // ---- screen: q~_k for every cluster from the TMEM accumulators ----
-      for (int c = 0; c < nch; ++c, ++cc) {
-        const int b = cc & 1;
-        tc::mbar_wait(&tfull[g * 2 + b], (cc >> 1) & 1);
-        tc::tc_fence_after();
-        const int ncl = min(TC_NCL, K - c * TC_NCL);
-        const uint32_t taddr = tmem_row + b * 128;
-        for (int kl = 0; kl < ncl; kl += 2) {
-          uint32_t v0[32], v1[32];
-          tc::tmem_ld32(taddr + kl * TC_D, v0);
-          if (kl + 1 < ncl) tc::tmem_ld32(taddr + (kl + 1) * TC_D, v1);
-          tc::tmem_ld_wait();
-          const int k = c * TC_NCL + kl;
-          rs[k * TC_TILE] = gauss_tc_screen_q(v0);
-          if (kl + 1 < ncl) rs[(k + 1) * TC_TILE] = gauss_tc_screen_q(v1);
+      // ---- screen: q~_k for every cluster from the TMEM accumulators (kept in registers: the
+      //      chunk / cluster loops are fully unrolled so that qt[] is indexed at compile time) ----
+      float qt[TC_MAX_K + 1];
+#pragma unroll
+      for (int c = 0; c < (TC_MAX_K + TC_NCL) / TC_NCL; ++c) {
+        if (c < nch) {
+          const int b = cc & 1;
+          tc::mbar_wait(&tfull[g * 2 + b], (cc >> 1) & 1);
+          tc::tc_fence_after();
+          const int ncl = min(TC_NCL, K - c * TC_NCL);
+          const uint32_t taddr = tmem_row + b * 128;
+#pragma unroll
+          for (int kl = 0; kl < TC_NCL; kl += 2) {
+            if (kl < ncl) {
+              uint32_t v0[32], v1[32];
+              tc::tmem_ld32(taddr + kl * TC_D, v0);
+              if (kl + 1 < ncl) tc::tmem_ld32(taddr + (kl + 1) * TC_D, v1);
+              tc::tmem_ld_wait();
+              qt[c * TC_NCL + kl] = gauss_tc_screen_q(v0);
+              if (kl + 1 < ncl) qt[c * TC_NCL + kl + 1] = gauss_tc_screen_q(v1);
+            }
+          }
+          tc::tc_fence_before();
+          tc::mbar_arrive(&tempty[g * 2 + b]);
+          ++cc;
         }
-        tc::tc_fence_before();
-        tc::mbar_arrive(&tempty[g * 2 + b]);
       }
       // ---- the point itself (the TMA wrote it with the 128B swizzle) ----
       tc::mbar_wait(&full[s], (li >> 1) & 1);
@@ -397,29 +407,33 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
         // ---- candidates: upper bound of r_k within DELTA of the best lower bound ----
         const float xnorm = sqrtf(xn) * (1.f / 512.f);   // 2^-9 |x|
         float best_lo = -CUDART_INF_F;
-        for (int k = 0; k < K; ++k) {
-          const float qt = rs[k * TC_TILE];
-          const float e = xnorm * frosm[k];
-          float sq;
-          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(fmaxf(qt, 0.f)));
-          const float dr = fmaf(1.01f * sq, e, fmaf(0.5f * e, e, 0.01f));   // |r~ - r| <= sqrt(q~) e + e^2/2
-          const float rt = lwsm[k] - csm[k] - 0.5f * qt;
-          weird |= !(fabsf(rt) < CUDART_INF_F) || !(dr < CUDART_INF_F);
-          best_lo = fmaxf(best_lo, rt - dr);
-          rs[k * TC_TILE] = rt + dr;                     // upper bound
+#pragma unroll
+        for (int k = 0; k < TC_MAX_K; ++k) {
+          if (k < K) {
+            const float e = xnorm * frosm[k];
+            float sq;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(fmaxf(qt[k], 0.f)));
+            const float dr = fmaf(1.01f * sq, e, fmaf(0.5f * e, e, 0.01f));   // |r~ - r| <= sqrt(q~) e + e^2/2
+            const float rt = fmaf(-0.5f, qt[k], ccsm[k]);
+            weird |= !(fabsf(rt) < CUDART_INF_F) || !(dr < CUDART_INF_F);
+            best_lo = fmaxf(best_lo, rt - dr);
+            qt[k] = rt + dr;                               // upper bound of r_k
+          }
         }
         const float thr = best_lo - TC_DELTA;
-        for (int k = 0; k < K; ++k) {
-          const bool cand = valid && (weird || rs[k * TC_TILE] >= thr);
-          if (cand) mask |= 1u << k;
-          else rs[k * TC_TILE] = -CUDART_INF_F;          // exactly-zero weight in the draw
-        }
+#pragma unroll
+        for (int k = 0; k < TC_MAX_K; ++k)
+          if (k < K && valid && (weird || qt[k] >= thr)) mask |= 1u << k;
       }
+      // A point with a single candidate is decided: every other cluster has weight exactly 0 in the
+      // draw, so its label is that cluster whatever the exact value is -- no refinement needed.
+      const bool multi = __popc(mask) > 1;
+      const uint32_t rmask = multi ? mask : 0u;
       // ---- regroup the (point, cluster) candidates by cluster so that a warp refines one cluster ----
       // (counting sort over <= 24 keys in shared memory: count, prefix, scatter)
       if (gt < 32) cnt[gt] = 0;
       group_barrier(g);
-      for (uint32_t m = mask; m; m &= m - 1) atomicAdd(&cnt[__ffs(m) - 1], 1);
+      for (uint32_t m = rmask; m; m &= m - 1) atomicAdd(&cnt[__ffs(m) - 1], 1);
       group_barrier(g);
       if (gt == 0) {
         int run = 0;
@@ -431,7 +445,7 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
         cnt[32] = run;
       }
       group_barrier(g);
-      for (uint32_t m = mask; m; m &= m - 1) {
+      for (uint32_t m = rmask; m; m &= m - 1) {
         const int k = __ffs(m) - 1;
         pairs[atomicAdd(&cnt[k], 1)] = (uint16_t)((row << 5) | k);
       }
@@ -457,8 +471,27 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
       // ---- draw ----
       if (valid) {
         int lab;
-        if (a.final_iter) {
-          lab = dpmm_draw_argmax(rs, TC_TILE, K);
+        if (!multi) {
+          lab = __ffs(mask) - 1;
+          // the walk of utils.jl:29 stops at i = 1 when t = u * sum(w) is 0, i.e. for the uniform u == 0
+          if (lab > 0 && !a.final_iter &&
+              dpmm_uniform(a.u_inj, i, a.seed, DPMM_STREAM_LABEL, a.call, (uint64_t)(a.goff + i)) == 0.0)
+            lab = 0;
+        } else if (a.final_iter) {
+          if (weird) {
+            lab = dpmm_draw_argmax(rs, TC_TILE, K);
+          } else {   // first maximum among the candidates (a non-candidate is > 30 below the maximum)
+            lab = 0;
+            float bv = -CUDART_INF_F;
+            for (uint32_t m = mask; m; m &= m - 1) {
+              const int k = __ffs(m) - 1;
+              const float v = rs[k * TC_TILE];
+              if (v > bv) {
+                bv = v;
+                lab = k;
+              }
+            }
+          }
         } else {
           const double u = dpmm_uniform(a.u_inj, i, a.seed, DPMM_STREAM_LABEL, a.call, (uint64_t)(a.goff + i));
           lab = weird ? dpmm_draw_inverse_cdf(rs, TC_TILE, K, u) : dpmm_draw_inverse_cdf_masked(rs, TC_TILE, K, mask, u);
