@@ -46,6 +46,31 @@ def test_niw_full_sweep_parity(pkg, D, K, n):
     print(f"D={D} K={K} n={n}: {rep}")
 
 
+@pytest.mark.parametrize("spread,K,n", [(0.3, 12, 20000), (0.0, 5, 8000), (1.0, 23, 12000)])
+def test_niw_tensor_core_refine_path_with_overlapping_clusters(pkg, spread, K, n):
+    """D=32 runs on the tcgen05 screen+refine kernel.  Heavily overlapping (or identical-centre)
+    clusters make most points multi-candidate, so the FP32 refinement and the masked draw decide
+    the labels; parity with the oracle must hold there too (incl. the final argmax mode)."""
+    case = make_niw_case(32, K, n, seed=int(10 * spread) + K, spread=spread)
+    for final in (False, True):
+        g = pkg.GpuSweep(case["x"], pkg.NIW, seed=7)
+        o = O.OracleSweep(case["x"], O.NIW, seed=7)
+        rep = compare_sweeps(g, o, case, np.random.default_rng(K), final=final)
+        g.close()
+    import os
+    os.environ["DPMM_TC_STATS"] = "1"
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=7)
+    set_params(g, case)
+    g.sample_labels(False)
+    npts, ncand = g.tc_stats()
+    g.close()
+    os.environ.pop("DPMM_TC_STATS")
+    assert npts == n, "the tensor-core path did not run"
+    print(f"spread={spread} K={K}: refined evaluations per point = {ncand / npts:.2f}")
+    if spread <= 0.3:
+        assert ncand > npts          # the refine path really was exercised
+
+
 @pytest.mark.parametrize("D,K,n", [(2, 6, 5000), (32, 20, 10000), (64, 4, 2000)])
 def test_niw_final_argmax_parity(pkg, D, K, n):
     case = make_niw_case(D, K, n, seed=5)
