@@ -75,6 +75,7 @@ struct dpmm_ctx {
   int label_bound = 1;    // every label value is < label_bound (0-based)
   bool params_set = false;
   int rec_f = 0;          // floats per distribution record (NIW) / D (multinomial)
+  float* raw_params = nullptr;  // NIW: [3K](mu[D] | invSigma[D][D] | logdet) as uploaded, input of niw_pack_kernel
   float* recs = nullptr;  // [3K][rec_f]
   float* cst = nullptr;   // [3K]
   float* logw = nullptr;  // [K]

@@ -17,6 +17,7 @@
 #include "kernels_gauss_tc.cuh"
 #include "kernels_mnm.cuh"
 #include "kernels_mnm_tc.cuh"
+#include "kernels_pack.cuh"
 #include "kernels_sort.cuh"
 #include "kernels_stats.cuh"
 
@@ -41,6 +42,7 @@ static int ensure_k(dpmm_ctx* ctx, int K) {
   ctx->stats_rec = (ctx->prior == DPMM_PRIOR_NIW) ? 1 + D + D * D : 1 + D;
   // preserve nothing: all K-sized buffers are rewritten by the next set_params / sort
   CK(dev_realloc(&ctx->recs, (size_t)3 * cap * ctx->rec_f));
+  if (ctx->prior == DPMM_PRIOR_NIW) CK(dev_realloc(&ctx->raw_params, (size_t)3 * cap * (D + D * D + 1)));
   CK(dev_realloc(&ctx->cst, (size_t)3 * cap));
   CK(dev_realloc(&ctx->logw, (size_t)cap));
   CK(dev_realloc(&ctx->loglr, (size_t)2 * cap));
@@ -258,7 +260,7 @@ extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
   }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   void* ptrs[] = {ctx->x, ctx->labels, ctx->sub, ctx->perm, ctx->perm2, ctx->u_label, ctx->u_sub, ctx->r_bits,
-                  ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->tc_w, ctx->tc_b, ctx->tc_mu, ctx->tc_fro, ctx->tc_stats, ctx->mtc_w, ctx->hist, ctx->seg_off,
+                  ctx->raw_params, ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->tc_w, ctx->tc_b, ctx->tc_mu, ctx->tc_fro, ctx->tc_stats, ctx->mtc_w, ctx->hist, ctx->seg_off,
                   ctx->scat_cursor, ctx->lr_cursor, ctx->lut_l, ctx->lut_r, ctx->rule, ctx->wanted,
                   ctx->idx_list, ctx->acc, ctx->outbuf, ctx->items, ctx->item_ctr};
   for (void* p : ptrs)
@@ -569,81 +571,40 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
   const int D = ctx->D, REC = ctx->rec_f, TRIP = gauss_col_off(D);
   const size_t nrec = (size_t)3 * K;
   const bool tcp = ctx->tc_ok && K <= TC_MAX_K;
-  const int nch = (K + TC_NCL - 1) / TC_NCL;
-  const size_t wfl = (size_t)nch * TC_NCL * TC_D * TC_D;   // factor floats incl. zero padding
-  const size_t tc_floats = tcp ? wfl + (size_t)2 * K * TC_D + K : 0;
-  const size_t bytes = (nrec * REC + nrec + K + 2 * K + tc_floats) * sizeof(float);
+  // raw parameters -> pinned staging -> device; the factorisation and packing run on the device
+  const size_t raw_floats = nrec * D + nrec * D * D + nrec;
+  const size_t bytes = (raw_floats + K + 2 * K) * sizeof(float);
   rc = ensure_stage(ctx, bytes);
   if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));  // staging buffer reuse
-  float* h_recs = (float*)ctx->hstage;
-  float* h_cst = h_recs + nrec * REC;
-  float* h_logw = h_cst + nrec;
+  float* h_mu = (float*)ctx->hstage;
+  float* h_inv = h_mu + nrec * D;
+  float* h_ld = h_inv + nrec * D * D;
+  float* h_logw = h_ld + nrec;
   float* h_loglr = h_logw + K;
-  float* h_w = h_loglr + 2 * K;                       // [nch * 4][32][32]
-  float* h_b = h_w + (tcp ? wfl : 0);
-  float* h_mu = h_b + (tcp ? (size_t)K * TC_D : 0);
-  float* h_fro = h_mu + (tcp ? (size_t)K * TC_D : 0);
-  if (tcp) std::fill(h_w, h_w + wfl, 0.f);
-  std::vector<double> L((size_t)D * D);
-  const float log2pi = (float)std::log(2.0 * M_PI);  // Float32(log(2pi)), mv_gaussian.jl:24
-  for (size_t t = 0; t < nrec; ++t) {
-    const float* A = inv_sigma + t * D * D;
-    float* rec = h_recs + t * REC;
-    std::fill(rec, rec + REC, 0.f);
-    // Cholesky A = L L' in Float64; U = L' (upper), so z'Az = |U z|^2.
-    bool ok = true;
-    for (int j = 0; j < D && ok; ++j) {
-      double s = 0.5 * ((double)A[(size_t)j * D + j] + (double)A[(size_t)j * D + j]);
-      for (int p = 0; p < j; ++p) s -= L[(size_t)j * D + p] * L[(size_t)j * D + p];
-      if (!(s > 0.0) || !std::isfinite(s)) {
-        ok = false;
-        break;
-      }
-      const double ljj = std::sqrt(s);
-      L[(size_t)j * D + j] = ljj;
-      for (int i = j + 1; i < D; ++i) {
-        double v = 0.5 * ((double)A[(size_t)i * D + j] + (double)A[(size_t)j * D + i]);
-        for (int p = 0; p < j; ++p) v -= L[(size_t)i * D + p] * L[(size_t)j * D + p];
-        L[(size_t)i * D + j] = v / ljj;
-      }
-    }
-    for (int j = 0; j < D; ++j) {  // column j of U = row j of L, padded to a multiple of 4 floats
-      const int off = gauss_col_off(j);
-      for (int i = 0; i <= j; ++i) rec[off + i] = ok ? (float)L[(size_t)j * D + i] : NAN;  // U[i][j] = L[j][i]
-    }
-    for (int j = 0; j < D; ++j) rec[TRIP + j] = mu[t * D + j];
-    h_cst[t] = ((float)(D * D) * log2pi + logdet[t]) / 2.f;
-    if (tcp && t % 3 == 0) {  // K2 operands of the cluster distribution: rows of U, U mu, mu, |U|_F
-      const int k = (int)(t / 3);
-      double fro = 0.0;
-      for (int i = 0; i < D; ++i) {
-        double bi = 0.0;
-        for (int j = i; j < D; ++j) {
-          const float u = ok ? (float)L[(size_t)j * D + i] : NAN;
-          h_w[((size_t)k * D + i) * D + j] = u;
-          bi += (double)u * (double)mu[t * D + j];
-          fro += (double)u * (double)u;
-        }
-        h_b[(size_t)k * D + i] = (float)bi;
-        h_mu[(size_t)k * D + i] = mu[t * D + i];
-      }
-      h_fro[k] = (float)std::sqrt(fro);
-    }
-  }
+  memcpy(h_mu, mu, nrec * D * 4);
+  memcpy(h_inv, inv_sigma, nrec * D * D * 4);
+  memcpy(h_ld, logdet, nrec * 4);
   common_weights(ctx, K, weights, lr_weights, h_logw, h_loglr);
-  CK(cudaMemcpyAsync(ctx->recs, h_recs, nrec * REC * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->cst, h_cst, nrec * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->raw_params, h_mu, raw_floats * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->logw, h_logw, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->loglr, h_loglr, (size_t)2 * K * 4, cudaMemcpyHostToDevice, ctx->stream));
   ctx->tc_params = false;
   if (tcp) {
-    CK(cudaMemcpyAsync(ctx->tc_w, h_w, wfl * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->tc_b, h_b, (size_t)K * TC_D * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->tc_mu, h_mu, (size_t)K * TC_D * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->tc_fro, h_fro, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->tc_params = true;
+    const size_t wfl = (size_t)((K + TC_NCL - 1) / TC_NCL) * TC_NCL * TC_D * TC_D;
+    CK(cudaMemsetAsync(ctx->tc_w, 0, wfl * 4, ctx->stream));   // zero padding of the last chunk
   }
+  {
+    NiwPackArgs pa{};
+    pa.D = D; pa.K = K; pa.rec_f = REC; pa.trip = TRIP;
+    pa.mu = ctx->raw_params; pa.inv_sigma = ctx->raw_params + nrec * D; pa.logdet = ctx->raw_params + nrec * D + nrec * D * D;
+    pa.recs = ctx->recs; pa.cst = ctx->cst;
+    pa.tc_w = tcp ? ctx->tc_w : nullptr; pa.tc_b = ctx->tc_b; pa.tc_mu = ctx->tc_mu; pa.tc_fro = ctx->tc_fro;
+    KernelTimer kt(ctx, TK_RELABEL);
+    niw_pack_kernel<<<(unsigned)nrec, 32, (size_t)D * (D + 1) * sizeof(double), ctx->stream>>>(pa);
+    CK(cudaGetLastError());
+  }
+  ctx->tc_params = tcp;
   ctx->K = K;
   ctx->params_set = true;
   return 0;

@@ -1,0 +1,82 @@
+// Parameter packing on the device: broadcast_cluster_params (src/local_clusters_actions.jl:518-549)
+// ships mv_gaussian fields (mu, invSigma, logdetSigma; mv_gaussian.jl:12-18); this kernel turns them
+// into what the sweep kernels read.  One warp per distribution:
+//   invSigma (Float32, symmetrised) -> Float64 Cholesky  invSigma = L L'  -> U = L' rounded to Float32,
+//   stored by columns (FMA path records) and, for the cluster distributions of the tensor-core path,
+//   by rows (K-major B operand) with b = U mu and |U|_F;  c = (D^2 * Float32(log 2pi) + logdetSigma)/2.
+// The reference carries the same factor (mv_gaussian.invChol, niw.jl:38-39).  A non positive definite
+// or NaN input gives NaN factors, i.e. NaN log-likelihoods, exactly like the reference's arithmetic.
+#pragma once
+#include "common.cuh"
+#include "kernels_gauss.cuh"   // gauss_col_off
+
+struct NiwPackArgs {
+  int D, K, rec_f, trip;
+  const float* mu;         // [3K][D]
+  const float* inv_sigma;  // [3K][D][D]
+  const float* logdet;     // [3K]
+  float* recs;             // [3K][rec_f]
+  float* cst;              // [3K]
+  float* tc_w;             // [K4][D][D] or nullptr
+  float* tc_b;             // [K][D]
+  float* tc_mu;            // [K][D]
+  float* tc_fro;           // [K]
+};
+
+__global__ void __launch_bounds__(32) niw_pack_kernel(const NiwPackArgs a) {
+  extern __shared__ double Ls[];   // [D][D+1]
+  const int D = a.D, LD = D + 1;
+  const int t = blockIdx.x, lane = threadIdx.x;
+  const float* A = a.inv_sigma + (size_t)t * D * D;
+  for (int e = lane; e < D * D; e += 32) {
+    const int i = e / D, j = e - i * D;
+    Ls[i * LD + j] = 0.5 * ((double)A[(size_t)i * D + j] + (double)A[(size_t)j * D + i]);
+  }
+  __syncwarp();
+  bool ok = true;
+  for (int j = 0; j < D; ++j) {
+    const double d = Ls[j * LD + j];
+    ok = ok && (d > 0.0) && (d < CUDART_INF);
+    const double ljj = sqrt(d);
+    __syncwarp();
+    if (lane == 0) Ls[j * LD + j] = ljj;
+    for (int i = j + 1 + lane; i < D; i += 32) Ls[i * LD + j] /= ljj;
+    __syncwarp();
+    for (int i = j + 1 + lane; i < D; i += 32) {
+      const double lij = Ls[i * LD + j];
+      for (int k = j + 1; k <= i; ++k) Ls[i * LD + k] -= lij * Ls[k * LD + j];
+    }
+    __syncwarp();
+  }
+  const float nanv = __int_as_float(0x7fc00000);
+  float* rec = a.recs + (size_t)t * a.rec_f;
+  for (int e = lane; e < a.rec_f; e += 32) rec[e] = 0.f;
+  __syncwarp();
+  for (int j = 0; j < D; ++j) {   // column j of U = row j of L
+    const int off = gauss_col_off(j);
+    for (int i = lane; i <= j; i += 32) rec[off + i] = ok ? (float)Ls[j * LD + i] : nanv;
+  }
+  for (int j = lane; j < D; j += 32) rec[a.trip + j] = a.mu[(size_t)t * D + j];
+  if (lane == 0) {
+    const float log2pi = 1.8378770664093453f;   // Float32(log(2pi)), mv_gaussian.jl:24
+    a.cst[t] = __fmul_rn(__fadd_rn(__fmul_rn((float)(D * D), log2pi), a.logdet[t]), 0.5f);
+  }
+  if (a.tc_w != nullptr && t % 3 == 0) {
+    const int k = t / 3;
+    double fro = 0.0;
+    for (int i = lane; i < D; i += 32) {
+      double bi = 0.0;
+      for (int j = 0; j < D; ++j) {
+        const float u = (j >= i) ? (ok ? (float)Ls[j * LD + i] : nanv) : 0.f;   // U[i][j] = L[j][i]
+        a.tc_w[((size_t)k * D + i) * D + j] = u;
+        bi += (double)u * (double)a.mu[(size_t)t * D + j];
+        fro += (double)u * (double)u;
+      }
+      a.tc_b[(size_t)k * D + i] = (float)bi;
+      a.tc_mu[(size_t)k * D + i] = a.mu[(size_t)t * D + i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fro += __shfl_xor_sync(0xffffffffu, fro, o);
+    if (lane == 0) a.tc_fro[k] = (float)sqrt(fro);
+  }
+}
