@@ -225,6 +225,7 @@ def main():
     ap.add_argument("--cpu-workers", type=int, default=0)
     ap.add_argument("--cpu-step-s", type=float, default=1.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fit", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -400,6 +401,21 @@ def main():
                                 "sample": f"{r['n_sample']} of {case['n']} points (strided), 4 sweeps, scaled linearly; "
                                           f"restated reference (NumPy/OpenBLAS oracle), {r['workers']} worker processes "
                                           f"x 1 BLAS thread, host has {cores} cores; Julia is not installed"}
+    # ---- a complete fit() on the same data (host parameter sampling in Python included): NMI, final K ----
+    if rank == 0 and world == 1 and not args.no_fit:
+        from dpmmsubclusters_jl_b200.host import normalized_mutual_info
+        t0 = time.perf_counter()
+        if "mu" in case:
+            out = pkg.fit(case["x"], 10.0, iters=100, seed=args.seed + 1, burnout=20)
+        else:
+            out = pkg.fit(case["x"], pkg.multinomial_hyper(np.ones(case["D"], np.float32)), 10.0, iters=100,
+                          seed=args.seed + 1, burnout=20)
+        dt = time.perf_counter() - t0
+        line["fit"] = {"iters": 100, "seconds": dt, "iters_per_s": 100 / dt, "final_K": len(out[1]),
+                       "K_true_nonempty": int(len(np.unique(case["gt"]))),
+                       "nmi": normalized_mutual_info(case["gt"], out[0]),
+                       "note": "fit(x, alpha=10, iters=100, burnout=20) from K=1: X upload, 100 Gibbs iterations with "
+                               "split/merge moves and the Python host's parameter sampling, label download"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

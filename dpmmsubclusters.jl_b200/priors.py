@@ -77,9 +77,10 @@ class multinomial_dist:
 
 def log_multivariate_gamma(x, D):
     """utils.jl:66-72 (accumulates in Float32 like the reference)."""
+    vals = gammaln(x + (1 - np.arange(1, D + 1)) / 2)       # one vectorised call; accumulation order as the reference
     res = F32(D * (D - 1) / 4 * np.log(np.pi))
-    for d in range(1, D + 1):
-        res = F32(res + gammaln(x + (1 - d) / 2))
+    for v in vals:
+        res = F32(res + v)
     return float(res)
 
 
