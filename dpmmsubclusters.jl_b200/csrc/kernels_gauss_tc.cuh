@@ -224,6 +224,21 @@ __device__ __forceinline__ float gauss_tc_screen_q(const uint32_t (&v)[32]) {
 }
 
 __device__ __forceinline__ void group_barrier(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+// barrier of the 128 threads of a point-group that also ORs a predicate across them
+__device__ __forceinline__ bool group_any(int g, bool pred) {
+  int r;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "bar.red.or.pred p, %2, 128, q;\n\t"
+      "selp.s32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(r)
+      : "r"((int)pred), "r"(g + 1)
+      : "memory");
+  return r != 0;
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcArgs a) {
@@ -319,14 +334,6 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
       }
       for (; tile < a.ntiles; tile += tstep, ++li) {
         const int s = g * 2 + (li & 1);
-        // prefetch this group's next tile into its other stage (freed when tile li-1 was finished)
-        const int64_t nt = tile + tstep;
-        if (nt < a.ntiles) {
-          const int ns = g * 2 + ((li + 1) & 1);
-          tc::mbar_wait(&empty[ns], (((li + 1) >> 1) & 1) ^ 1);
-          tc::mbar_arrive_expect_tx(&full[ns], TC_STAGE_BYTES);
-          tc::tma_load_2d(stage0 + (size_t)ns * TC_STAGE_BYTES, &tmap_x, &full[ns], 0, (int)(nt * TC_TILE));
-        }
         tc::mbar_wait(&full[s], (li >> 1) & 1);
         tc::tc_fence_after();
         const uint64_t adesc = tc::smem_desc_k128(tc::smem_u32(stage0 + (size_t)s * TC_STAGE_BYTES));
@@ -344,6 +351,14 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
           tc::umma_tf32(tmem_d, tc::smem_desc_k_noswz(tc::smem_u32(aaug)),
                         tc::smem_desc_k_noswz(tc::smem_u32(baug) + c * 4096), idesc, 1u);   // Y -= U mu
           tc::umma_commit(&tfull[g * 2 + b]);
+        }
+        // prefetch this group's next tile into its other stage (freed when tile li-1 was finished)
+        const int64_t nt = tile + tstep;
+        if (nt < a.ntiles) {
+          const int ns = g * 2 + ((li + 1) & 1);
+          tc::mbar_wait(&empty[ns], (((li + 1) >> 1) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(&full[ns], TC_STAGE_BYTES);
+          tc::tma_load_2d(stage0 + (size_t)ns * TC_STAGE_BYTES, &tmap_x, &full[ns], 0, (int)(nt * TC_TILE));
         }
       }
     }
@@ -429,43 +444,47 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
       // draw, so its label is that cluster whatever the exact value is -- no refinement needed.
       const bool multi = __popc(mask) > 1;
       const uint32_t rmask = multi ? mask : 0u;
-      // ---- regroup the (point, cluster) candidates by cluster so that a warp refines one cluster ----
-      // (counting sort over <= 24 keys in shared memory: count, prefix, scatter)
-      if (gt < 32) cnt[gt] = 0;
-      group_barrier(g);
-      for (uint32_t m = rmask; m; m &= m - 1) atomicAdd(&cnt[__ffs(m) - 1], 1);
-      group_barrier(g);
-      if (gt == 0) {
-        int run = 0;
-        for (int k = 0; k < K; ++k) {
-          const int c = cnt[k];
-          cnt[k] = run;        // becomes the scatter cursor of cluster k
-          run += c;
+      // ---- refine only if some point of the group has several candidates (rare once clusters separate) ----
+      int npairs = 0;
+      if (group_any(g, multi)) {
+        // ---- regroup the (point, cluster) candidates by cluster so that a warp refines one cluster ----
+        // (counting sort over <= 24 keys in shared memory: count, prefix, scatter)
+        if (gt < 32) cnt[gt] = 0;
+        group_barrier(g);
+        for (uint32_t m = rmask; m; m &= m - 1) atomicAdd(&cnt[__ffs(m) - 1], 1);
+        group_barrier(g);
+        if (gt == 0) {
+          int run = 0;
+          for (int k = 0; k < K; ++k) {
+            const int c = cnt[k];
+            cnt[k] = run;        // becomes the scatter cursor of cluster k
+            run += c;
+          }
+          cnt[32] = run;
         }
-        cnt[32] = run;
-      }
-      group_barrier(g);
-      for (uint32_t m = rmask; m; m &= m - 1) {
-        const int k = __ffs(m) - 1;
-        pairs[atomicAdd(&cnt[k], 1)] = (uint16_t)((row << 5) | k);
-      }
-      group_barrier(g);
-      const int npairs = cnt[32];
-      for (int idx = gt; idx < npairs; idx += 128) {
-        const uint32_t pr = pairs[idx];
-        const int prow = pr >> 5, k = pr & 31;
-        float x[TC_D];
-        const float* xrow = stage + prow * TC_D;
+        group_barrier(g);
+        for (uint32_t m = rmask; m; m &= m - 1) {
+          const int k = __ffs(m) - 1;
+          pairs[atomicAdd(&cnt[k], 1)] = (uint16_t)((row << 5) | k);
+        }
+        group_barrier(g);
+        npairs = cnt[32];
+        for (int idx = gt; idx < npairs; idx += 128) {
+          const uint32_t pr = pairs[idx];
+          const int prow = pr >> 5, k = pr & 31;
+          float x[TC_D];
+          const float* xrow = stage + prow * TC_D;
 #pragma unroll
-        for (int c = 0; c < TC_D / 4; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(xrow + ((c ^ (prow & 7)) << 2));
-          x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+          for (int c = 0; c < TC_D / 4; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(xrow + ((c ^ (prow & 7)) << 2));
+            x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+          }
+          const float q = gauss_tc_exact_q(wsm + (size_t)k * TC_D * TC_D, musm + k * TC_D, x);
+          rsg[k * TC_TILE + prow] = gauss_finish(csm[k], q, lwsm[k]);
+          ++ncand_total;
         }
-        const float q = gauss_tc_exact_q(wsm + (size_t)k * TC_D * TC_D, musm + k * TC_D, x);
-        rsg[k * TC_TILE + prow] = gauss_finish(csm[k], q, lwsm[k]);
-        ++ncand_total;
+        group_barrier(g);
       }
-      group_barrier(g);
       // the stage can be refilled now
       tc::mbar_arrive(&empty[s]);
       // ---- draw ----
