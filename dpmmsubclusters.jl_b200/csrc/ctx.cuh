@@ -50,6 +50,7 @@ struct dpmm_ctx {
   int device = 0;
   int sm_count = 148;
   int smem_optin = 0;
+  int smem_per_sm = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   int64_t n = 0;
@@ -105,6 +106,7 @@ struct dpmm_ctx {
   int32_t* idx_list = nullptr;
   int stats_rec = 0;
   double* acc = nullptr;
+  float* centers = nullptr;   // [2K][D] per-run shift of the tensor-core statistics
   double* outbuf = nullptr;
   StatsItem* items = nullptr;
   int64_t items_cap = 0;

@@ -20,6 +20,7 @@
 #include "kernels_pack.cuh"
 #include "kernels_sort.cuh"
 #include "kernels_stats.cuh"
+#include "kernels_stats_tc.cuh"
 
 #include "ctx.cuh"
 static int keff(const dpmm_ctx* c) { return std::max(std::max(c->K, c->label_bound), 1); }
@@ -69,6 +70,7 @@ static int ensure_k(dpmm_ctx* ctx, int K) {
   CK(dev_realloc(&ctx->wanted, (size_t)cap));
   CK(dev_realloc(&ctx->idx_list, (size_t)cap));
   CK(dev_realloc(&ctx->acc, (size_t)2 * cap * ctx->stats_rec));
+  CK(dev_realloc(&ctx->centers, (size_t)2 * cap * ctx->D));
   CK(dev_realloc(&ctx->outbuf, (size_t)3 * cap * ctx->stats_rec));
   ctx->items_cap = ctx->n / ctx->chunk + 2 * (int64_t)cap + 2;
   CK(dev_realloc(&ctx->items, (size_t)ctx->items_cap));
@@ -185,6 +187,7 @@ extern "C" int dpmm_create(dpmm_ctx** out, const float* x, int64_t n_local, int3
   }
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  ctx->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
   CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CKC(cudaMalloc((void**)&ctx->x, (size_t)n_local * d * sizeof(float)));
   CKC(cudaMalloc((void**)&ctx->labels, (size_t)n_local * sizeof(int32_t)));
@@ -262,7 +265,7 @@ extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
   void* ptrs[] = {ctx->x, ctx->labels, ctx->sub, ctx->perm, ctx->perm2, ctx->u_label, ctx->u_sub, ctx->r_bits,
                   ctx->raw_params, ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->tc_w, ctx->tc_b, ctx->tc_mu, ctx->tc_fro, ctx->tc_stats, ctx->mtc_w, ctx->hist, ctx->seg_off,
                   ctx->scat_cursor, ctx->lr_cursor, ctx->lut_l, ctx->lut_r, ctx->rule, ctx->wanted,
-                  ctx->idx_list, ctx->acc, ctx->outbuf, ctx->items, ctx->item_ctr};
+                  ctx->idx_list, ctx->acc, ctx->centers, ctx->outbuf, ctx->items, ctx->item_ctr};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (ctx->hstage) cudaFreeHost(ctx->hstage);
@@ -871,7 +874,10 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
       CK(cudaMemcpyAsync(ctx->wanted, h_w, K, cudaMemcpyHostToDevice, ctx->stream));
     }
   }
-  {
+  // K5 on tcgen05: all clusters of a D = 32 NIW model (no work list: CTAs own ranges of the tile sequence)
+  const bool stats_tc = ctx->prior == DPMM_PRIOR_NIW && D == STC_D && all && ctx->tc_ok && env_int("DPMM_STATS_TC", 1) != 0 &&
+                        StatsTcSmem(K).total <= (size_t)ctx->smem_optin;
+  if (!stats_tc) {
     KernelTimer kt(ctx, TK_STATS_AUX);
     stats_worklist_kernel<<<1, 256, (size_t)2 * K * 4, ctx->stream>>>(ctx->seg_off, ctx->lr_cursor,
                                                                       all ? nullptr : ctx->wanted, K, ctx->chunk,
@@ -882,7 +888,25 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
   StatsArgs sa{};
   sa.x = ctx->x; sa.D = D; sa.perm2 = ctx->perm2; sa.items = ctx->items; sa.n_items = ctx->item_ctr;
   sa.next_item = ctx->item_ctr + 1; sa.acc = ctx->acc; sa.rec = rec;
-  if (ctx->prior == DPMM_PRIOR_NIW) {
+  if (stats_tc) {
+    StatsTcArgs ta{};
+    ta.x = ctx->x; ta.perm2 = ctx->perm2; ta.seg_off = ctx->seg_off; ta.lr_cursor = ctx->lr_cursor; ta.K = K;
+    ta.acc = ctx->acc; ta.rec = rec; ta.centers = ctx->centers;
+    {
+      KernelTimer kt(ctx, TK_STATS_AUX);
+      stats_centers_kernel<<<2 * K, 256, 0, ctx->stream>>>(ctx->x, ctx->perm2, ctx->seg_off, ctx->lr_cursor, ctx->centers);
+      CK(cudaGetLastError());
+    }
+    const size_t smem = StatsTcSmem(K).total;
+    CK(cudaFuncSetAttribute(niw_stats_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(niw_stats_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // two CTAs per SM when their shared memory fits (every CTA owns a contiguous slice of the tile
+    // sequence, so the grid size is free)
+    const int occ = 2 * (smem + 1024) <= (size_t)ctx->smem_per_sm ? 2 : 1;
+    KernelTimer kt(ctx, TK_STATS);
+    niw_stats_tc_kernel<<<ctx->sm_count * occ, STC_THREADS, smem, ctx->stream>>>(ta);
+    CK(cudaGetLastError());
+  } else if (ctx->prior == DPMM_PRIOR_NIW) {
     rc = niw_launch_stats(ctx, sa);
     if (rc) return rc;
   } else {
@@ -898,7 +922,8 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
     const int T = 256;
     dim3 grid((unsigned)std::min((rec + T - 1) / T, 64), (unsigned)m);
     stats_finalize_kernel<<<grid, T, 0, ctx->stream>>>(ctx->acc, ctx->seg_off, ctx->lr_cursor, ctx->idx_list, m, D, rec,
-                                                       ctx->prior == DPMM_PRIOR_NIW ? 1 : 0, ctx->outbuf);
+                                                       ctx->prior == DPMM_PRIOR_NIW ? 1 : 0, ctx->outbuf,
+                                                       stats_tc ? ctx->centers : nullptr);
     CK(cudaGetLastError());
   }
   if (ctx->comm != nullptr) {

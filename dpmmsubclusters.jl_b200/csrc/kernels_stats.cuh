@@ -363,24 +363,31 @@ __global__ void __launch_bounds__(256) mnm_stats_kernel(const StatsArgs a) {
 }
 
 // K8: finalise + pack.  out[m][3][rec] for the m requested clusters: cluster = left + right, S
-// mirrored from its upper triangle, counts from the partition cursors.
+// mirrored from its upper triangle, counts from the partition cursors.  When `xc` is given the
+// accumulators hold sums of y = x - c about a centre c of every run (centers [2K][D], see
+// kernels_stats_tc.cuh) and are shifted back here in Float64: sum x = s + N c,  S = sum y y' + c s' + s c' + N c c'.
 __global__ void stats_finalize_kernel(const double* __restrict__ acc, const int32_t* __restrict__ seg_off,
                                       const int32_t* __restrict__ lr_cursor, const int32_t* __restrict__ idx_list,
-                                      int m, int D, int rec, int niw, double* out) {
+                                      int m, int D, int rec, int niw, double* out, const float* __restrict__ centers) {
   const int a = blockIdx.y;
   if (a >= m) return;
   const int k = idx_list[a];
   const double* L = acc + (size_t)(2 * k) * rec;
   const double* R = acc + (size_t)(2 * k + 1) * rec;
+  const int beg = seg_off[k], mid = lr_cursor[2 * k], end = seg_off[k + 1];
+  const double nl = (double)(mid - beg), nr = (double)(end - mid);
+  const float* cl = centers != nullptr ? centers + (size_t)(2 * k) * D : nullptr;
+  const float* cr = centers != nullptr ? centers + (size_t)(2 * k + 1) * D : nullptr;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < rec; e += gridDim.x * blockDim.x) {
     double l, r;
     if (e == 0) {
-      const int mid = lr_cursor[2 * k];
-      l = (double)(mid - seg_off[k]);
-      r = (double)(seg_off[k + 1] - mid);
+      l = nl;
+      r = nr;
     } else if (e <= D || !niw) {
       l = L[e];
       r = R[e];
+      if (cl != nullptr) l += nl * (double)cl[e - 1];
+      if (cr != nullptr) r += nr * (double)cr[e - 1];
     } else {
       const int q = e - 1 - D;
       int i = q / D, j = q - i * D;
@@ -391,6 +398,14 @@ __global__ void stats_finalize_kernel(const double* __restrict__ acc, const int3
       }
       l = L[1 + D + (size_t)i * D + j];
       r = R[1 + D + (size_t)i * D + j];
+      if (cl != nullptr) {
+        const double ci = cl[i], cj = cl[j];
+        l += ci * L[1 + j] + L[1 + i] * cj + nl * ci * cj;
+      }
+      if (cr != nullptr) {
+        const double ci = cr[i], cj = cr[j];
+        r += ci * R[1 + j] + R[1 + i] * cj + nr * ci * cj;
+      }
     }
     double* o = out + (size_t)a * 3 * rec;
     o[e] = l + r;
