@@ -87,6 +87,11 @@ struct dpmm_ctx {
   float* tc_mu = nullptr;
   float* tc_fro = nullptr;
   int32_t* tc_stats = nullptr;
+  // fused sub-label + statistics tensor-core path (NIW, D == 32): U rows / bias / centre per cluster, left counts
+  float* ss_w = nullptr;
+  float* ss_b = nullptr;
+  float* ss_c = nullptr;
+  int32_t* lcount = nullptr;
   CUtensorMap tmap_x;
   float* mtc_w = nullptr;   // multinomial tensor-core path: TF32-exact 3-way split of the log-probabilities
   bool mtc_ok = false;      // multinomial: tensor map built and the counts are TF32-exact
@@ -118,6 +123,7 @@ struct dpmm_ctx {
   size_t hstage_bytes = 0;
 
   bool hist_valid = false, sorted = false, partitioned = false;
+  bool stats_cached = false;   // acc / lcount / centers hold the l/r statistics of every cluster for the current labels
   bool cursors_fresh = false;  // lr_cursor still holds the segment bounds (not yet consumed by a partition)
   int64_t launches = 0;
   bool timing = false;

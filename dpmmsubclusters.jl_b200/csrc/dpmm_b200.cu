@@ -21,6 +21,7 @@
 #include "kernels_sort.cuh"
 #include "kernels_stats.cuh"
 #include "kernels_stats_tc.cuh"
+#include "kernels_substats_tc.cuh"
 
 #include "ctx.cuh"
 static int keff(const dpmm_ctx* c) { return std::max(std::max(c->K, c->label_bound), 1); }
@@ -59,6 +60,10 @@ static int ensure_k(dpmm_ctx* ctx, int K) {
     CK(dev_realloc(&ctx->tc_mu, (size_t)capc * TC_D));
     CK(dev_realloc(&ctx->tc_fro, (size_t)capc));
     ctx->tc_params = false;
+    CK(dev_realloc(&ctx->ss_w, (size_t)cap * 2 * SS_D * SS_D));
+    CK(dev_realloc(&ctx->ss_b, (size_t)cap * 2 * SS_D));
+    CK(dev_realloc(&ctx->ss_c, (size_t)cap * SS_D));
+    CK(dev_realloc(&ctx->lcount, (size_t)cap));
   }
   CK(dev_realloc(&ctx->hist, (size_t)cap));
   CK(dev_realloc(&ctx->seg_off, (size_t)cap + 1));
@@ -75,7 +80,7 @@ static int ensure_k(dpmm_ctx* ctx, int K) {
   ctx->items_cap = ctx->n / ctx->chunk + 2 * (int64_t)cap + 2;
   CK(dev_realloc(&ctx->items, (size_t)ctx->items_cap));
   ctx->Kcap = cap;
-  ctx->hist_valid = ctx->sorted = ctx->partitioned = false;
+  ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
   return 0;
 }
 
@@ -263,7 +268,7 @@ extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
   }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   void* ptrs[] = {ctx->x, ctx->labels, ctx->sub, ctx->perm, ctx->perm2, ctx->u_label, ctx->u_sub, ctx->r_bits,
-                  ctx->raw_params, ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->tc_w, ctx->tc_b, ctx->tc_mu, ctx->tc_fro, ctx->tc_stats, ctx->mtc_w, ctx->hist, ctx->seg_off,
+                  ctx->raw_params, ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->tc_w, ctx->tc_b, ctx->tc_mu, ctx->tc_fro, ctx->tc_stats, ctx->ss_w, ctx->ss_b, ctx->ss_c, ctx->lcount, ctx->mtc_w, ctx->hist, ctx->seg_off,
                   ctx->scat_cursor, ctx->lr_cursor, ctx->lut_l, ctx->lut_r, ctx->rule, ctx->wanted,
                   ctx->idx_list, ctx->acc, ctx->centers, ctx->outbuf, ctx->items, ctx->item_ctr};
   for (void* p : ptrs)
@@ -348,7 +353,7 @@ extern "C" int dpmm_init_labels(dpmm_ctx* ctx, int32_t init_clusters, int32_t ou
                                                     ctx->call, ctx->goff);
     CK(cudaGetLastError());
   }
-  ctx->hist_valid = ctx->sorted = ctx->partitioned = false;
+  ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
   return dpmm_randomize_sublabels(ctx, nullptr, 0);
 }
 
@@ -369,7 +374,7 @@ extern "C" int dpmm_randomize_sublabels(dpmm_ctx* ctx, const int64_t* indices, i
     if (n_indices == 0) return 0;
     for (int i = 0; i < n_indices; ++i) rule[indices[i] - 1] = 3;
   }
-  ctx->partitioned = false;
+  ctx->partitioned = ctx->stats_cached = false;
   return run_relabel(ctx, ll, lr, rule, true);
 }
 
@@ -403,7 +408,7 @@ extern "C" int dpmm_apply_split(dpmm_ctx* ctx, const int64_t* indices, const int
     }
   }
   ctx->label_bound = std::max(ctx->label_bound, K);
-  ctx->hist_valid = ctx->sorted = ctx->partitioned = false;
+  ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
   return run_relabel(ctx, ll, lr, rule, true);
 }
 
@@ -433,7 +438,7 @@ extern "C" int dpmm_apply_merge(dpmm_ctx* ctx, const int64_t* indices, const int
         lab[k] = idx;
       }
   }
-  ctx->hist_valid = ctx->sorted = ctx->partitioned = false;
+  ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
   return run_relabel(ctx, lab, lab, rule, false);
 }
 
@@ -458,7 +463,7 @@ extern "C" int dpmm_remove_empty(dpmm_ctx* ctx, const int64_t* pts_count, int32_
   ctx->label_bound = std::max(1, k - removed);
   ctx->K = std::min(ctx->K, ctx->label_bound);  // parameters of the dropped clusters are stale anyway
   ctx->params_set = false;
-  ctx->hist_valid = ctx->sorted = ctx->partitioned = false;
+  ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
   return run_relabel(ctx, lab, lab, rule, false);
 }
 
@@ -508,7 +513,7 @@ extern "C" int dpmm_set_labels(dpmm_ctx* ctx, const int64_t* labels) {
   h = (int32_t*)ctx->hstage;
   CK(cudaMemcpyAsync(ctx->labels, h, (size_t)ctx->n * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->hist_valid = ctx->sorted = ctx->partitioned = false;
+  ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
   return 0;
 }
 
@@ -525,7 +530,7 @@ extern "C" int dpmm_set_sublabels(dpmm_ctx* ctx, const int64_t* sublabels) {
   }
   CK(cudaMemcpyAsync(ctx->sub, h, (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->partitioned = false;
+  ctx->partitioned = ctx->stats_cached = false;
   return 0;
 }
 
@@ -603,6 +608,7 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
     pa.mu = ctx->raw_params; pa.inv_sigma = ctx->raw_params + nrec * D; pa.logdet = ctx->raw_params + nrec * D + nrec * D * D;
     pa.recs = ctx->recs; pa.cst = ctx->cst;
     pa.tc_w = tcp ? ctx->tc_w : nullptr; pa.tc_b = ctx->tc_b; pa.tc_mu = ctx->tc_mu; pa.tc_fro = ctx->tc_fro;
+    pa.ss_w = ctx->tc_ok ? ctx->ss_w : nullptr; pa.ss_b = ctx->ss_b; pa.ss_c = ctx->ss_c;
     KernelTimer kt(ctx, TK_RELABEL);
     niw_pack_kernel<<<(unsigned)nrec, 32, (size_t)D * (D + 1) * sizeof(double), ctx->stream>>>(pa);
     CK(cudaGetLastError());
@@ -746,7 +752,7 @@ static int run_sample_labels(dpmm_ctx* ctx, int final_iter, float* dump) {
   }
   ctx->hist_valid = true;
   ctx->sorted = false;
-  ctx->partitioned = false;
+  ctx->partitioned = ctx->stats_cached = false;
   ctx->label_bound = K;
   return 0;
 }
@@ -776,7 +782,7 @@ static int ensure_sorted(dpmm_ctx* ctx) {
     CK(cudaGetLastError());
   }
   ctx->sorted = true;
-  ctx->partitioned = false;
+  ctx->partitioned = ctx->stats_cached = false;
   ctx->cursors_fresh = true;
   return 0;
 }
@@ -797,6 +803,29 @@ static int run_sublabels(dpmm_ctx* ctx, bool sample, float* dump) {
   a.labels = ctx->labels; a.sub = ctx->sub; a.perm = ctx->perm; a.perm2 = ctx->perm2; a.cursor = ctx->lr_cursor;
   a.seg_off = ctx->seg_off;
   a.u_inj = ctx->u_sub; a.seed = ctx->seed; a.call = ctx->call; a.goff = ctx->goff; a.dump = dump; a.D = ctx->D;
+  // K4+K5 fused on tcgen05 (NIW, D = 32): the sub-label draw also accumulates the left / right statistics
+  // of every cluster, which the next dpmm_suff_stats calls serve from the accumulators.
+  if (sample && ctx->prior == DPMM_PRIOR_NIW && ctx->D == SS_D && ctx->tc_ok && env_int("DPMM_SUBSTATS_TC", 1) != 0 &&
+      SubStatsSmem(ctx->K).total <= (size_t)ctx->smem_optin && keff(ctx) == ctx->K) {
+    const int K = ctx->K, recs = ctx->stats_rec;
+    CK(cudaMemsetAsync(ctx->acc, 0, (size_t)2 * K * recs * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->lcount, 0, (size_t)K * 4, ctx->stream));
+    SubStatsArgs f{};
+    f.x = ctx->x; f.n = ctx->n; f.K = K; f.perm = ctx->perm; f.seg_off = ctx->seg_off; f.w = ctx->ss_w; f.bias = ctx->ss_b;
+    f.cen = ctx->ss_c; f.cst = ctx->cst; f.loglr = ctx->loglr; f.sub = ctx->sub; f.acc = ctx->acc; f.rec = recs;
+    f.lcount = ctx->lcount; f.centers = ctx->centers; f.u_inj = ctx->u_sub; f.seed = ctx->seed; f.call = ctx->call;
+    f.goff = ctx->goff; f.dump = dump;
+    const size_t smem = SubStatsSmem(K).total;
+    CK(cudaFuncSetAttribute(niw_substats_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+      KernelTimer kt(ctx, TK_SUBLABEL);
+      niw_substats_tc_kernel<<<ctx->sm_count, SS_THREADS, smem, ctx->stream>>>(f);
+      CK(cudaGetLastError());
+    }
+    ctx->partitioned = false;
+    ctx->stats_cached = true;
+    return 0;
+  }
   if (ctx->prior == DPMM_PRIOR_NIW) {
     rc = niw_launch_sublabel(ctx, a, sample);
     if (rc) return rc;
@@ -855,7 +884,8 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
   const int m = (int)idx.size();
   if (m == 0) return 0;
   NEED(m <= ctx->Kcap, DPMM_EINVAL, "more indices than clusters");
-  if (!ctx->partitioned) {
+  const bool cached = ctx->stats_cached;   // accumulators of every cluster left by the fused sub-label kernel
+  if (!cached && !ctx->partitioned) {
     rc = run_sublabels(ctx, false, nullptr);
     if (rc) return rc;
   }
@@ -875,20 +905,24 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
     }
   }
   // K5 on tcgen05: all clusters of a D = 32 NIW model (no work list: CTAs own ranges of the tile sequence)
-  const bool stats_tc = ctx->prior == DPMM_PRIOR_NIW && D == STC_D && all && ctx->tc_ok && env_int("DPMM_STATS_TC", 1) != 0 &&
-                        StatsTcSmem(K).total <= (size_t)ctx->smem_optin;
-  if (!stats_tc) {
+  const bool stats_tc = !cached && ctx->prior == DPMM_PRIOR_NIW && D == STC_D && all && ctx->tc_ok &&
+                        env_int("DPMM_STATS_TC", 1) != 0 && StatsTcSmem(K).total <= (size_t)ctx->smem_optin;
+  if (cached) {
+    // nothing to accumulate
+  } else if (!stats_tc) {
     KernelTimer kt(ctx, TK_STATS_AUX);
     stats_worklist_kernel<<<1, 256, (size_t)2 * K * 4, ctx->stream>>>(ctx->seg_off, ctx->lr_cursor,
                                                                       all ? nullptr : ctx->wanted, K, ctx->chunk,
                                                                       ctx->items, ctx->item_ctr, ctx->item_ctr + 1);
     CK(cudaGetLastError());
   }
-  CK(cudaMemsetAsync(ctx->acc, 0, (size_t)2 * K * rec * 8, ctx->stream));
+  if (!cached) CK(cudaMemsetAsync(ctx->acc, 0, (size_t)2 * K * rec * 8, ctx->stream));
   StatsArgs sa{};
   sa.x = ctx->x; sa.D = D; sa.perm2 = ctx->perm2; sa.items = ctx->items; sa.n_items = ctx->item_ctr;
   sa.next_item = ctx->item_ctr + 1; sa.acc = ctx->acc; sa.rec = rec;
-  if (stats_tc) {
+  if (cached) {
+    // served from the accumulators
+  } else if (stats_tc) {
     StatsTcArgs ta{};
     ta.x = ctx->x; ta.perm2 = ctx->perm2; ta.seg_off = ctx->seg_off; ta.lr_cursor = ctx->lr_cursor; ta.K = K;
     ta.acc = ctx->acc; ta.rec = rec; ta.centers = ctx->centers;
@@ -923,7 +957,8 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
     dim3 grid((unsigned)std::min((rec + T - 1) / T, 64), (unsigned)m);
     stats_finalize_kernel<<<grid, T, 0, ctx->stream>>>(ctx->acc, ctx->seg_off, ctx->lr_cursor, ctx->idx_list, m, D, rec,
                                                        ctx->prior == DPMM_PRIOR_NIW ? 1 : 0, ctx->outbuf,
-                                                       stats_tc ? ctx->centers : nullptr);
+                                                       (stats_tc || cached) ? ctx->centers : nullptr,
+                                                       cached ? ctx->lcount : nullptr);
     CK(cudaGetLastError());
   }
   if (ctx->comm != nullptr) {
@@ -973,7 +1008,7 @@ extern "C" int dpmm_debug_loglik(dpmm_ctx* ctx, int32_t which, float* out) {
     ctx->labels = keep;
     ctx->call = call0;
     ctx->label_bound = lb0;
-    ctx->hist_valid = ctx->sorted = ctx->partitioned = false;  // the histogram describes the scratch labels
+    ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;  // the histogram describes the scratch labels
     cudaFree(scratch);
   } else {
     // sub-label matrix under the CURRENT labels; sub-labels are restored afterwards
@@ -992,7 +1027,7 @@ extern "C" int dpmm_debug_loglik(dpmm_ctx* ctx, int32_t which, float* out) {
     cudaMemcpyAsync(ctx->sub, keep, (size_t)ctx->n, cudaMemcpyDeviceToDevice, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     ctx->call = call0;
-    ctx->partitioned = false;
+    ctx->partitioned = ctx->stats_cached = false;
     cudaFree(keep);
   }
   if (rc == 0) {

@@ -21,7 +21,22 @@ struct NiwPackArgs {
   float* tc_b;             // [K][D]
   float* tc_mu;            // [K][D]
   float* tc_fro;           // [K]
+  // fused sub-label + statistics tensor-core path (kernels_substats_tc.cuh), or nullptr
+  float* ss_w;             // [K][2][D][D] rows of U of the left / right distributions
+  float* ss_b;             // [K][2][D]    U_s (mu_s - c_k)
+  float* ss_c;             // [K][D]       c_k = cluster mean rounded to 12 significant bits
 };
+
+// The centre every point of cluster k is shifted by before it meets the tensor core: the cluster mean
+// rounded to 12 significant bits, so that x - c is EXACT in Float32 for every point within a few
+// widths of the cluster (the operands share their exponent range and c has 12 trailing zero bits).
+__device__ __forceinline__ float niw_pack_center(float m) {
+  if (!(fabsf(m) < CUDART_INF_F)) return 0.f;
+  uint32_t u = __float_as_uint(m);
+  u += 0x7FFu + ((u >> 12) & 1u);
+  u &= 0xFFFFF000u;
+  return __uint_as_float(u);
+}
 
 __global__ void __launch_bounds__(32) niw_pack_kernel(const NiwPackArgs a) {
   extern __shared__ double Ls[];   // [D][D+1]
@@ -78,5 +93,23 @@ __global__ void __launch_bounds__(32) niw_pack_kernel(const NiwPackArgs a) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) fro += __shfl_xor_sync(0xffffffffu, fro, o);
     if (lane == 0) a.tc_fro[k] = (float)sqrt(fro);
+  }
+  if (a.ss_w != nullptr) {
+    const int k = t / 3, side = t % 3 - 1;
+    const float* mu0 = a.mu + (size_t)(3 * k) * D;
+    if (side < 0) {
+      for (int j = lane; j < D; j += 32) a.ss_c[(size_t)k * D + j] = niw_pack_center(mu0[j]);
+    } else {
+      float* W = a.ss_w + ((size_t)k * 2 + side) * D * D;
+      for (int i = lane; i < D; i += 32) {
+        double bi = 0.0;
+        for (int j = 0; j < D; ++j) {
+          const float u = (j >= i) ? (ok ? (float)Ls[j * LD + i] : nanv) : 0.f;   // U[i][j] = L[j][i]
+          W[(size_t)i * D + j] = u;
+          bi += (double)u * ((double)a.mu[(size_t)t * D + j] - (double)niw_pack_center(mu0[j]));
+        }
+        a.ss_b[((size_t)k * 2 + side) * D + i] = (float)bi;
+      }
+    }
   }
 }

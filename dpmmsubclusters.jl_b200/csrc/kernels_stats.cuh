@@ -368,13 +368,16 @@ __global__ void __launch_bounds__(256) mnm_stats_kernel(const StatsArgs a) {
 // kernels_stats_tc.cuh) and are shifted back here in Float64: sum x = s + N c,  S = sum y y' + c s' + s c' + N c c'.
 __global__ void stats_finalize_kernel(const double* __restrict__ acc, const int32_t* __restrict__ seg_off,
                                       const int32_t* __restrict__ lr_cursor, const int32_t* __restrict__ idx_list,
-                                      int m, int D, int rec, int niw, double* out, const float* __restrict__ centers) {
+                                      int m, int D, int rec, int niw, double* out, const float* __restrict__ centers,
+                                      const int32_t* __restrict__ lcount) {
   const int a = blockIdx.y;
   if (a >= m) return;
   const int k = idx_list[a];
   const double* L = acc + (size_t)(2 * k) * rec;
   const double* R = acc + (size_t)(2 * k + 1) * rec;
-  const int beg = seg_off[k], mid = lr_cursor[2 * k], end = seg_off[k + 1];
+  // left count: from the partition cursors, or as counted by the fused sub-label + statistics kernel
+  const int beg = seg_off[k], end = seg_off[k + 1];
+  const int mid = lcount != nullptr ? beg + lcount[k] : lr_cursor[2 * k];
   const double nl = (double)(mid - beg), nr = (double)(end - mid);
   const float* cl = centers != nullptr ? centers + (size_t)(2 * k) * D : nullptr;
   const float* cr = centers != nullptr ? centers + (size_t)(2 * k + 1) * D : nullptr;

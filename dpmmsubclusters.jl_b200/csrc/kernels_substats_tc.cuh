@@ -1,0 +1,497 @@
+// Stages 2b + 3 fused on the tensor cores (NIW, D = 32): ONE pass over the label-sorted points draws every
+// sub-label and accumulates the left / right sufficient statistics of every cluster.
+//
+//   sample_sub_clusters_worker! / create_subclusters_labels!   src/local_clusters_actions.jl:70-95
+//   log_likelihood!(mv_gaussian)                               src/distributions/mv_gaussian.jl:21-25
+//   sample_log_cat_array! (C = 2)                              src/utils.jl:19-31
+//   create_suff_stats_dict_worker                              src/local_clusters_actions.jl:149-169
+//   create_sufficient_statistics (NIW)                         src/priors/niw.jl:42-51
+//
+// A tile = 128 consecutive positions of ONE cluster k in the label-sorted permutation `perm`.  Its rows
+// are gathered with cp.async, shifted by the cluster's centre c_k (x - c_k is exact in Float32, see
+// niw_pack_center) and split z = h + l with h = tf32(z) into two [point][feature] panels of 128-byte rows,
+// written twice: with the 32-byte-atom 128B swizzle (the only MN-major layout tcgen05 takes for 32-bit
+// data) for GEMM2 and with the standard 128B swizzle for GEMM1 (tcgen05 rejects the 32-byte-atom swizzle
+// for a K-major operand: "misaligned address").  The K-major copies live in the slot that later receives
+// the masked panels, so they cost no shared memory.
+//
+//   GEMM1 (contraction over FEATURES; K-major A operand, M = 128 points, N = 64):
+//       Y = h Wh' + l Wh' + h Wl' - b,   W = [U_left; U_right] = Wh + Wl,   b = U_s (mu_s - c_k)
+//     i.e. a 3-term error-compensated TF32 product (only l Wl', <= 2^-22 relative, is dropped) whose
+//     accumulator row p holds U_l (x_p - mu_l) | U_r (x_p - mu_r).  The epilogue warps read it with
+//     tcgen05.ld, form q = |y|^2, r = -c - q/2 + log w (the reference's Float32 final operations) and
+//     draw the sub-label with the reference's inverse-CDF rule.
+//   GEMM2 (contraction over POINTS; panels read as MN-major operands, M = 64, N = 64):
+//       D = [h | l]' [h_left | h_right]
+//     where h_left / h_right are copies of h with the rows of the other side zeroed (written by the
+//     epilogue warps once the sub-labels are known).  Rows 0-31 of D hold sum h h', rows 32-63 sum l h'
+//     for the left (columns 0-31) and right (columns 32-63) side;  S = hh' + lh' + (lh')' as in
+//     kernels_stats_tc.cuh, flushed to the Float64 accumulators every STC_FLUSH tiles.
+//   sum y and the left count come from the masking pass.  Everything is shifted back by c_k in
+//   Float64 by stats_finalize_kernel.
+//
+// Warp roles (448 threads, one CTA per SM; every CTA owns a contiguous range of the tile sequence):
+//   warps 0-3  gather + shift + split          warps 5-8   GEMM1 epilogue: draw, mask, sum y
+//   warp  4    tcgen05.mma issuer              warps 9-12  GEMM2 accumulator drain
+//   warp  13   stages the factors of the next cluster (double-buffered)
+#pragma once
+#include "kernels_stats_tc.cuh"
+
+#define SS_D 32
+#define SS_TILE 128
+#define SS_STAGES 3                      // h | l ring
+#define SS_MSLOTS 2                      // h_left | h_right ring
+#define SS_THREADS 448
+#define SS_PANEL 16384                   // one [128][32] Float32 panel
+#define SS_WSLOT (8192 + 8192 + 2048)    // Wh | Wl | bias k-step operand
+#define SS_TMEM_COLS 256                 // GEMM1: 2 x 64 columns, GEMM2: 2 x 64 columns
+#define SS_TLD 65
+
+struct SubStatsArgs {
+  const float* x;
+  int64_t n;
+  int K;
+  const int32_t* perm;     // [n] point indices sorted by label
+  const int32_t* seg_off;  // [K+1]
+  const float* w;          // [K][2][32][32] rows of U_left, U_right
+  const float* bias;       // [K][2][32]     U_s (mu_s - c_k)
+  const float* cen;        // [K][32]        c_k
+  const float* cst;        // [3K]
+  const float* loglr;      // [2K]
+  uint8_t* sub;            // [n] out
+  double* acc;             // [2K][rec] (zeroed by the caller)
+  int rec;
+  int32_t* lcount;         // [K] out: number of left points (zeroed by the caller)
+  float* centers;          // [2K][32] out: the shift of every (cluster, side) accumulator
+  const double* u_inj;
+  uint64_t seed;
+  uint32_t call;
+  int64_t goff;
+  float* dump;             // optional [2][n]
+};
+
+struct SubStatsSmem {
+  size_t stages, mslots, wslots, aaug, tbuf, tri, idxs, side, bnd, pre, bars, slot, total;
+  __host__ __device__ explicit SubStatsSmem(int K) {
+    size_t o = 0;
+    stages = o; o += (size_t)SS_STAGES * 2 * SS_PANEL;
+    mslots = o; o += (size_t)SS_MSLOTS * 2 * SS_PANEL;
+    wslots = o; o += 2 * (size_t)SS_WSLOT;
+    aaug = o;   o += 4096;
+    tbuf = o;   o += 64 * SS_TLD * 4;
+    tri = o;    o += 528 * 2;
+    o = (o + 15) & ~(size_t)15;
+    idxs = o;   o += SS_STAGES * SS_TILE * 4;
+    side = o;   o += 2 * SS_TILE;
+    bnd = o;    o += (size_t)(K + 1) * 4;
+    pre = o;    o += (size_t)(K + 1) * 4;
+    o = (o + 15) & ~(size_t)15;
+    bars = o;   o += 24 * 8;
+    slot = o;   o += 16;
+    total = o;
+  }
+};
+
+__global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const SubStatsArgs a) {
+  extern __shared__ __align__(1024) uint8_t ss_smem[];
+  const SubStatsSmem L(a.K);
+  uint8_t* stage0 = ss_smem + L.stages;
+  uint8_t* mslot0 = ss_smem + L.mslots;
+  uint8_t* wslot0 = ss_smem + L.wslots;
+  float* aaug = reinterpret_cast<float*>(ss_smem + L.aaug);
+  float* T = reinterpret_cast<float*>(ss_smem + L.tbuf);
+  uint16_t* tri = reinterpret_cast<uint16_t*>(ss_smem + L.tri);
+  int32_t* idxs = reinterpret_cast<int32_t*>(ss_smem + L.idxs);
+  uint8_t* side_s = ss_smem + L.side;
+  int32_t* B = reinterpret_cast<int32_t*>(ss_smem + L.bnd);
+  int32_t* P = reinterpret_cast<int32_t*>(ss_smem + L.pre);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ss_smem + L.bars);
+  uint64_t* ready = bars;            // [3] h | l of the stage split and visible
+  uint64_t* empty = bars + 3;        // [3] GEMM2 of the stage retired
+  uint64_t* d1full = bars + 6;       // [2] GEMM1 accumulator complete
+  uint64_t* d1empty = bars + 8;      // [2] ... read by the epilogue
+  uint64_t* masked = bars + 10;      // [2] h_left | h_right written
+  uint64_t* mempty = bars + 12;      // [2] GEMM2 that read the slot retired
+  uint64_t* d2full = bars + 14;      // [2] flush group complete
+  uint64_t* d2empty = bars + 16;     // [2] ... drained
+  uint64_t* wfull = bars + 18;       // [2] factors of a cluster staged
+  uint64_t* wempty = bars + 20;      // [2] last GEMM1 of the cluster retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ss_smem + L.slot);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nkeys = a.K;
+
+  // ---- cluster boundaries, triangle index table, constant operands ----
+  for (int j = tid; j <= nkeys; j += SS_THREADS) B[j] = __ldg(a.seg_off + j);
+  for (int e = tid; e < 1024; e += SS_THREADS) {
+    const int i = e >> 5, j = e & 31;
+    if (j >= i) tri[i * 32 - (i * (i - 1)) / 2 + (j - i)] = (uint16_t)((i << 8) | j);
+  }
+  for (int e = tid; e < 1024; e += SS_THREADS) aaug[e] = 0.f;
+  for (int s = 0; s < 2; ++s) {
+    float* baug = reinterpret_cast<float*>(wslot0 + (size_t)s * SS_WSLOT + 16384);
+    for (int e = tid; e < 512; e += SS_THREADS) baug[e] = 0.f;
+  }
+  if (blockIdx.x == 0)
+    for (int e = tid; e < 2 * nkeys * SS_D; e += SS_THREADS)
+      a.centers[e] = __ldg(a.cen + (size_t)(e >> 6) * SS_D + (e & 31));
+  if (tid == 0) {
+    for (int s = 0; s < SS_STAGES; ++s) {
+      tc::mbar_init(&ready[s], 128);
+      tc::mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&d1full[b], 1);
+      tc::mbar_init(&d1empty[b], 128);
+      tc::mbar_init(&masked[b], 128);
+      tc::mbar_init(&mempty[b], 1);
+      tc::mbar_init(&d2full[b], 1);
+      tc::mbar_init(&d2empty[b], 128);
+      tc::mbar_init(&wfull[b], 32);
+      tc::mbar_init(&wempty[b], 1);
+    }
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  for (int r = tid; r < SS_TILE; r += SS_THREADS) {   // bias k-step A operand: (1, 1, 0, ...) per row
+    float* p = aaug + (r >> 3) * 64 + (r & 7) * 4;
+    p[0] = 1.f;
+    p[1] = 1.f;
+  }
+  if (warp == 0) {   // exclusive prefix of tiles per cluster
+    int carry = 0;
+    if (lane == 0) P[0] = 0;
+    for (int base = 0; base < nkeys; base += 32) {
+      const int j = base + lane;
+      int v = j < nkeys ? (B[j + 1] - B[j] + SS_TILE - 1) / SS_TILE : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+      }
+      if (j < nkeys) P[j + 1] = carry + v;
+      carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+  if (warp == 4) tc::tmem_alloc(tmem_slot, SS_TMEM_COLS);
+  tc::fence_proxy_async();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ntot = P[nkeys];
+  const int t0 = (int)(((int64_t)ntot * blockIdx.x) / gridDim.x);
+  const int t1 = (int)(((int64_t)ntot * (blockIdx.x + 1)) / gridDim.x);
+  const int nt = t1 - t0;
+
+  if (nt > 0) {
+    if (warp < 4) {
+      // ======================= gather + shift + split =======================
+      const int c = tid & 7, r0 = tid >> 3;   // 16-byte chunk, first row; rows r0 + 16 j
+      const uint32_t off0 = (uint32_t)(r0 * 128 + (((((c >> 1) ^ (r0 & 3)) << 1) | (c & 1)) << 4));
+      const uint32_t offk = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));   // standard 128B swizzle (K-major copy)
+      StcWalk wl, wc;
+      stc_walk_init(wl, B, P, nkeys, t0, t1);
+      wc = wl;
+      int idx[8];
+      auto load_idx = [&]() {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int p = wl.pos + r0 + 16 * j;
+          idx[j] = p < wl.end ? __ldg(a.perm + p) : -1;
+        }
+      };
+      auto issue = [&](int s) {
+        uint8_t* h = stage0 + (size_t)s * 2 * SS_PANEL + off0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool ok = idx[j] >= 0;
+          cp_async16(h + j * 2048, a.x + (size_t)(ok ? idx[j] : 0) * SS_D + 4 * c, ok ? 16 : 0);
+        }
+        if (c == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) idxs[s * SS_TILE + r0 + 16 * j] = idx[j];
+        }
+      };
+#pragma unroll
+      for (int li = 0; li < SS_STAGES - 1; ++li) {
+        if (li < nt) {
+          load_idx();
+          issue(li);
+          stc_advance(wl, B);
+        }
+        cp_async_commit();
+      }
+      if (SS_STAGES - 1 < nt) load_idx();
+      auto load_center = [&](int key) { return __ldg(reinterpret_cast<const float4*>(a.cen + (size_t)key * SS_D) + c); };
+      int ckey = wc.key;
+      float4 cen = load_center(ckey);
+      for (int li = 0; li < nt; ++li) {
+        const int s = li % SS_STAGES;
+        if (wc.key != ckey) {
+          ckey = wc.key;
+          cen = load_center(ckey);
+        }
+        const int npts = wc.end - wc.pos;   // rows >= npts are zero padding
+        cp_async_wait_group<SS_STAGES - 2>();
+        uint8_t* h = stage0 + (size_t)s * 2 * SS_PANEL + off0;
+        uint8_t* hk = mslot0 + (size_t)(li & 1) * 2 * SS_PANEL + offk;
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(h + j * 2048);
+        tc::mbar_wait(&mempty[li & 1], ((li >> 1) & 1) ^ 1);   // the GEMM2 that read this slot two tiles ago
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (r0 + 16 * j < npts) {
+            v[j].x -= cen.x; v[j].y -= cen.y; v[j].z -= cen.z; v[j].w -= cen.w;
+          }
+          float4 hi, lo;
+          hi.x = tc::to_tf32(v[j].x); hi.y = tc::to_tf32(v[j].y); hi.z = tc::to_tf32(v[j].z); hi.w = tc::to_tf32(v[j].w);
+          lo.x = v[j].x - hi.x; lo.y = v[j].y - hi.y; lo.z = v[j].z - hi.z; lo.w = v[j].w - hi.w;
+          *reinterpret_cast<float4*>(h + j * 2048) = hi;
+          *reinterpret_cast<float4*>(h + SS_PANEL + j * 2048) = lo;
+          *reinterpret_cast<float4*>(hk + j * 2048) = hi;
+          *reinterpret_cast<float4*>(hk + SS_PANEL + j * 2048) = lo;
+        }
+        tc::fence_proxy_async();
+        tc::mbar_arrive(&ready[s]);
+        const int ln = li + SS_STAGES - 1;
+        if (ln < nt) {
+          const int sn = ln % SS_STAGES;
+          tc::mbar_wait(&empty[sn], ((ln / SS_STAGES) & 1) ^ 1);
+          issue(sn);
+          stc_advance(wl, B);
+          if (ln + 1 < nt) load_idx();
+        }
+        cp_async_commit();
+        stc_advance(wc, B);
+      }
+    } else if (warp == 4) {
+      // ======================= MMA issuer =======================
+      if (lane == 0) {
+        StcWalk wm;
+        stc_walk_init(wm, B, P, nkeys, t0, t1);
+        const uint32_t idesc1 = tc::idesc_tf32(64);
+        const uint32_t idesc2 = tc::idesc_tf32_mn_m64(64);
+        const uint64_t aaug_desc = tc::smem_desc_k_noswz(tc::smem_u32(aaug));
+        int kj = -1, prevkey = -1, g2 = 0;
+        bool pv = false, pfirst = false, plast = false;
+        int pli = 0, pnpts = 0;
+        auto gemm2 = [&]() {
+          const int ps = pli % SS_STAGES, pms = pli & 1;
+          tc::mbar_wait(&masked[pms], (pli >> 1) & 1);
+          if (pfirst) tc::mbar_wait(&d2empty[g2 & 1], ((g2 >> 1) & 1) ^ 1);
+          tc::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + 128 + (g2 & 1) * 64;
+          const uint64_t ad = tc::smem_desc_mn128(tc::smem_u32(stage0 + (size_t)ps * 2 * SS_PANEL), SS_PANEL);
+          const uint64_t bd = tc::smem_desc_mn128(tc::smem_u32(mslot0 + (size_t)pms * 2 * SS_PANEL), SS_PANEL);
+          const int nks = (pnpts + 7) >> 3;
+          for (int ks = 0; ks < nks; ++ks) tc::umma_tf32(tmem_d, ad + ks * 64, bd + ks * 64, idesc2, (pfirst && ks == 0) ? 0u : 1u);
+          tc::umma_commit(&empty[ps]);
+          tc::umma_commit(&mempty[pms]);
+          if (plast) {
+            tc::umma_commit(&d2full[g2 & 1]);
+            ++g2;
+          }
+        };
+        for (int li = 0; li < nt; ++li) {
+          const int s = li % SS_STAGES, b1 = li & 1;
+          if (wm.key != prevkey) {
+            prevkey = wm.key;
+            ++kj;
+            tc::mbar_wait(&wfull[kj & 1], (kj >> 1) & 1);
+          }
+          tc::mbar_wait(&ready[s], (li / SS_STAGES) & 1);
+          tc::mbar_wait(&d1empty[b1], ((li >> 1) & 1) ^ 1);
+          tc::tc_fence_after();
+          const uint32_t ws = tc::smem_u32(wslot0 + (size_t)(kj & 1) * SS_WSLOT);
+          const uint32_t ks_ = tc::smem_u32(mslot0 + (size_t)(li & 1) * 2 * SS_PANEL);   // K-major copies of h | l
+          const uint64_t hd = tc::smem_desc_k128(ks_), ld = tc::smem_desc_k128(ks_ + SS_PANEL);
+          const uint64_t whd = tc::smem_desc_k128(ws), wld = tc::smem_desc_k128(ws + 8192);
+          const uint32_t tmem_d = tmem_base + b1 * 64;
+#pragma unroll
+          for (int ks = 0; ks < SS_D / 8; ++ks) tc::umma_tf32(tmem_d, hd + ks * 2, whd + ks * 2, idesc1, ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < SS_D / 8; ++ks) tc::umma_tf32(tmem_d, ld + ks * 2, whd + ks * 2, idesc1, 1u);
+#pragma unroll
+          for (int ks = 0; ks < SS_D / 8; ++ks) tc::umma_tf32(tmem_d, hd + ks * 2, wld + ks * 2, idesc1, 1u);
+          tc::umma_tf32(tmem_d, aaug_desc, tc::smem_desc_k_noswz(ws + 16384), idesc1, 1u);   // Y -= b
+          tc::umma_commit(&d1full[b1]);
+          if (wm.pos + SS_TILE >= wm.end) tc::umma_commit(&wempty[kj & 1]);   // last tile of the cluster
+          if (pv) gemm2();
+          pv = true;
+          pli = li;
+          pnpts = min(SS_TILE, wm.end - wm.pos);
+          pfirst = wm.gcount == 0;
+          plast = stc_is_last(wm);
+          stc_advance(wm, B);
+        }
+        if (pv) gemm2();
+      }
+    } else if (warp < 9) {
+      // ======================= GEMM1 epilogue: draw, mask, sum y =======================
+      const int sub = warp & 3;                       // TMEM sub-partition of this warp
+      const int row = (sub << 5) | lane;              // TMEM lane == row of the tile
+      const int gt = tid - 160;                       // 0..127
+      const int c = gt & 7, r0 = gt >> 3;
+      const uint32_t off0 = (uint32_t)(r0 * 128 + (((((c >> 1) ^ (r0 & 3)) << 1) | (c & 1)) << 4));
+      StcWalk we;
+      stc_walk_init(we, B, P, nkeys, t0, t1);
+      float sxl[4] = {0.f, 0.f, 0.f, 0.f}, sxr[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int li = 0; li < nt; ++li) {
+        const int s = li % SS_STAGES, ms = li & 1, b1 = li & 1;
+        const int key = we.key;
+        const int npts = min(SS_TILE, we.end - we.pos);
+        tc::mbar_wait(&d1full[b1], (li >> 1) & 1);
+        tc::tc_fence_after();
+        uint32_t v0[32], v1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + b1 * 64;
+        tc::tmem_ld32(taddr, v0);
+        tc::tmem_ld32(taddr + 32, v1);
+        tc::tmem_ld_wait();
+        tc::tc_fence_before();
+        tc::mbar_arrive(&d1empty[b1]);
+        const float ql = gauss_tc_screen_q(v0), qr = gauss_tc_screen_q(v1);
+        tc::mbar_wait(&ready[s], (li / SS_STAGES) & 1);   // the gather warps' writes (indices, panels)
+        const int32_t idx = idxs[s * SS_TILE + row];
+        const bool valid = row < npts;
+        int side = 2;
+        if (valid) {
+          const float rl = gauss_finish(__ldg(a.cst + 3 * key + 1), ql, __ldg(a.loglr + 2 * key));
+          const float rr = gauss_finish(__ldg(a.cst + 3 * key + 2), qr, __ldg(a.loglr + 2 * key + 1));
+          if (a.dump != nullptr) {
+            a.dump[idx] = rl;
+            a.dump[a.n + idx] = rr;
+          }
+          const double u = dpmm_uniform(a.u_inj, idx, a.seed, DPMM_STREAM_SUBLABEL, a.call, (uint64_t)(a.goff + idx));
+          side = dpmm_draw_two(rl, rr, u);
+          a.sub[idx] = (uint8_t)side;
+        }
+        side_s[(li & 1) * SS_TILE + row] = (uint8_t)side;
+        const int nl = __popc(__ballot_sync(0xffffffffu, side == 0));
+        if (lane == 0 && nl > 0) atomicAdd(a.lcount + key, nl);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const uint8_t* hp = stage0 + (size_t)s * 2 * SS_PANEL + off0;
+        uint8_t* mp = mslot0 + (size_t)ms * 2 * SS_PANEL + off0;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int sd = side_s[(li & 1) * SS_TILE + r0 + 16 * j];
+          const float4 h4 = *reinterpret_cast<const float4*>(hp + j * 2048);
+          const float4 l4 = *reinterpret_cast<const float4*>(hp + SS_PANEL + j * 2048);
+          *reinterpret_cast<float4*>(mp + j * 2048) = sd == 0 ? h4 : zero4;
+          *reinterpret_cast<float4*>(mp + SS_PANEL + j * 2048) = sd == 1 ? h4 : zero4;
+          const float yx = h4.x + l4.x, yy = h4.y + l4.y, yz = h4.z + l4.z, yw = h4.w + l4.w;
+          if (sd == 0) {
+            sxl[0] += yx; sxl[1] += yy; sxl[2] += yz; sxl[3] += yw;
+          } else if (sd == 1) {
+            sxr[0] += yx; sxr[1] += yy; sxr[2] += yz; sxr[3] += yw;
+          }
+        }
+        tc::fence_proxy_async();
+        tc::mbar_arrive(&masked[ms]);
+        if (stc_is_last(we)) {   // sum y of the flush group -> Float64 accumulators
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            sxl[q] += __shfl_xor_sync(0xffffffffu, sxl[q], 8);
+            sxl[q] += __shfl_xor_sync(0xffffffffu, sxl[q], 16);
+            sxr[q] += __shfl_xor_sync(0xffffffffu, sxr[q], 8);
+            sxr[q] += __shfl_xor_sync(0xffffffffu, sxr[q], 16);
+          }
+          if (lane < 8) {   // lane == c for lanes 0-7
+            double* dl = a.acc + (size_t)(2 * key) * a.rec + 1 + 4 * lane;
+            double* dr = dl + a.rec;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (sxl[q] != 0.f) atomicAdd(dl + q, (double)sxl[q]);
+              if (sxr[q] != 0.f) atomicAdd(dr + q, (double)sxr[q]);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sxl[q] = sxr[q] = 0.f;
+        }
+        stc_advance(we, B);
+      }
+    } else if (warp < 13) {
+      // ======================= GEMM2 accumulator drain =======================
+      const int sub = warp & 3;
+      const int gt = tid - 288;   // 0..127
+      StcWalk wd;
+      stc_walk_init(wd, B, P, nkeys, t0, t1);
+      int g2 = 0;
+      for (int li = 0; li < nt; ++li) {
+        if (stc_is_last(wd)) {
+          const int buf = g2 & 1;
+          tc::mbar_wait(&d2full[buf], (g2 >> 1) & 1);
+          ++g2;
+          tc::tc_fence_after();
+          uint32_t v0[32], v1[32];
+          const uint32_t taddr = tmem_base + 128 + buf * 64 + ((uint32_t)(sub * 32) << 16);
+          tc::tmem_ld32(taddr, v0);
+          tc::tmem_ld32(taddr + 32, v1);
+          tc::tmem_ld_wait();
+          tc::tc_fence_before();
+          tc::mbar_arrive(&d2empty[buf]);
+          // M = 64: accumulator row m lives in lane (m % 16) of sub-partition m / 16
+          if (lane < 16) {
+            float* trow = T + (16 * sub + lane) * SS_TLD;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              trow[j] = __uint_as_float(v0[j]);
+              trow[32 + j] = __uint_as_float(v1[j]);
+            }
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          for (int e = gt; e < 2 * 528; e += 128) {
+            const int sd = e >= 528 ? 1 : 0;
+            const int ij = tri[e - sd * 528], i = ij >> 8, j = ij & 255;
+            const int co = 32 * sd;
+            const float sv = (T[i * SS_TLD + co + j] + T[(32 + i) * SS_TLD + co + j]) + T[(32 + j) * SS_TLD + co + i];
+            if (sv != 0.f) atomicAdd(a.acc + (size_t)(2 * wd.key + sd) * a.rec + 1 + SS_D + i * SS_D + j, (double)sv);
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+        stc_advance(wd, B);
+      }
+    } else {
+      // ======================= factor staging (warp 13) =======================
+      StcWalk wp;
+      stc_walk_init(wp, B, P, nkeys, t0, t1);
+      int kj = 0, prevkey = -1;
+      for (int li = 0; li < nt; ++li) {
+        if (wp.key != prevkey) {
+          prevkey = wp.key;
+          const int slot = kj & 1;
+          tc::mbar_wait(&wempty[slot], ((kj >> 1) & 1) ^ 1);
+          float* wh = reinterpret_cast<float*>(wslot0 + (size_t)slot * SS_WSLOT);
+          float* wlo = wh + 2048;
+          float* baug = wh + 4096;
+          const float4* src = reinterpret_cast<const float4*>(a.w + (size_t)wp.key * 2 * SS_D * SS_D);
+          for (int e = lane; e < 512; e += 32) {
+            const int r = e >> 3, cc = e & 7;   // row (side, i), 16-byte chunk
+            const float4 v = __ldg(src + e);
+            float4 hi, lo;
+            hi.x = tc::to_tf32(v.x); hi.y = tc::to_tf32(v.y); hi.z = tc::to_tf32(v.z); hi.w = tc::to_tf32(v.w);
+            lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+            const int o = r * SS_D + ((cc ^ (r & 7)) << 2);
+            *reinterpret_cast<float4*>(wh + o) = hi;
+            *reinterpret_cast<float4*>(wlo + o) = lo;
+          }
+          for (int r = lane; r < 64; r += 32) {
+            const float b = __ldg(a.bias + (size_t)wp.key * 64 + r);
+            const float bhi = tc::to_tf32(b), blo = b - bhi;
+            float* p = baug + (r >> 3) * 64 + (r & 7) * 4;
+            p[0] = -bhi;
+            p[1] = -blo;
+          }
+          tc::fence_proxy_async();
+          tc::mbar_arrive(&wfull[slot]);
+          ++kj;
+        }
+        stc_advance(wp, B);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem_base, SS_TMEM_COLS);
+}
