@@ -347,12 +347,24 @@ def main():
     lab_s = stages["label"]["us_per_step"] * 1e-6
     stages["label"].update({"algorithmic_tflops": work["label_flops"] / lab_s / 1e12,
                             "hbm_gbs": work["label_bytes"] / lab_s / 1e9})
-    st_s = stages["stats"]["us_per_step"] * 1e-6
-    stages["stats"].update({"bound": "hbm", "achieved_gbs": work["stats_bytes"] / st_s / 1e9,
-                            "frac": work["stats_bytes"] / st_s / 1e9 / pk["hbm_gbs"]})
     sl_s = stages["sublabel"]["us_per_step"] * 1e-6
-    stages["sublabel"].update({"algorithmic_tflops": work["sublabel_flops"] / sl_s / 1e12,
-                               "hbm_gbs": work["sublabel_bytes"] / sl_s / 1e9})
+    if "stats" in stages:
+        st_s = stages["stats"]["us_per_step"] * 1e-6
+        stages["stats"].update({"bound": "hbm", "achieved_gbs": work["stats_bytes"] / st_s / 1e9,
+                                "frac": work["stats_bytes"] / st_s / 1e9 / pk["hbm_gbs"]})
+        stages["sublabel"].update({"algorithmic_tflops": work["sublabel_flops"] / sl_s / 1e12,
+                                   "hbm_gbs": work["sublabel_bytes"] / sl_s / 1e9})
+    else:
+        # NIW D=32: niw_substats_tc_kernel draws the sub-labels AND accumulates the statistics in one pass
+        # over X; it is credited with the algorithmic bytes of both stages (B_1 and B_3 each read
+        # X once) and, separately, with the bytes it actually has to move (one pass).
+        both = work["sublabel_bytes"] + work["stats_bytes"]
+        stages["sublabel"].update({"kernel": "niw_substats_tc_kernel (sub-label draw + left/right statistics, fused)",
+                                   "fused_stages": ["sublabel", "stats"], "bound": "hbm",
+                                   "achieved_gbs": both / sl_s / 1e9, "frac": both / sl_s / 1e9 / pk["hbm_gbs"],
+                                   "one_pass_gbs": work["stats_bytes"] / sl_s / 1e9,
+                                   "one_pass_frac": work["stats_bytes"] / sl_s / 1e9 / pk["hbm_gbs"],
+                                   "algorithmic_tflops": work["sublabel_flops"] / sl_s / 1e12})
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):

@@ -76,7 +76,7 @@ static int ensure_k(dpmm_ctx* ctx, int K) {
   CK(dev_realloc(&ctx->idx_list, (size_t)cap));
   CK(dev_realloc(&ctx->acc, (size_t)2 * cap * ctx->stats_rec));
   CK(dev_realloc(&ctx->centers, (size_t)2 * cap * ctx->D));
-  CK(dev_realloc(&ctx->outbuf, (size_t)3 * cap * ctx->stats_rec));
+  CK(dev_realloc(&ctx->outbuf, (size_t)3 * cap * ctx->stats_rec + 1));   // + the risk counter of the cached statistics
   ctx->items_cap = ctx->n / ctx->chunk + 2 * (int64_t)cap + 2;
   CK(dev_realloc(&ctx->items, (size_t)ctx->items_cap));
   ctx->Kcap = cap;
@@ -890,7 +890,7 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
     if (rc) return rc;
   }
   const bool all = (indices == nullptr);
-  rc = ensure_stage(ctx, std::max<size_t>((size_t)m * 4 + K, (size_t)m * 3 * rec * 8));
+  rc = ensure_stage(ctx, std::max<size_t>((size_t)m * 4 + K, ((size_t)m * 3 * rec + 1) * 8));
   if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   {
@@ -955,23 +955,31 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
     KernelTimer kt(ctx, TK_STATS_AUX);
     const int T = 256;
     dim3 grid((unsigned)std::min((rec + T - 1) / T, 64), (unsigned)m);
+    if (cached) CK(cudaMemsetAsync(ctx->outbuf + (size_t)m * 3 * rec, 0, 8, ctx->stream));
     stats_finalize_kernel<<<grid, T, 0, ctx->stream>>>(ctx->acc, ctx->seg_off, ctx->lr_cursor, ctx->idx_list, m, D, rec,
                                                        ctx->prior == DPMM_PRIOR_NIW ? 1 : 0, ctx->outbuf,
                                                        (stats_tc || cached) ? ctx->centers : nullptr,
-                                                       cached ? ctx->lcount : nullptr);
+                                                       cached ? ctx->lcount : nullptr,
+                                                       cached ? ctx->outbuf + (size_t)m * 3 * rec : nullptr);
     CK(cudaGetLastError());
   }
   if (ctx->comm != nullptr) {
     KernelTimer kt(ctx, TK_ALLREDUCE);
     // aggregate_suff_stats across workers (niw.jl:64-66; local_clusters_actions.jl:194-196, 246-248)
-    const int r = ctx->nccl.AllReduce(ctx->outbuf, ctx->outbuf, (size_t)m * 3 * rec, /*ncclFloat64*/ 8, /*ncclSum*/ 0,
+    const int r = ctx->nccl.AllReduce(ctx->outbuf, ctx->outbuf, (size_t)m * 3 * rec + (cached ? 1 : 0), /*ncclFloat64*/ 8, /*ncclSum*/ 0,
                                       ctx->comm, ctx->stream);
     if (r != 0) return fail(ctx, DPMM_ENCCL, std::string("ncclAllReduce: ") + ctx->nccl.GetErrorString(r));
   }
   if (counts == nullptr && sum_x == nullptr && sum_xx == nullptr) return 0;
   double* h = (double*)ctx->hstage;
-  CK(cudaMemcpyAsync(h, ctx->outbuf, (size_t)m * 3 * rec * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h, ctx->outbuf, ((size_t)m * 3 * rec + (cached ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (cached && h[(size_t)m * 3 * rec] != 0.0) {
+    // some (tiny or degenerate) run lies far from its cluster's centre relative to its own magnitude:
+    // recompute with the FP32/FP64 statistics kernel (on every rank: the counter was all-reduced)
+    ctx->stats_cached = false;
+    return dpmm_suff_stats(ctx, indices, n_indices, counts, sum_x, sum_xx);
+  }
   for (int a = 0; a < m; ++a)
     for (int s = 0; s < 3; ++s) {
       const double* r = h + ((size_t)a * 3 + s) * rec;

@@ -8,41 +8,39 @@
 //   create_sufficient_statistics (NIW)                         src/priors/niw.jl:42-51
 //
 // A tile = 128 consecutive positions of ONE cluster k in the label-sorted permutation `perm`.  Its rows
-// are gathered with cp.async, shifted by the cluster's centre c_k (x - c_k is exact in Float32, see
-// niw_pack_center) and split z = h + l with h = tf32(z) into two [point][feature] panels of 128-byte rows,
-// written twice: with the 32-byte-atom 128B swizzle (the only MN-major layout tcgen05 takes for 32-bit
-// data) for GEMM2 and with the standard 128B swizzle for GEMM1 (tcgen05 rejects the 32-byte-atom swizzle
-// for a K-major operand: "misaligned address").  The K-major copies live in the slot that later receives
-// the masked panels, so they cost no shared memory.
+// are gathered with cp.async into a thread-private landing ring, shifted by the cluster's centre c_k
+// (x - c_k is exact in Float32, see niw_pack_center) and split z = h + l with h = tf32(z).
 //
-//   GEMM1 (contraction over FEATURES; K-major A operand, M = 128 points, N = 64):
+//   GEMM1 (contraction over FEATURES; h | l as K-major A operands, 128B swizzle, M = 128 points, N = 64):
 //       Y = h Wh' + l Wh' + h Wl' - b,   W = [U_left; U_right] = Wh + Wl,   b = U_s (mu_s - c_k)
-//     i.e. a 3-term error-compensated TF32 product (only l Wl', <= 2^-22 relative, is dropped) whose
+//     a 3-term error-compensated TF32 product (only l Wl', <= 2^-22 relative, is dropped) whose
 //     accumulator row p holds U_l (x_p - mu_l) | U_r (x_p - mu_r).  The epilogue warps read it with
 //     tcgen05.ld, form q = |y|^2, r = -c - q/2 + log w (the reference's Float32 final operations) and
 //     draw the sub-label with the reference's inverse-CDF rule.
-//   GEMM2 (contraction over POINTS; panels read as MN-major operands, M = 64, N = 64):
-//       D = [h | l]' [h_left | h_right]
-//     where h_left / h_right are copies of h with the rows of the other side zeroed (written by the
-//     epilogue warps once the sub-labels are known).  Rows 0-31 of D hold sum h h', rows 32-63 sum l h'
-//     for the left (columns 0-31) and right (columns 32-63) side;  S = hh' + lh' + (lh')' as in
-//     kernels_stats_tc.cuh, flushed to the Float64 accumulators every STC_FLUSH tiles.
-//   sum y and the left count come from the masking pass.  Everything is shifted back by c_k in
+//   GEMM2 (contraction over POINTS; MN-major operands, M = 64, N = 32): once the sub-labels are known the
+//     epilogue warps copy the rows of h | l into a second pair of panels PERMUTED so that the left rows
+//     come first and the right rows start at a multiple of 8 (zero rows pad both runs), in the MN-major
+//     layout (128B swizzle with 32-byte atoms, the only one tcgen05 takes for 32-bit MN-major data).
+//     Every 8-row k-step then belongs to one side:   D_side += [h | l]' h   (rows 0-31 sum h h',
+//     rows 32-63 sum l h'),  S = hh' + lh' + (lh')' as in kernels_stats_tc.cuh, flushed to the Float64
+//     accumulators every STC_FLUSH tiles.  No masked copies, no left/right partition of the permutation.
+//   sum y and the left count come from the permuting pass.  Everything is shifted back by c_k in
 //   Float64 by stats_finalize_kernel.
 //
 // Warp roles (448 threads, one CTA per SM; every CTA owns a contiguous range of the tile sequence):
-//   warps 0-3  gather + shift + split          warps 5-8   GEMM1 epilogue: draw, mask, sum y
+//   warps 0-3  gather + shift + split          warps 5-8   GEMM1 epilogue: draw, permute, sum y
 //   warp  4    tcgen05.mma issuer              warps 9-12  GEMM2 accumulator drain
-//   warp  13   stages the factors of the next cluster (double-buffered)
+//   warp  13   stages the factors of the next cluster
 #pragma once
 #include "kernels_stats_tc.cuh"
 
 #define SS_D 32
 #define SS_TILE 128
-#define SS_STAGES 3                      // h | l ring
-#define SS_MSLOTS 2                      // h_left | h_right ring
+#define SS_RAW 3                         // landing ring of raw rows (thread-private slots)
 #define SS_THREADS 448
 #define SS_PANEL 16384                   // one [128][32] Float32 panel
+#define SS_PROWS 136                     // rows of a permuted panel: both runs padded to a multiple of 8
+#define SS_PPANEL (SS_PROWS * 128)
 #define SS_WSLOT (8192 + 8192 + 2048)    // Wh | Wl | bias k-step operand
 #define SS_TMEM_COLS 256                 // GEMM1: 2 x 64 columns, GEMM2: 2 x 64 columns
 #define SS_TLD 65
@@ -71,18 +69,20 @@ struct SubStatsArgs {
 };
 
 struct SubStatsSmem {
-  size_t stages, mslots, wslots, aaug, tbuf, tri, idxs, side, bnd, pre, bars, slot, total;
+  size_t raw, split, perm, wslot, aaug, tbuf, tri, dest, cnt, kcnt, bnd, pre, bars, slot, total;
   __host__ __device__ explicit SubStatsSmem(int K) {
     size_t o = 0;
-    stages = o; o += (size_t)SS_STAGES * 2 * SS_PANEL;
-    mslots = o; o += (size_t)SS_MSLOTS * 2 * SS_PANEL;
-    wslots = o; o += 2 * (size_t)SS_WSLOT;
+    raw = o;    o += (size_t)SS_RAW * SS_PANEL;
+    split = o;  o += (size_t)2 * 2 * SS_PANEL;       // 2 x (h | l), K-major
+    perm = o;   o += (size_t)2 * 2 * SS_PPANEL;      // 2 x (h | l), permuted, MN-major
+    wslot = o;  o += (size_t)SS_WSLOT;
     aaug = o;   o += 4096;
     tbuf = o;   o += 64 * SS_TLD * 4;
     tri = o;    o += 528 * 2;
     o = (o + 15) & ~(size_t)15;
-    idxs = o;   o += SS_STAGES * SS_TILE * 4;
-    side = o;   o += 2 * SS_TILE;
+    dest = o;   o += SS_TILE;
+    cnt = o;    o += 4 * 4;
+    kcnt = o;   o += 4 * 4;
     bnd = o;    o += (size_t)(K + 1) * 4;
     pre = o;    o += (size_t)(K + 1) * 4;
     o = (o + 15) & ~(size_t)15;
@@ -95,27 +95,29 @@ struct SubStatsSmem {
 __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const SubStatsArgs a) {
   extern __shared__ __align__(1024) uint8_t ss_smem[];
   const SubStatsSmem L(a.K);
-  uint8_t* stage0 = ss_smem + L.stages;
-  uint8_t* mslot0 = ss_smem + L.mslots;
-  uint8_t* wslot0 = ss_smem + L.wslots;
+  uint8_t* raw0 = ss_smem + L.raw;
+  uint8_t* split0 = ss_smem + L.split;
+  uint8_t* perm0 = ss_smem + L.perm;
+  uint8_t* wslot = ss_smem + L.wslot;
   float* aaug = reinterpret_cast<float*>(ss_smem + L.aaug);
   float* T = reinterpret_cast<float*>(ss_smem + L.tbuf);
   uint16_t* tri = reinterpret_cast<uint16_t*>(ss_smem + L.tri);
-  int32_t* idxs = reinterpret_cast<int32_t*>(ss_smem + L.idxs);
-  uint8_t* side_s = ss_smem + L.side;
+  uint8_t* dest_s = ss_smem + L.dest;
+  volatile int32_t* cnt_s = reinterpret_cast<int32_t*>(ss_smem + L.cnt);
+  volatile int32_t* kcnt = reinterpret_cast<int32_t*>(ss_smem + L.kcnt);
   int32_t* B = reinterpret_cast<int32_t*>(ss_smem + L.bnd);
   int32_t* P = reinterpret_cast<int32_t*>(ss_smem + L.pre);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ss_smem + L.bars);
-  uint64_t* ready = bars;            // [3] h | l of the stage split and visible
-  uint64_t* empty = bars + 3;        // [3] GEMM2 of the stage retired
-  uint64_t* d1full = bars + 6;       // [2] GEMM1 accumulator complete
-  uint64_t* d1empty = bars + 8;      // [2] ... read by the epilogue
-  uint64_t* masked = bars + 10;      // [2] h_left | h_right written
-  uint64_t* mempty = bars + 12;      // [2] GEMM2 that read the slot retired
-  uint64_t* d2full = bars + 14;      // [2] flush group complete
-  uint64_t* d2empty = bars + 16;     // [2] ... drained
-  uint64_t* wfull = bars + 18;       // [2] factors of a cluster staged
-  uint64_t* wempty = bars + 20;      // [2] last GEMM1 of the cluster retired
+  uint64_t* ready = bars;            // [2] h | l of the tile split (K-major) and visible
+  uint64_t* sfree = bars + 2;        // [2] ... read by GEMM1 and by the permuting pass
+  uint64_t* d1full = bars + 4;       // [2] GEMM1 accumulator complete
+  uint64_t* d1empty = bars + 6;      // [2] ... read by the epilogue
+  uint64_t* permd = bars + 8;        // [2] permuted panels written
+  uint64_t* pfree = bars + 10;       // [2] GEMM2 that read them retired
+  uint64_t* d2full = bars + 12;      // [2] flush group complete
+  uint64_t* d2empty = bars + 14;     // [2] ... drained
+  uint64_t* wfull = bars + 16;       // factors of a cluster staged
+  uint64_t* wempty = bars + 17;      // last GEMM1 of the cluster retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ss_smem + L.slot);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nkeys = a.K;
@@ -127,28 +129,26 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
     if (j >= i) tri[i * 32 - (i * (i - 1)) / 2 + (j - i)] = (uint16_t)((i << 8) | j);
   }
   for (int e = tid; e < 1024; e += SS_THREADS) aaug[e] = 0.f;
-  for (int s = 0; s < 2; ++s) {
-    float* baug = reinterpret_cast<float*>(wslot0 + (size_t)s * SS_WSLOT + 16384);
+  {
+    float* baug = reinterpret_cast<float*>(wslot + 16384);
     for (int e = tid; e < 512; e += SS_THREADS) baug[e] = 0.f;
   }
   if (blockIdx.x == 0)
     for (int e = tid; e < 2 * nkeys * SS_D; e += SS_THREADS)
       a.centers[e] = __ldg(a.cen + (size_t)(e >> 6) * SS_D + (e & 31));
   if (tid == 0) {
-    for (int s = 0; s < SS_STAGES; ++s) {
-      tc::mbar_init(&ready[s], 128);
-      tc::mbar_init(&empty[s], 1);
-    }
     for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&ready[b], 128);
+      tc::mbar_init(&sfree[b], 128);
       tc::mbar_init(&d1full[b], 1);
       tc::mbar_init(&d1empty[b], 128);
-      tc::mbar_init(&masked[b], 128);
-      tc::mbar_init(&mempty[b], 1);
+      tc::mbar_init(&permd[b], 128);
+      tc::mbar_init(&pfree[b], 1);
       tc::mbar_init(&d2full[b], 1);
       tc::mbar_init(&d2empty[b], 128);
-      tc::mbar_init(&wfull[b], 32);
-      tc::mbar_init(&wempty[b], 1);
     }
+    tc::mbar_init(wfull, 32);
+    tc::mbar_init(wempty, 1);
     tc::fence_barrier_init();
   }
   __syncthreads();
@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
     if (warp < 4) {
       // ======================= gather + shift + split =======================
       const int c = tid & 7, r0 = tid >> 3;   // 16-byte chunk, first row; rows r0 + 16 j
-      const uint32_t off0 = (uint32_t)(r0 * 128 + (((((c >> 1) ^ (r0 & 3)) << 1) | (c & 1)) << 4));
-      const uint32_t offk = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));   // standard 128B swizzle (K-major copy)
+      const uint32_t offr = (uint32_t)(r0 * 128 + c * 16);                  // landing ring: plain rows
+      const uint32_t offk = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));   // K-major panels: 128B swizzle
       StcWalk wl, wc;
       stc_walk_init(wl, B, P, nkeys, t0, t1);
       wc = wl;
@@ -201,19 +201,15 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         }
       };
       auto issue = [&](int s) {
-        uint8_t* h = stage0 + (size_t)s * 2 * SS_PANEL + off0;
+        uint8_t* dst = raw0 + (size_t)s * SS_PANEL + offr;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const bool ok = idx[j] >= 0;
-          cp_async16(h + j * 2048, a.x + (size_t)(ok ? idx[j] : 0) * SS_D + 4 * c, ok ? 16 : 0);
-        }
-        if (c == 0) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) idxs[s * SS_TILE + r0 + 16 * j] = idx[j];
+          cp_async16(dst + j * 2048, a.x + (size_t)(ok ? idx[j] : 0) * SS_D + 4 * c, ok ? 16 : 0);
         }
       };
 #pragma unroll
-      for (int li = 0; li < SS_STAGES - 1; ++li) {
+      for (int li = 0; li < SS_RAW - 1; ++li) {
         if (li < nt) {
           load_idx();
           issue(li);
@@ -221,24 +217,32 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         }
         cp_async_commit();
       }
-      if (SS_STAGES - 1 < nt) load_idx();
+      if (SS_RAW - 1 < nt) load_idx();
       auto load_center = [&](int key) { return __ldg(reinterpret_cast<const float4*>(a.cen + (size_t)key * SS_D) + c); };
       int ckey = wc.key;
       float4 cen = load_center(ckey);
       for (int li = 0; li < nt; ++li) {
-        const int s = li % SS_STAGES;
+        const int b = li & 1;
         if (wc.key != ckey) {
           ckey = wc.key;
           cen = load_center(ckey);
         }
         const int npts = wc.end - wc.pos;   // rows >= npts are zero padding
-        cp_async_wait_group<SS_STAGES - 2>();
-        uint8_t* h = stage0 + (size_t)s * 2 * SS_PANEL + off0;
-        uint8_t* hk = mslot0 + (size_t)(li & 1) * 2 * SS_PANEL + offk;
+        cp_async_wait_group<SS_RAW - 2>();
+        const uint8_t* src = raw0 + (size_t)(li % SS_RAW) * SS_PANEL + offr;
         float4 v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(h + j * 2048);
-        tc::mbar_wait(&mempty[li & 1], ((li >> 1) & 1) ^ 1);   // the GEMM2 that read this slot two tiles ago
+        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(src + j * 2048);
+        // this thread's slot of tile li - 1 is free again (it alone reads what it gathered): next gather
+        const int ln = li + SS_RAW - 1;
+        if (ln < nt) {
+          issue(ln % SS_RAW);
+          stc_advance(wl, B);
+          if (ln + 1 < nt) load_idx();
+        }
+        cp_async_commit();
+        tc::mbar_wait(&sfree[b], ((li >> 1) & 1) ^ 1);   // GEMM1 and the permuting pass of tile li - 2
+        uint8_t* hk = split0 + (size_t)b * 2 * SS_PANEL + offk;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (r0 + 16 * j < npts) {
@@ -247,22 +251,11 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           float4 hi, lo;
           hi.x = tc::to_tf32(v[j].x); hi.y = tc::to_tf32(v[j].y); hi.z = tc::to_tf32(v[j].z); hi.w = tc::to_tf32(v[j].w);
           lo.x = v[j].x - hi.x; lo.y = v[j].y - hi.y; lo.z = v[j].z - hi.z; lo.w = v[j].w - hi.w;
-          *reinterpret_cast<float4*>(h + j * 2048) = hi;
-          *reinterpret_cast<float4*>(h + SS_PANEL + j * 2048) = lo;
           *reinterpret_cast<float4*>(hk + j * 2048) = hi;
           *reinterpret_cast<float4*>(hk + SS_PANEL + j * 2048) = lo;
         }
         tc::fence_proxy_async();
-        tc::mbar_arrive(&ready[s]);
-        const int ln = li + SS_STAGES - 1;
-        if (ln < nt) {
-          const int sn = ln % SS_STAGES;
-          tc::mbar_wait(&empty[sn], ((ln / SS_STAGES) & 1) ^ 1);
-          issue(sn);
-          stc_advance(wl, B);
-          if (ln + 1 < nt) load_idx();
-        }
-        cp_async_commit();
+        tc::mbar_arrive(&ready[b]);
         stc_advance(wc, B);
       }
     } else if (warp == 4) {
@@ -271,56 +264,57 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         StcWalk wm;
         stc_walk_init(wm, B, P, nkeys, t0, t1);
         const uint32_t idesc1 = tc::idesc_tf32(64);
-        const uint32_t idesc2 = tc::idesc_tf32_mn_m64(64);
+        const uint32_t idesc2 = tc::idesc_tf32_mn_m64(32);
         const uint64_t aaug_desc = tc::smem_desc_k_noswz(tc::smem_u32(aaug));
+        const uint32_t ws = tc::smem_u32(wslot);
+        const uint64_t whd = tc::smem_desc_k128(ws), wld = tc::smem_desc_k128(ws + 8192);
+        const uint64_t baug_desc = tc::smem_desc_k_noswz(ws + 16384);
         int kj = -1, prevkey = -1, g2 = 0;
         bool pv = false, pfirst = false, plast = false;
-        int pli = 0, pnpts = 0;
+        int pli = 0;
         auto gemm2 = [&]() {
-          const int ps = pli % SS_STAGES, pms = pli & 1;
-          tc::mbar_wait(&masked[pms], (pli >> 1) & 1);
+          const int pms = pli & 1;
+          tc::mbar_wait(&permd[pms], (pli >> 1) & 1);
           if (pfirst) tc::mbar_wait(&d2empty[g2 & 1], ((g2 >> 1) & 1) ^ 1);
           tc::tc_fence_after();
-          const uint32_t tmem_d = tmem_base + 128 + (g2 & 1) * 64;
-          const uint64_t ad = tc::smem_desc_mn128(tc::smem_u32(stage0 + (size_t)ps * 2 * SS_PANEL), SS_PANEL);
-          const uint64_t bd = tc::smem_desc_mn128(tc::smem_u32(mslot0 + (size_t)pms * 2 * SS_PANEL), SS_PANEL);
-          const int nks = (pnpts + 7) >> 3;
-          for (int ks = 0; ks < nks; ++ks) tc::umma_tf32(tmem_d, ad + ks * 64, bd + ks * 64, idesc2, (pfirst && ks == 0) ? 0u : 1u);
-          tc::umma_commit(&empty[ps]);
-          tc::umma_commit(&mempty[pms]);
+          const int nkl = kcnt[pms * 2], nkr = kcnt[pms * 2 + 1];
+          const uint32_t tmem_l = tmem_base + 128 + (g2 & 1) * 64, tmem_r = tmem_l + 32;
+          // A = [h | l] (two 32-row atoms, one panel apart), B = h: the same descriptor, one k-step = 8 rows = 1024 B
+          const uint64_t pd = tc::smem_desc_mn128(tc::smem_u32(perm0 + (size_t)pms * 2 * SS_PPANEL), SS_PPANEL);
+          for (int ks = 0; ks < nkl; ++ks) tc::umma_tf32(tmem_l, pd + ks * 64, pd + ks * 64, idesc2, (pfirst && ks == 0) ? 0u : 1u);
+          for (int ks = 0; ks < nkr; ++ks)
+            tc::umma_tf32(tmem_r, pd + (nkl + ks) * 64, pd + (nkl + ks) * 64, idesc2, (pfirst && ks == 0) ? 0u : 1u);
+          tc::umma_commit(&pfree[pms]);
           if (plast) {
             tc::umma_commit(&d2full[g2 & 1]);
             ++g2;
           }
         };
         for (int li = 0; li < nt; ++li) {
-          const int s = li % SS_STAGES, b1 = li & 1;
+          const int b = li & 1;
           if (wm.key != prevkey) {
             prevkey = wm.key;
             ++kj;
-            tc::mbar_wait(&wfull[kj & 1], (kj >> 1) & 1);
+            tc::mbar_wait(wfull, kj & 1);
           }
-          tc::mbar_wait(&ready[s], (li / SS_STAGES) & 1);
-          tc::mbar_wait(&d1empty[b1], ((li >> 1) & 1) ^ 1);
+          tc::mbar_wait(&ready[b], (li >> 1) & 1);
+          tc::mbar_wait(&d1empty[b], ((li >> 1) & 1) ^ 1);
           tc::tc_fence_after();
-          const uint32_t ws = tc::smem_u32(wslot0 + (size_t)(kj & 1) * SS_WSLOT);
-          const uint32_t ks_ = tc::smem_u32(mslot0 + (size_t)(li & 1) * 2 * SS_PANEL);   // K-major copies of h | l
-          const uint64_t hd = tc::smem_desc_k128(ks_), ld = tc::smem_desc_k128(ks_ + SS_PANEL);
-          const uint64_t whd = tc::smem_desc_k128(ws), wld = tc::smem_desc_k128(ws + 8192);
-          const uint32_t tmem_d = tmem_base + b1 * 64;
+          const uint32_t hs = tc::smem_u32(split0 + (size_t)b * 2 * SS_PANEL);
+          const uint64_t hd = tc::smem_desc_k128(hs), ld = tc::smem_desc_k128(hs + SS_PANEL);
+          const uint32_t tmem_d = tmem_base + b * 64;
 #pragma unroll
           for (int ks = 0; ks < SS_D / 8; ++ks) tc::umma_tf32(tmem_d, hd + ks * 2, whd + ks * 2, idesc1, ks > 0 ? 1u : 0u);
 #pragma unroll
           for (int ks = 0; ks < SS_D / 8; ++ks) tc::umma_tf32(tmem_d, ld + ks * 2, whd + ks * 2, idesc1, 1u);
 #pragma unroll
           for (int ks = 0; ks < SS_D / 8; ++ks) tc::umma_tf32(tmem_d, hd + ks * 2, wld + ks * 2, idesc1, 1u);
-          tc::umma_tf32(tmem_d, aaug_desc, tc::smem_desc_k_noswz(ws + 16384), idesc1, 1u);   // Y -= b
-          tc::umma_commit(&d1full[b1]);
-          if (wm.pos + SS_TILE >= wm.end) tc::umma_commit(&wempty[kj & 1]);   // last tile of the cluster
+          tc::umma_tf32(tmem_d, aaug_desc, baug_desc, idesc1, 1u);   // Y -= b
+          tc::umma_commit(&d1full[b]);
+          if (wm.pos + SS_TILE >= wm.end) tc::umma_commit(wempty);   // last tile of the cluster
           if (pv) gemm2();
           pv = true;
           pli = li;
-          pnpts = min(SS_TILE, wm.end - wm.pos);
           pfirst = wm.gcount == 0;
           plast = stc_is_last(wm);
           stc_advance(wm, B);
@@ -328,67 +322,111 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         if (pv) gemm2();
       }
     } else if (warp < 9) {
-      // ======================= GEMM1 epilogue: draw, mask, sum y =======================
+      // ======================= GEMM1 epilogue: draw, permute, sum y =======================
       const int sub = warp & 3;                       // TMEM sub-partition of this warp
       const int row = (sub << 5) | lane;              // TMEM lane == row of the tile
       const int gt = tid - 160;                       // 0..127
       const int c = gt & 7, r0 = gt >> 3;
-      const uint32_t off0 = (uint32_t)(r0 * 128 + (((((c >> 1) ^ (r0 & 3)) << 1) | (c & 1)) << 4));
+      const uint32_t offk = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));
+      const uint32_t lt_mask = (1u << lane) - 1u;
       StcWalk we;
       stc_walk_init(we, B, P, nkeys, t0, t1);
       float sxl[4] = {0.f, 0.f, 0.f, 0.f}, sxr[4] = {0.f, 0.f, 0.f, 0.f};
+      int ckey = -1;
+      float cl = 0.f, cr = 0.f, lwl = 0.f, lwr = 0.f;
       for (int li = 0; li < nt; ++li) {
-        const int s = li % SS_STAGES, ms = li & 1, b1 = li & 1;
+        const int b = li & 1;
         const int key = we.key;
         const int npts = min(SS_TILE, we.end - we.pos);
-        tc::mbar_wait(&d1full[b1], (li >> 1) & 1);
+        const bool valid = row < npts;
+        // everything that does not depend on the accumulator comes first: index, constants, uniform
+        const int32_t idx = valid ? __ldg(a.perm + we.pos + row) : 0;
+        if (key != ckey) {
+          ckey = key;
+          cl = __ldg(a.cst + 3 * key + 1); cr = __ldg(a.cst + 3 * key + 2);
+          lwl = __ldg(a.loglr + 2 * key); lwr = __ldg(a.loglr + 2 * key + 1);
+        }
+        double u = 0.0;
+        if (valid) u = dpmm_uniform(a.u_inj, idx, a.seed, DPMM_STREAM_SUBLABEL, a.call, (uint64_t)(a.goff + idx));
+        tc::mbar_wait(&d1full[b], (li >> 1) & 1);
         tc::tc_fence_after();
         uint32_t v0[32], v1[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + b1 * 64;
+        const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + b * 64;
         tc::tmem_ld32(taddr, v0);
         tc::tmem_ld32(taddr + 32, v1);
         tc::tmem_ld_wait();
         tc::tc_fence_before();
-        tc::mbar_arrive(&d1empty[b1]);
+        tc::mbar_arrive(&d1empty[b]);
         const float ql = gauss_tc_screen_q(v0), qr = gauss_tc_screen_q(v1);
-        tc::mbar_wait(&ready[s], (li / SS_STAGES) & 1);   // the gather warps' writes (indices, panels)
-        const int32_t idx = idxs[s * SS_TILE + row];
-        const bool valid = row < npts;
         int side = 2;
         if (valid) {
-          const float rl = gauss_finish(__ldg(a.cst + 3 * key + 1), ql, __ldg(a.loglr + 2 * key));
-          const float rr = gauss_finish(__ldg(a.cst + 3 * key + 2), qr, __ldg(a.loglr + 2 * key + 1));
+          const float rl = gauss_finish(cl, ql, lwl), rr = gauss_finish(cr, qr, lwr);
           if (a.dump != nullptr) {
             a.dump[idx] = rl;
             a.dump[a.n + idx] = rr;
           }
-          const double u = dpmm_uniform(a.u_inj, idx, a.seed, DPMM_STREAM_SUBLABEL, a.call, (uint64_t)(a.goff + idx));
           side = dpmm_draw_two(rl, rr, u);
           a.sub[idx] = (uint8_t)side;
         }
-        side_s[(li & 1) * SS_TILE + row] = (uint8_t)side;
-        const int nl = __popc(__ballot_sync(0xffffffffu, side == 0));
-        if (lane == 0 && nl > 0) atomicAdd(a.lcount + key, nl);
+        // ---- destination row of every point: left run first, right run from a multiple of 8 ----
+        const uint32_t bl = __ballot_sync(0xffffffffu, side == 0), br = __ballot_sync(0xffffffffu, side == 1);
+        if (lane == 0) cnt_s[sub] = __popc(bl) | (__popc(br) << 8);
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const uint8_t* hp = stage0 + (size_t)s * 2 * SS_PANEL + off0;
-        uint8_t* mp = mslot0 + (size_t)ms * 2 * SS_PANEL + off0;
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        int nl = 0, nr = 0, offl = 0, offr_ = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const int cw = cnt_s[w];
+          if (w < sub) {
+            offl += cw & 255;
+            offr_ += cw >> 8;
+          }
+          nl += cw & 255;
+          nr += cw >> 8;
+        }
+        const int nl8 = max(8, (nl + 7) & ~7), nr8 = max(8, (nr + 7) & ~7);
+        dest_s[row] = side == 0 ? (uint8_t)(offl + __popc(bl & lt_mask))
+                                : (side == 1 ? (uint8_t)(nl8 + offr_ + __popc(br & lt_mask)) : (uint8_t)255);
+        if (gt == 0 && nl > 0) atomicAdd(a.lcount + key, nl);
+        tc::mbar_wait(&ready[b], (li >> 1) & 1);          // the gather warps' panel writes
+        tc::mbar_wait(&pfree[b], ((li >> 1) & 1) ^ 1);    // the GEMM2 that read this slot two tiles ago
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (gt == 0) {
+          kcnt[b * 2] = nl8 >> 3;
+          kcnt[b * 2 + 1] = nr8 >> 3;
+        }
+        const uint8_t* hp = split0 + (size_t)b * 2 * SS_PANEL + offk;
+        uint8_t* pp = perm0 + (size_t)b * 2 * SS_PPANEL;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int sd = side_s[(li & 1) * SS_TILE + r0 + 16 * j];
-          const float4 h4 = *reinterpret_cast<const float4*>(hp + j * 2048);
-          const float4 l4 = *reinterpret_cast<const float4*>(hp + SS_PANEL + j * 2048);
-          *reinterpret_cast<float4*>(mp + j * 2048) = sd == 0 ? h4 : zero4;
-          *reinterpret_cast<float4*>(mp + SS_PANEL + j * 2048) = sd == 1 ? h4 : zero4;
-          const float yx = h4.x + l4.x, yy = h4.y + l4.y, yz = h4.z + l4.z, yw = h4.w + l4.w;
-          if (sd == 0) {
-            sxl[0] += yx; sxl[1] += yy; sxl[2] += yz; sxl[3] += yw;
-          } else if (sd == 1) {
-            sxr[0] += yx; sxr[1] += yy; sxr[2] += yz; sxr[3] += yw;
+          const int d = dest_s[r0 + 16 * j];
+          if (d != 255) {
+            const float4 h4 = *reinterpret_cast<const float4*>(hp + j * 2048);
+            const float4 l4 = *reinterpret_cast<const float4*>(hp + SS_PANEL + j * 2048);
+            uint8_t* q = pp + d * 128 + (((((c >> 1) ^ (d & 3)) << 1) | (c & 1)) << 4);
+            *reinterpret_cast<float4*>(q) = h4;
+            *reinterpret_cast<float4*>(q + SS_PPANEL) = l4;
+            const float yx = h4.x + l4.x, yy = h4.y + l4.y, yz = h4.z + l4.z, yw = h4.w + l4.w;
+            if (d < nl8) {
+              sxl[0] += yx; sxl[1] += yy; sxl[2] += yz; sxl[3] += yw;
+            } else {
+              sxr[0] += yx; sxr[1] += yy; sxr[2] += yz; sxr[3] += yw;
+            }
+          }
+        }
+        {   // zero rows that pad the two runs to a multiple of 8 (at most 8 + 8): thread = (row, chunk)
+          const int z = gt >> 3, padl = nl8 - nl, padr = nr8 - nr;
+          int d = -1;
+          if (z < padl) d = nl + z;
+          else if (z - padl < padr) d = nl8 + nr + (z - padl);
+          if (d >= 0) {
+            uint8_t* q = pp + d * 128 + (((((c >> 1) ^ (d & 3)) << 1) | (c & 1)) << 4);
+            *reinterpret_cast<float4*>(q) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(q + SS_PPANEL) = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         tc::fence_proxy_async();
-        tc::mbar_arrive(&masked[ms]);
+        tc::mbar_arrive(&permd[b]);
+        tc::mbar_arrive(&sfree[b]);
         if (stc_is_last(we)) {   // sum y of the flush group -> Float64 accumulators
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -457,14 +495,13 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       StcWalk wp;
       stc_walk_init(wp, B, P, nkeys, t0, t1);
       int kj = 0, prevkey = -1;
+      float* wh = reinterpret_cast<float*>(wslot);
+      float* wlo = wh + 2048;
+      float* baug = wh + 4096;
       for (int li = 0; li < nt; ++li) {
         if (wp.key != prevkey) {
           prevkey = wp.key;
-          const int slot = kj & 1;
-          tc::mbar_wait(&wempty[slot], ((kj >> 1) & 1) ^ 1);
-          float* wh = reinterpret_cast<float*>(wslot0 + (size_t)slot * SS_WSLOT);
-          float* wlo = wh + 2048;
-          float* baug = wh + 4096;
+          tc::mbar_wait(wempty, (kj & 1) ^ 1);   // every GEMM1 of the previous cluster has retired
           const float4* src = reinterpret_cast<const float4*>(a.w + (size_t)wp.key * 2 * SS_D * SS_D);
           for (int e = lane; e < 512; e += 32) {
             const int r = e >> 3, cc = e & 7;   // row (side, i), 16-byte chunk
@@ -477,14 +514,14 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
             *reinterpret_cast<float4*>(wlo + o) = lo;
           }
           for (int r = lane; r < 64; r += 32) {
-            const float b = __ldg(a.bias + (size_t)wp.key * 64 + r);
-            const float bhi = tc::to_tf32(b), blo = b - bhi;
+            const float bv = __ldg(a.bias + (size_t)wp.key * 64 + r);
+            const float bhi = tc::to_tf32(bv), blo = bv - bhi;
             float* p = baug + (r >> 3) * 64 + (r & 7) * 4;
             p[0] = -bhi;
             p[1] = -blo;
           }
           tc::fence_proxy_async();
-          tc::mbar_arrive(&wfull[slot]);
+          tc::mbar_arrive(wfull);
           ++kj;
         }
         stc_advance(wp, B);

@@ -65,3 +65,19 @@ else:
             worst = max(worst, (np.abs(sxx1[k, s] - S) / (dd[:, None] * dd[None, :])).max())
             assert c1[k, s] == m.sum(), (k, s, c1[k, s], m.sum())
     print("fused stats vs Float64 (own sub-labels): worst scaled err", worst)
+# worst (cluster, side) of the fused run against Float64 sums of its own sub-labels
+x = case["x"].astype(np.float64)
+c1, sx1, sxx1 = st1
+rows = []
+for k in range(K):
+    for s in (1, 2):
+        m = (l1 == k + 1) & (s1 == s)
+        if not m.any():
+            continue
+        S = x[:, m] @ x[:, m].T
+        dd = np.sqrt(np.maximum(np.diag(S), 1e-300))
+        E = np.abs(sxx1[k, s] - S) / (dd[:, None] * dd[None, :])
+        ex = np.abs(sx1[k, s] - x[:, m].sum(1)) / (np.sqrt(m.sum()) * dd)
+        rows.append((E.max(), ex.max(), k, s, int(m.sum()), np.unravel_index(E.argmax(), E.shape)))
+rows.sort(reverse=True)
+print("worst (err_S, err_x, k, side, N, ij):", rows[:5])
