@@ -123,6 +123,7 @@ struct dpmm_ctx {
   size_t hstage_bytes = 0;
 
   bool hist_valid = false, sorted = false, partitioned = false;
+  int64_t n_fused = 0, n_cached = 0, n_recompute = 0;   // DPMM_VERBOSE counters
   bool stats_cached = false;   // acc / lcount / centers hold the l/r statistics of every cluster for the current labels
   bool cursors_fresh = false;  // lr_cursor still holds the segment bounds (not yet consumed by a partition)
   int64_t launches = 0;

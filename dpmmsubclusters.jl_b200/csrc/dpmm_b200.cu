@@ -261,6 +261,9 @@ extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (env_int("DPMM_VERBOSE", 0))
+    fprintf(stderr, "[dpmm] fused sub-label+statistics launches %lld, statistics served from them %lld, exact recomputations %lld\n",
+            (long long)ctx->n_fused, (long long)ctx->n_cached, (long long)ctx->n_recompute);
   if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
   for (auto& t : ctx->tev) {
     cudaEventDestroy(t.a);
@@ -814,7 +817,7 @@ static int run_sublabels(dpmm_ctx* ctx, bool sample, float* dump) {
     f.x = ctx->x; f.n = ctx->n; f.K = K; f.perm = ctx->perm; f.seg_off = ctx->seg_off; f.w = ctx->ss_w; f.bias = ctx->ss_b;
     f.cen = ctx->ss_c; f.cst = ctx->cst; f.loglr = ctx->loglr; f.sub = ctx->sub; f.acc = ctx->acc; f.rec = recs;
     f.lcount = ctx->lcount; f.centers = ctx->centers; f.u_inj = ctx->u_sub; f.seed = ctx->seed; f.call = ctx->call;
-    f.goff = ctx->goff; f.dump = dump;
+    f.goff = ctx->goff; f.dump = dump; f.dbg = env_int("DPMM_SS_DEBUG", 0);
     const size_t smem = SubStatsSmem(K).total;
     CK(cudaFuncSetAttribute(niw_substats_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
@@ -824,6 +827,7 @@ static int run_sublabels(dpmm_ctx* ctx, bool sample, float* dump) {
     }
     ctx->partitioned = false;
     ctx->stats_cached = true;
+    ++ctx->n_fused;
     return 0;
   }
   if (ctx->prior == DPMM_PRIOR_NIW) {
@@ -978,8 +982,10 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
     // some (tiny or degenerate) run lies far from its cluster's centre relative to its own magnitude:
     // recompute with the FP32/FP64 statistics kernel (on every rank: the counter was all-reduced)
     ctx->stats_cached = false;
+    ++ctx->n_recompute;
     return dpmm_suff_stats(ctx, indices, n_indices, counts, sum_x, sum_xx);
   }
+  if (cached) ++ctx->n_cached;
   for (int a = 0; a < m; ++a)
     for (int s = 0; s < 3; ++s) {
       const double* r = h + ((size_t)a * 3 + s) * rec;
@@ -1056,6 +1062,14 @@ extern "C" int dpmm_debug_tc_stats(dpmm_ctx* ctx, int64_t* out2) {
   CK(cudaMemcpy(h, ctx->tc_stats, 8, cudaMemcpyDeviceToHost));
   out2[0] = h[0];
   out2[1] = h[1];
+  return 0;
+}
+
+extern "C" int dpmm_debug_fused_stats(dpmm_ctx* ctx, int64_t* out3) {
+  NEED(ctx && out3, DPMM_EINVAL, "NULL argument");
+  out3[0] = ctx->n_fused;
+  out3[1] = ctx->n_cached;
+  out3[2] = ctx->n_recompute;
   return 0;
 }
 

@@ -30,8 +30,15 @@ struct NiwPackArgs {
 // The centre every point of cluster k is shifted by before it meets the tensor core: the cluster mean
 // rounded to 12 significant bits, so that x - c is EXACT in Float32 for every point within a few
 // widths of the cluster (the operands share their exponent range and c has 12 trailing zero bits).
-__device__ __forceinline__ float niw_pack_center(float m) {
+// A component is NOT centred (c_i = 0) when one of the two sub-cluster means lies closer to the origin
+// than half the cluster mean: the points of that sub-cluster would then be far from c_i relative to
+// their own magnitude, and the statistics' rounding (relative to sum y_i^2) would not be small against
+// the un-centred sum x_i^2 the result is measured by.  In that case the cluster is at least |c_i|/2
+// wide in this component, so nothing is lost by not centring it.
+__device__ __forceinline__ float niw_pack_center(float m, float ml, float mr) {
   if (!(fabsf(m) < CUDART_INF_F)) return 0.f;
+  const float h = 0.5f * fabsf(m);
+  if (!(ml * m > 0.f && mr * m > 0.f && fabsf(ml) >= h && fabsf(mr) >= h)) return 0.f;
   uint32_t u = __float_as_uint(m);
   u += 0x7FFu + ((u >> 12) & 1u);
   u &= 0xFFFFF000u;
@@ -98,7 +105,7 @@ __global__ void __launch_bounds__(32) niw_pack_kernel(const NiwPackArgs a) {
     const int k = t / 3, side = t % 3 - 1;
     const float* mu0 = a.mu + (size_t)(3 * k) * D;
     if (side < 0) {
-      for (int j = lane; j < D; j += 32) a.ss_c[(size_t)k * D + j] = niw_pack_center(mu0[j]);
+      for (int j = lane; j < D; j += 32) a.ss_c[(size_t)k * D + j] = niw_pack_center(mu0[j], mu0[D + j], mu0[2 * D + j]);
     } else {
       float* W = a.ss_w + ((size_t)k * 2 + side) * D * D;
       for (int i = lane; i < D; i += 32) {
@@ -106,7 +113,7 @@ __global__ void __launch_bounds__(32) niw_pack_kernel(const NiwPackArgs a) {
         for (int j = 0; j < D; ++j) {
           const float u = (j >= i) ? (ok ? (float)Ls[j * LD + i] : nanv) : 0.f;   // U[i][j] = L[j][i]
           W[(size_t)i * D + j] = u;
-          bi += (double)u * ((double)a.mu[(size_t)t * D + j] - (double)niw_pack_center(mu0[j]));
+          bi += (double)u * ((double)a.mu[(size_t)t * D + j] - (double)niw_pack_center(mu0[j], mu0[D + j], mu0[2 * D + j]));
         }
         a.ss_b[((size_t)k * 2 + side) * D + i] = (float)bi;
       }

@@ -366,9 +366,9 @@ __global__ void __launch_bounds__(256) mnm_stats_kernel(const StatsArgs a) {
 // mirrored from its upper triangle, counts from the partition cursors.  When `xc` is given the
 // accumulators hold sums of y = x - c about a centre c of every run (centers [2K][D], see
 // kernels_stats_tc.cuh) and are shifted back here in Float64: sum x = s + N c,  S = sum y y' + c s' + s c' + N c c'.
-// `risk` (optional) counts the diagonal entries whose centred sum exceeds 64 x the un-centred one: the
+// `risk` (optional) counts the diagonal entries whose centred sum exceeds 32 x the un-centred one: the
 // centre was far from the run relative to the run's own magnitude (only tiny or degenerate runs), so the
-// tensor core's ~2^-21 |y_i||y_j| rounding is not small against sqrt(S_ii S_jj); the caller then recomputes
+// tensor core's ~2e-6 |y_i||y_j| accumulation error (round-toward-zero over the k-steps of a flush group) is not small against sqrt(S_ii S_jj); the caller then recomputes
 // the statistics with the FP32/FP64 kernel.
 __global__ void stats_finalize_kernel(const double* __restrict__ acc, const int32_t* __restrict__ seg_off,
                                       const int32_t* __restrict__ lr_cursor, const int32_t* __restrict__ idx_list,
@@ -408,12 +408,12 @@ __global__ void stats_finalize_kernel(const double* __restrict__ acc, const int3
       if (cl != nullptr) {
         const double ci = cl[i], cj = cl[j], l0 = l;
         l += ci * L[1 + j] + L[1 + i] * cj + nl * ci * cj;
-        if (risk != nullptr && i == j && nl > 0 && l0 > 64.0 * l) atomicAdd(risk, 1.0);
+        if (risk != nullptr && i == j && nl > 0 && l0 > 32.0 * l) atomicAdd(risk, 1.0);
       }
       if (cr != nullptr) {
         const double ci = cr[i], cj = cr[j], r0 = r;
         r += ci * R[1 + j] + R[1 + i] * cj + nr * ci * cj;
-        if (risk != nullptr && i == j && nr > 0 && r0 > 64.0 * r) atomicAdd(risk, 1.0);
+        if (risk != nullptr && i == j && nr > 0 && r0 > 32.0 * r) atomicAdd(risk, 1.0);
       }
     }
     double* o = out + (size_t)a * 3 * rec;

@@ -27,17 +27,21 @@
 //   sum y and the left count come from the permuting pass.  Everything is shifted back by c_k in
 //   Float64 by stats_finalize_kernel.
 //
-// Warp roles (448 threads, one CTA per SM; every CTA owns a contiguous range of the tile sequence):
-//   warps 0-3  gather + shift + split          warps 5-8   GEMM1 epilogue: draw, permute, sum y
-//   warp  4    tcgen05.mma issuer              warps 9-12  GEMM2 accumulator drain
-//   warp  13   stages the factors of the next cluster
+// Warp roles (608 threads, one CTA per SM; every CTA owns a contiguous range of the tile sequence):
+//   warps 0-3  gather + shift + split          warps 5-8 / 9-12  GEMM1 epilogue of the even / odd tiles:
+//   warp  4    GEMM1 issuer                                      draw, permute, sum y
+//   warp  17   stages the next cluster's       warps 13-16       GEMM2 accumulator drain
+//              factors                         warp  18          GEMM2 issuer
+// (the epilogue is a long dependent instruction chain per tile -- a single warp per scheduler issues one
+// instruction every ~7 cycles -- so two groups work on alternate tiles.)
 #pragma once
 #include "kernels_stats_tc.cuh"
 
 #define SS_D 32
 #define SS_TILE 128
-#define SS_RAW 3                         // landing ring of raw rows (thread-private slots)
-#define SS_THREADS 448
+#define SS_RAW 5                         // ring of raw tiles: landing -> split -> permuting pass
+#define SS_PF 3                          // tiles of gather in flight
+#define SS_THREADS 608
 #define SS_PANEL 16384                   // one [128][32] Float32 panel
 #define SS_PROWS 136                     // rows of a permuted panel: both runs padded to a multiple of 8
 #define SS_PPANEL (SS_PROWS * 128)
@@ -66,6 +70,7 @@ struct SubStatsArgs {
   uint32_t call;
   int64_t goff;
   float* dump;             // optional [2][n]
+  int dbg;                 // development switches (timing experiments only; results are wrong when set)
 };
 
 struct SubStatsSmem {
@@ -73,20 +78,20 @@ struct SubStatsSmem {
   __host__ __device__ explicit SubStatsSmem(int K) {
     size_t o = 0;
     raw = o;    o += (size_t)SS_RAW * SS_PANEL;
-    split = o;  o += (size_t)2 * 2 * SS_PANEL;       // 2 x (h | l), K-major
+    split = o;  o += (size_t)2 * SS_PANEL;           // h | l, K-major (lives from the split to the end of GEMM1)
     perm = o;   o += (size_t)2 * 2 * SS_PPANEL;      // 2 x (h | l), permuted, MN-major
     wslot = o;  o += (size_t)SS_WSLOT;
     aaug = o;   o += 4096;
     tbuf = o;   o += 64 * SS_TLD * 4;
     tri = o;    o += 528 * 2;
     o = (o + 15) & ~(size_t)15;
-    dest = o;   o += SS_TILE;
-    cnt = o;    o += 4 * 4;
+    dest = o;   o += 2 * SS_TILE;
+    cnt = o;    o += 2 * 4 * 4;
     kcnt = o;   o += 4 * 4;
     bnd = o;    o += (size_t)(K + 1) * 4;
     pre = o;    o += (size_t)(K + 1) * 4;
     o = (o + 15) & ~(size_t)15;
-    bars = o;   o += 24 * 8;
+    bars = o;   o += 32 * 8;
     slot = o;   o += 16;
     total = o;
   }
@@ -108,8 +113,10 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
   int32_t* B = reinterpret_cast<int32_t*>(ss_smem + L.bnd);
   int32_t* P = reinterpret_cast<int32_t*>(ss_smem + L.pre);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ss_smem + L.bars);
-  uint64_t* ready = bars;            // [2] h | l of the tile split (K-major) and visible
-  uint64_t* sfree = bars + 2;        // [2] ... read by GEMM1 and by the permuting pass
+  uint64_t* ready = bars;            // h | l of the tile split (K-major) and visible
+  uint64_t* sfree = bars + 1;        // ... read by GEMM1
+  uint64_t* landed = bars + 18;      // [5] raw tile in shared memory
+  uint64_t* rfree = bars + 23;       // [5] ... consumed by the permuting pass
   uint64_t* d1full = bars + 4;       // [2] GEMM1 accumulator complete
   uint64_t* d1empty = bars + 6;      // [2] ... read by the epilogue
   uint64_t* permd = bars + 8;        // [2] permuted panels written
@@ -138,8 +145,6 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       a.centers[e] = __ldg(a.cen + (size_t)(e >> 6) * SS_D + (e & 31));
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
-      tc::mbar_init(&ready[b], 128);
-      tc::mbar_init(&sfree[b], 128);
       tc::mbar_init(&d1full[b], 1);
       tc::mbar_init(&d1empty[b], 128);
       tc::mbar_init(&permd[b], 128);
@@ -147,6 +152,12 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       tc::mbar_init(&d2full[b], 1);
       tc::mbar_init(&d2empty[b], 128);
     }
+    for (int r = 0; r < SS_RAW; ++r) {
+      tc::mbar_init(&landed[r], 128);
+      tc::mbar_init(&rfree[r], 128);
+    }
+    tc::mbar_init(ready, 128);
+    tc::mbar_init(sfree, 1);
     tc::mbar_init(wfull, 32);
     tc::mbar_init(wempty, 1);
     tc::fence_barrier_init();
@@ -205,11 +216,11 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const bool ok = idx[j] >= 0;
-          cp_async16(dst + j * 2048, a.x + (size_t)(ok ? idx[j] : 0) * SS_D + 4 * c, ok ? 16 : 0);
+          if (!(a.dbg & 16)) cp_async16(dst + j * 2048, a.x + (size_t)(ok ? idx[j] : 0) * SS_D + 4 * c, ok ? 16 : 0);
         }
       };
 #pragma unroll
-      for (int li = 0; li < SS_RAW - 1; ++li) {
+      for (int li = 0; li < SS_PF; ++li) {
         if (li < nt) {
           load_idx();
           issue(li);
@@ -217,79 +228,72 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         }
         cp_async_commit();
       }
-      if (SS_RAW - 1 < nt) load_idx();
+      if (SS_PF < nt) load_idx();
       auto load_center = [&](int key) { return __ldg(reinterpret_cast<const float4*>(a.cen + (size_t)key * SS_D) + c); };
       int ckey = wc.key;
       float4 cen = load_center(ckey);
+      uint8_t* hk = split0 + offk;
       for (int li = 0; li < nt; ++li) {
-        const int b = li & 1;
         if (wc.key != ckey) {
           ckey = wc.key;
           cen = load_center(ckey);
         }
         const int npts = wc.end - wc.pos;   // rows >= npts are zero padding
-        cp_async_wait_group<SS_RAW - 2>();
+        cp_async_wait_group<SS_PF - 1>();
+        tc::mbar_arrive(&landed[li % SS_RAW]);             // this thread's chunks of tile li are in shared memory
         const uint8_t* src = raw0 + (size_t)(li % SS_RAW) * SS_PANEL + offr;
         float4 v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(src + j * 2048);
-        // this thread's slot of tile li - 1 is free again (it alone reads what it gathered): next gather
-        const int ln = li + SS_RAW - 1;
-        if (ln < nt) {
-          issue(ln % SS_RAW);
-          stc_advance(wl, B);
-          if (ln + 1 < nt) load_idx();
-        }
-        cp_async_commit();
-        tc::mbar_wait(&sfree[b], ((li >> 1) & 1) ^ 1);   // GEMM1 and the permuting pass of tile li - 2
-        uint8_t* hk = split0 + (size_t)b * 2 * SS_PANEL + offk;
+        float4 hi[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (r0 + 16 * j < npts) {
             v[j].x -= cen.x; v[j].y -= cen.y; v[j].z -= cen.z; v[j].w -= cen.w;
           }
-          float4 hi, lo;
-          hi.x = tc::to_tf32(v[j].x); hi.y = tc::to_tf32(v[j].y); hi.z = tc::to_tf32(v[j].z); hi.w = tc::to_tf32(v[j].w);
-          lo.x = v[j].x - hi.x; lo.y = v[j].y - hi.y; lo.z = v[j].z - hi.z; lo.w = v[j].w - hi.w;
-          *reinterpret_cast<float4*>(hk + j * 2048) = hi;
-          *reinterpret_cast<float4*>(hk + SS_PANEL + j * 2048) = lo;
+          hi[j].x = tc::to_tf32(v[j].x); hi[j].y = tc::to_tf32(v[j].y); hi[j].z = tc::to_tf32(v[j].z); hi[j].w = tc::to_tf32(v[j].w);
+          v[j].x -= hi[j].x; v[j].y -= hi[j].y; v[j].z -= hi[j].z; v[j].w -= hi[j].w;
+        }
+        tc::mbar_wait(sfree, (li & 1) ^ 1);               // GEMM1 of tile li - 1 has read the panels
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          *reinterpret_cast<float4*>(hk + j * 2048) = hi[j];
+          *reinterpret_cast<float4*>(hk + SS_PANEL + j * 2048) = v[j];
         }
         tc::fence_proxy_async();
-        tc::mbar_arrive(&ready[b]);
+        tc::mbar_arrive(ready);
+        // next gather: tile li + PF goes into the slot of tile li + PF - RAW once its permuting pass is done
+        const int ln = li + SS_PF;
+        if (ln < nt) {
+          tc::mbar_wait(&rfree[ln % SS_RAW], ((ln / SS_RAW) & 1) ^ 1);
+          issue(ln % SS_RAW);
+          stc_advance(wl, B);
+          if (ln + 1 < nt) load_idx();
+        }
+        cp_async_commit();
         stc_advance(wc, B);
       }
     } else if (warp == 4) {
-      // ======================= MMA issuer =======================
-      if (lane == 0) {
+      // ======================= GEMM1 issuer =======================
+      // (one thread; its instruction stream is a serial chain, so everything that does not change from
+      //  tile to tile -- all thirteen descriptor pairs -- is computed once, and GEMM2 has its own issuer)
+      {   // all 32 lanes run the loop (warp-uniform), one elected lane issues: see umma_tf32_*_w
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         StcWalk wm;
         stc_walk_init(wm, B, P, nkeys, t0, t1);
         const uint32_t idesc1 = tc::idesc_tf32(64);
-        const uint32_t idesc2 = tc::idesc_tf32_mn_m64(32);
         const uint64_t aaug_desc = tc::smem_desc_k_noswz(tc::smem_u32(aaug));
-        const uint32_t ws = tc::smem_u32(wslot);
-        const uint64_t whd = tc::smem_desc_k128(ws), wld = tc::smem_desc_k128(ws + 8192);
+        const uint32_t ws = tc::smem_u32(wslot), hs = tc::smem_u32(split0);
         const uint64_t baug_desc = tc::smem_desc_k_noswz(ws + 16384);
-        int kj = -1, prevkey = -1, g2 = 0;
-        bool pv = false, pfirst = false, plast = false;
-        int pli = 0;
-        auto gemm2 = [&]() {
-          const int pms = pli & 1;
-          tc::mbar_wait(&permd[pms], (pli >> 1) & 1);
-          if (pfirst) tc::mbar_wait(&d2empty[g2 & 1], ((g2 >> 1) & 1) ^ 1);
-          tc::tc_fence_after();
-          const int nkl = kcnt[pms * 2], nkr = kcnt[pms * 2 + 1];
-          const uint32_t tmem_l = tmem_base + 128 + (g2 & 1) * 64, tmem_r = tmem_l + 32;
-          // A = [h | l] (two 32-row atoms, one panel apart), B = h: the same descriptor, one k-step = 8 rows = 1024 B
-          const uint64_t pd = tc::smem_desc_mn128(tc::smem_u32(perm0 + (size_t)pms * 2 * SS_PPANEL), SS_PPANEL);
-          for (int ks = 0; ks < nkl; ++ks) tc::umma_tf32(tmem_l, pd + ks * 64, pd + ks * 64, idesc2, (pfirst && ks == 0) ? 0u : 1u);
-          for (int ks = 0; ks < nkr; ++ks)
-            tc::umma_tf32(tmem_r, pd + (nkl + ks) * 64, pd + (nkl + ks) * 64, idesc2, (pfirst && ks == 0) ? 0u : 1u);
-          tc::umma_commit(&pfree[pms]);
-          if (plast) {
-            tc::umma_commit(&d2full[g2 & 1]);
-            ++g2;
-          }
-        };
+        uint64_t hd[4], ld[4], whd[4], wld[4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          hd[ks] = tc::smem_desc_k128(hs) + ks * 2;
+          ld[ks] = tc::smem_desc_k128(hs + SS_PANEL) + ks * 2;
+          whd[ks] = tc::smem_desc_k128(ws) + ks * 2;
+          wld[ks] = tc::smem_desc_k128(ws + 8192) + ks * 2;
+        }
+        int kj = -1, prevkey = -1;
         for (int li = 0; li < nt; ++li) {
           const int b = li & 1;
           if (wm.key != prevkey) {
@@ -297,37 +301,72 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
             ++kj;
             tc::mbar_wait(wfull, kj & 1);
           }
-          tc::mbar_wait(&ready[b], (li >> 1) & 1);
+          tc::mbar_wait(ready, li & 1);
           tc::mbar_wait(&d1empty[b], ((li >> 1) & 1) ^ 1);
           tc::tc_fence_after();
-          const uint32_t hs = tc::smem_u32(split0 + (size_t)b * 2 * SS_PANEL);
-          const uint64_t hd = tc::smem_desc_k128(hs), ld = tc::smem_desc_k128(hs + SS_PANEL);
-          const uint32_t tmem_d = tmem_base + b * 64;
+          const uint32_t tmem_d = tmem_u + b * 64;
+          if (!(a.dbg & 8)) {
+          tc::umma_tf32_first_w(tmem_d, hd[0], whd[0], idesc1);
 #pragma unroll
-          for (int ks = 0; ks < SS_D / 8; ++ks) tc::umma_tf32(tmem_d, hd + ks * 2, whd + ks * 2, idesc1, ks > 0 ? 1u : 0u);
+          for (int ks = 1; ks < 4; ++ks) tc::umma_tf32_acc_w(tmem_d, hd[ks], whd[ks], idesc1);
 #pragma unroll
-          for (int ks = 0; ks < SS_D / 8; ++ks) tc::umma_tf32(tmem_d, ld + ks * 2, whd + ks * 2, idesc1, 1u);
+          for (int ks = 0; ks < 4; ++ks) tc::umma_tf32_acc_w(tmem_d, ld[ks], whd[ks], idesc1);
 #pragma unroll
-          for (int ks = 0; ks < SS_D / 8; ++ks) tc::umma_tf32(tmem_d, hd + ks * 2, wld + ks * 2, idesc1, 1u);
-          tc::umma_tf32(tmem_d, aaug_desc, baug_desc, idesc1, 1u);   // Y -= b
-          tc::umma_commit(&d1full[b]);
-          if (wm.pos + SS_TILE >= wm.end) tc::umma_commit(wempty);   // last tile of the cluster
-          if (pv) gemm2();
-          pv = true;
-          pli = li;
-          pfirst = wm.gcount == 0;
-          plast = stc_is_last(wm);
+          for (int ks = 0; ks < 4; ++ks) tc::umma_tf32_acc_w(tmem_d, hd[ks], wld[ks], idesc1);
+          tc::umma_tf32_acc_w(tmem_d, aaug_desc, baug_desc, idesc1);   // Y -= b
+          }
+          tc::umma_commit_w(sfree);
+          tc::umma_commit_w(&d1full[b]);
+          if (wm.pos + SS_TILE >= wm.end) tc::umma_commit_w(wempty);   // last tile of the cluster
           stc_advance(wm, B);
         }
-        if (pv) gemm2();
       }
-    } else if (warp < 9) {
+    } else if (warp == 18) {
+      // ======================= GEMM2 issuer =======================
+      {
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        StcWalk wm;
+        stc_walk_init(wm, B, P, nkeys, t0, t1);
+        const uint32_t idesc2 = tc::idesc_tf32_mn_m64(32);
+        // A = [h | l] (two 32-row atoms, one panel apart), B = h: the same descriptor, one k-step = 8 rows = 1024 B
+        const uint64_t pd0 = tc::smem_desc_mn128(tc::smem_u32(perm0), SS_PPANEL);
+        const uint64_t pd1 = tc::smem_desc_mn128(tc::smem_u32(perm0 + 2 * SS_PPANEL), SS_PPANEL);
+        int g2 = 0;
+        for (int li = 0; li < nt; ++li) {
+          const int b = li & 1;
+          const bool first = wm.gcount == 0, last = stc_is_last(wm);
+          tc::mbar_wait(&permd[b], (li >> 1) & 1);
+          if (first) tc::mbar_wait(&d2empty[g2 & 1], ((g2 >> 1) & 1) ^ 1);
+          tc::tc_fence_after();
+          const int nkl = __shfl_sync(0xffffffffu, kcnt[b * 2], 0), ntotk = nkl + __shfl_sync(0xffffffffu, kcnt[b * 2 + 1], 0);
+          const uint32_t tmem_l = tmem_u + 128 + (g2 & 1) * 64;
+          uint64_t pd = b ? pd1 : pd0;
+          for (int ks = 0; ks < ((a.dbg & 4) ? 0 : ntotk); ++ks, pd += 64) {
+            const bool right = ks >= nkl;
+            const uint32_t tm = tmem_l + (right ? 32u : 0u);
+            if (first && (ks == 0 || ks == nkl)) tc::umma_tf32_first_w(tm, pd, pd, idesc2);
+            else tc::umma_tf32_acc_w(tm, pd, pd, idesc2);
+          }
+          tc::umma_commit_w(&pfree[b]);
+          if (last) {
+            tc::umma_commit_w(&d2full[g2 & 1]);
+            ++g2;
+          }
+          stc_advance(wm, B);
+        }
+      }
+    } else if (warp < 13) {
       // ======================= GEMM1 epilogue: draw, permute, sum y =======================
+      const int g = (warp - 5) >> 2;                  // group g owns the tiles li = g (mod 2): buffers [g]
       const int sub = warp & 3;                       // TMEM sub-partition of this warp
       const int row = (sub << 5) | lane;              // TMEM lane == row of the tile
-      const int gt = tid - 160;                       // 0..127
+      const int gt = (tid - 160) & 127;               // 0..127 within the group
+      uint8_t* const dest_g = dest_s + g * SS_TILE;
+      volatile int32_t* const cnt_g = cnt_s + g * 4;
+      int nacc = 0;
       const int c = gt & 7, r0 = gt >> 3;
-      const uint32_t offk = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));
+      const uint32_t offr = (uint32_t)(r0 * 128 + c * 16);
+      float4 cen = make_float4(0.f, 0.f, 0.f, 0.f);
       const uint32_t lt_mask = (1u << lane) - 1u;
       StcWalk we;
       stc_walk_init(we, B, P, nkeys, t0, t1);
@@ -335,7 +374,11 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       int ckey = -1;
       float cl = 0.f, cr = 0.f, lwl = 0.f, lwr = 0.f;
       for (int li = 0; li < nt; ++li) {
-        const int b = li & 1;
+        if ((li & 1) != g) {
+          stc_advance(we, B);
+          continue;
+        }
+        const int b = g;
         const int key = we.key;
         const int npts = min(SS_TILE, we.end - we.pos);
         const bool valid = row < npts;
@@ -345,9 +388,10 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           ckey = key;
           cl = __ldg(a.cst + 3 * key + 1); cr = __ldg(a.cst + 3 * key + 2);
           lwl = __ldg(a.loglr + 2 * key); lwr = __ldg(a.loglr + 2 * key + 1);
+          cen = __ldg(reinterpret_cast<const float4*>(a.cen + (size_t)key * SS_D) + c);
         }
         double u = 0.0;
-        if (valid) u = dpmm_uniform(a.u_inj, idx, a.seed, DPMM_STREAM_SUBLABEL, a.call, (uint64_t)(a.goff + idx));
+        if (valid && !(a.dbg & 1)) u = dpmm_uniform(a.u_inj, idx, a.seed, DPMM_STREAM_SUBLABEL, a.call, (uint64_t)(a.goff + idx));
         tc::mbar_wait(&d1full[b], (li >> 1) & 1);
         tc::tc_fence_after();
         uint32_t v0[32], v1[32];
@@ -365,17 +409,17 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
             a.dump[idx] = rl;
             a.dump[a.n + idx] = rr;
           }
-          side = dpmm_draw_two(rl, rr, u);
+          side = (a.dbg & 1) ? (row & 1) : dpmm_draw_two(rl, rr, u);
           a.sub[idx] = (uint8_t)side;
         }
         // ---- destination row of every point: left run first, right run from a multiple of 8 ----
         const uint32_t bl = __ballot_sync(0xffffffffu, side == 0), br = __ballot_sync(0xffffffffu, side == 1);
-        if (lane == 0) cnt_s[sub] = __popc(bl) | (__popc(br) << 8);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (lane == 0) cnt_g[sub] = __popc(bl) | (__popc(br) << 8);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         int nl = 0, nr = 0, offl = 0, offr_ = 0;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          const int cw = cnt_s[w];
+          const int cw = cnt_g[w];
           if (w < sub) {
             offl += cw & 255;
             offr_ += cw >> 8;
@@ -384,28 +428,31 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           nr += cw >> 8;
         }
         const int nl8 = max(8, (nl + 7) & ~7), nr8 = max(8, (nr + 7) & ~7);
-        dest_s[row] = side == 0 ? (uint8_t)(offl + __popc(bl & lt_mask))
+        dest_g[row] = side == 0 ? (uint8_t)(offl + __popc(bl & lt_mask))
                                 : (side == 1 ? (uint8_t)(nl8 + offr_ + __popc(br & lt_mask)) : (uint8_t)255);
         if (gt == 0 && nl > 0) atomicAdd(a.lcount + key, nl);
-        tc::mbar_wait(&ready[b], (li >> 1) & 1);          // the gather warps' panel writes
+        tc::mbar_wait(&landed[li % SS_RAW], (li / SS_RAW) & 1);   // the raw tile (gathered by the gather warps)
         tc::mbar_wait(&pfree[b], ((li >> 1) & 1) ^ 1);    // the GEMM2 that read this slot two tiles ago
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         if (gt == 0) {
           kcnt[b * 2] = nl8 >> 3;
           kcnt[b * 2 + 1] = nr8 >> 3;
         }
-        const uint8_t* hp = split0 + (size_t)b * 2 * SS_PANEL + offk;
+        const uint8_t* rp = raw0 + (size_t)(li % SS_RAW) * SS_PANEL + offr;
         uint8_t* pp = perm0 + (size_t)b * 2 * SS_PPANEL;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int d = dest_s[r0 + 16 * j];
-          if (d != 255) {
-            const float4 h4 = *reinterpret_cast<const float4*>(hp + j * 2048);
-            const float4 l4 = *reinterpret_cast<const float4*>(hp + SS_PANEL + j * 2048);
+          const int d = dest_g[r0 + 16 * j];
+          if (d != 255 && !(a.dbg & 2)) {
+            float4 y4 = *reinterpret_cast<const float4*>(rp + j * 2048);   // the split of the gather warps, redone
+            y4.x -= cen.x; y4.y -= cen.y; y4.z -= cen.z; y4.w -= cen.w;
+            float4 h4, l4;
+            h4.x = tc::to_tf32(y4.x); h4.y = tc::to_tf32(y4.y); h4.z = tc::to_tf32(y4.z); h4.w = tc::to_tf32(y4.w);
+            l4.x = y4.x - h4.x; l4.y = y4.y - h4.y; l4.z = y4.z - h4.z; l4.w = y4.w - h4.w;
             uint8_t* q = pp + d * 128 + (((((c >> 1) ^ (d & 3)) << 1) | (c & 1)) << 4);
             *reinterpret_cast<float4*>(q) = h4;
             *reinterpret_cast<float4*>(q + SS_PPANEL) = l4;
-            const float yx = h4.x + l4.x, yy = h4.y + l4.y, yz = h4.z + l4.z, yw = h4.w + l4.w;
+            const float yx = y4.x, yy = y4.y, yz = y4.z, yw = y4.w;
             if (d < nl8) {
               sxl[0] += yx; sxl[1] += yy; sxl[2] += yz; sxl[3] += yw;
             } else {
@@ -426,8 +473,18 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         }
         tc::fence_proxy_async();
         tc::mbar_arrive(&permd[b]);
-        tc::mbar_arrive(&sfree[b]);
-        if (stc_is_last(we)) {   // sum y of the flush group -> Float64 accumulators
+        tc::mbar_arrive(&rfree[li % SS_RAW]);
+        // sum y -> Float64 accumulators when this group's next tile (li + 2) belongs to another cluster,
+        // after 4 own tiles, or at the end of the range
+        bool flush = we.tleft <= 2 || ++nacc == 4;
+        if (!flush) {
+          StcWalk w2 = we;
+          stc_advance(w2, B);
+          stc_advance(w2, B);
+          flush = w2.key != key;
+        }
+        if (flush) {
+          nacc = 0;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             sxl[q] += __shfl_xor_sync(0xffffffffu, sxl[q], 8);
@@ -449,10 +506,10 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         }
         stc_advance(we, B);
       }
-    } else if (warp < 13) {
+    } else if (warp < 17) {
       // ======================= GEMM2 accumulator drain =======================
       const int sub = warp & 3;
-      const int gt = tid - 288;   // 0..127
+      const int gt = tid - 416;   // 0..127
       StcWalk wd;
       stc_walk_init(wd, B, P, nkeys, t0, t1);
       int g2 = 0;
@@ -478,20 +535,20 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
               trow[32 + j] = __uint_as_float(v1[j]);
             }
           }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+          asm volatile("bar.sync 3, 128;" ::: "memory");
           for (int e = gt; e < 2 * 528; e += 128) {
             const int sd = e >= 528 ? 1 : 0;
             const int ij = tri[e - sd * 528], i = ij >> 8, j = ij & 255;
             const int co = 32 * sd;
             const float sv = (T[i * SS_TLD + co + j] + T[(32 + i) * SS_TLD + co + j]) + T[(32 + j) * SS_TLD + co + i];
-            if (sv != 0.f) atomicAdd(a.acc + (size_t)(2 * wd.key + sd) * a.rec + 1 + SS_D + i * SS_D + j, (double)sv);
+            if (sv != 0.f && !(a.dbg & 32)) atomicAdd(a.acc + (size_t)(2 * wd.key + sd) * a.rec + 1 + SS_D + i * SS_D + j, (double)sv);
           }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+          asm volatile("bar.sync 3, 128;" ::: "memory");
         }
         stc_advance(wd, B);
       }
     } else {
-      // ======================= factor staging (warp 13) =======================
+      // ======================= factor staging (warp 17) =======================
       StcWalk wp;
       stc_walk_init(wp, B, P, nkeys, t0, t1);
       int kj = 0, prevkey = -1;

@@ -195,6 +195,12 @@ class GpuSweep:
         self._ck(self.lib.dpmm_debug_tc_stats(self.h, _ptr(out, C.c_int64)))
         return int(out[0]), int(out[1])
 
+    def fused_stats(self):
+        """(fused sub-label+statistics launches, suff_stats calls served from them, exact recomputations)."""
+        out = np.zeros(3, np.int64)
+        self._ck(self.lib.dpmm_debug_fused_stats(self.h, _ptr(out, C.c_int64)))
+        return int(out[0]), int(out[1]), int(out[2])
+
     def timing_enable(self, on=True):
         self._ck(self.lib.dpmm_timing_enable(self.h, 1 if on else 0))
 

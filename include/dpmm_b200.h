@@ -147,6 +147,10 @@ int dpmm_debug_loglik(dpmm_ctx* ctx, int32_t which, float* out);
 /* Tensor-core label path diagnostics (set DPMM_TC_STATS=1): out[0] = points drawn, out[1] = exact
  * (FP32-refined) cluster evaluations of the last dpmm_sample_labels; both 0 when the FMA path ran. */
 int dpmm_debug_tc_stats(dpmm_ctx* ctx, int64_t* out2);
+/* Fused sub-label + statistics path diagnostics (NIW, D = 32): out[0] = launches of the fused kernel by
+ * dpmm_sample_sublabels, out[1] = dpmm_suff_stats calls served from its accumulators, out[2] = calls that
+ * fell back to the separate statistics kernel because a run lay far from its cluster's centre. */
+int dpmm_debug_fused_stats(dpmm_ctx* ctx, int64_t* out3);
 /* Per-kernel device timing (CUDA events around every launch) for roofline reporting. */
 int dpmm_timing_enable(dpmm_ctx* ctx, int32_t on);
 int dpmm_timing_kinds(void);

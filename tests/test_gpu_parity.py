@@ -71,6 +71,61 @@ def test_niw_tensor_core_refine_path_with_overlapping_clusters(pkg, spread, K, n
         assert ncand > npts          # the refine path really was exercised
 
 
+@pytest.mark.parametrize("spread,K,n", [(2.5, 20, 30000), (10.0, 20, 100000), (10.0, 3, 40000)])
+def test_niw_fused_sublabel_statistics_kernel(pkg, spread, K, n):
+    """D=32: dpmm_sample_sublabels runs niw_substats_tc_kernel (sub-label draw + left/right statistics in one
+    pass on tcgen05) and dpmm_suff_stats is served from its accumulators.  Full parity against the oracle at
+    cluster means far from the origin (|x| ~ 50: the centre shift has to be exact), the fused path must
+    really have run, and it must agree with the separate FP32 sub-label / statistics kernels."""
+    case = make_niw_case(32, K, n, seed=int(spread) + K, spread=spread)
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=7)
+    o = O.OracleSweep(case["x"], O.NIW, seed=7)
+    rep = compare_sweeps(g, o, case, np.random.default_rng(K))
+    fused, served, redone = g.fused_stats()
+    g.close()
+    assert fused >= 1 and served >= 1, "the fused sub-label + statistics kernel did not run"
+    print(f"spread={spread} K={K} n={n}: {rep}; fused launches {fused}, served {served}, recomputed {redone}")
+    rng = np.random.default_rng(3)
+    u_label, u_sub = rng.random(n), rng.random(n)
+    res = []
+    for mode in ("1", "0"):
+        os.environ["DPMM_SUBSTATS_TC"] = mode
+        try:
+            g = pkg.GpuSweep(case["x"], pkg.NIW, seed=7)
+            g.set_uniforms(u_label, u_sub, np.zeros(n, np.uint8))
+            set_params(g, case)
+            g.sample_labels(False)
+            ll = g.debug_loglik(1)
+            g.sample_sublabels()
+            res.append((ll, g.get_sublabels(), g.suff_stats(), g.fused_stats()))
+            g.close()
+        finally:
+            os.environ.pop("DPMM_SUBSTATS_TC")
+    (ll1, s1, st1, f1), (ll0, s0, st0, f0) = res
+    assert f1[0] >= 1 and f0[0] == 0
+    check_loglik(ll1, ll0, "fused vs FP32 sub-label log-likelihood")
+    check_draws(ll0.astype(np.float32), u_sub, s1, s0, "fused vs FP32 sub-labels")
+    if np.array_equal(s1, s0):
+        check_stats(st1, st0, O.NIW, "fused vs separate statistics")
+
+
+def test_niw_fused_statistics_fall_back_when_a_run_is_far_from_its_centre(pkg):
+    """The fused kernel accumulates sums about the cluster's centre c.  When the points of a run are much
+    closer to the origin than to c in some component (here: x_0 ~ 0.01 while every mean says 30), the
+    centred sums cannot resolve the un-centred sum x_0^2; the finalise kernel counts such entries and
+    dpmm_suff_stats recomputes with the FP32/FP64 statistics kernel.  Parity must hold either way."""
+    K, n = 4, 6000
+    case = make_niw_case(32, K, n, seed=5)
+    case["x"][0, :] = (0.01 * np.random.default_rng(1).standard_normal(n)).astype(np.float32)
+    case["mu"][:, :, 0] = 30.0
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=7)
+    o = O.OracleSweep(case["x"], O.NIW, seed=7)
+    compare_sweeps(g, o, case, np.random.default_rng(2))
+    fused, served, redone = g.fused_stats()
+    g.close()
+    assert fused >= 1 and redone >= 1, (fused, served, redone)
+
+
 @pytest.mark.parametrize("D,K,n", [(2, 6, 5000), (32, 20, 10000), (64, 4, 2000)])
 def test_niw_final_argmax_parity(pkg, D, K, n):
     case = make_niw_case(D, K, n, seed=5)
