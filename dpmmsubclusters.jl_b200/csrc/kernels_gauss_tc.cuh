@@ -379,15 +379,17 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
   if (warp < 2) {
     // =============================== control warp of group g ===============================
     const int g = warp;
-    if (lane == 0) {
+    {   // all 32 lanes run the loop (warp-uniform control flow), one elected lane issues: see umma_tf32_*_w
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int li = 0;
       uint32_t cc = 0;  // chunk counter of this group
       int64_t tile = (int64_t)blockIdx.x + (int64_t)g * gridDim.x;
       const int64_t tstep = 2 * (int64_t)gridDim.x;
-      if (tile < a.ntiles) {  // prologue: first tile of this group
+      if (tile < a.ntiles && lane == 0) {  // prologue: first tile of this group
         tc::mbar_arrive_expect_tx(&full[g * 2], TC_STAGE_BYTES);
         tc::tma_load_2d(stage0 + (size_t)(g * 2) * TC_STAGE_BYTES, &tmap_x, &full[g * 2], 0, (int)(tile * TC_TILE));
       }
+      const uint64_t aaug_desc = tc::smem_desc_k_noswz(tc::smem_u32(aaug));
       for (; tile < a.ntiles; tile += tstep, ++li) {
         const int s = g * 2 + (li & 1);
         tc::mbar_wait(&full[s], (li >> 1) & 1);
@@ -400,21 +402,24 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
           const int ncl = min(TC_NCL, K - c * TC_NCL);
           const uint64_t bdesc = tc::smem_desc_k128(tc::smem_u32(wsm) + c * TC_CHUNK_BYTES);
           const uint32_t idesc = tc::idesc_tf32(ncl * TC_D);
-          const uint32_t tmem_d = tmem_base + g * 256 + b * 128;
+          const uint32_t tmem_d = tmem_u + g * 256 + b * 128;
+          tc::umma_tf32_first_w(tmem_d, adesc, bdesc, idesc);
 #pragma unroll
-          for (int ks = 0; ks < TC_D / 8; ++ks)   // 32-byte k-steps inside the 128-byte swizzled rows
-            tc::umma_tf32(tmem_d, adesc + ks * 2, bdesc + ks * 2, idesc, ks > 0 ? 1u : 0u);
-          tc::umma_tf32(tmem_d, tc::smem_desc_k_noswz(tc::smem_u32(aaug)),
-                        tc::smem_desc_k_noswz(tc::smem_u32(baug) + c * 4096), idesc, 1u);   // Y -= U mu
-          tc::umma_commit(&tfull[g * 2 + b]);
+          for (int ks = 1; ks < TC_D / 8; ++ks)   // 32-byte k-steps inside the 128-byte swizzled rows
+            tc::umma_tf32_acc_w(tmem_d, adesc + ks * 2, bdesc + ks * 2, idesc);
+          tc::umma_tf32_acc_w(tmem_d, aaug_desc, tc::smem_desc_k_noswz(tc::smem_u32(baug) + c * 4096), idesc);   // Y -= U mu
+          tc::umma_commit_w(&tfull[g * 2 + b]);
         }
         // prefetch this group's next tile into its other stage (freed when tile li-1 was finished)
         const int64_t nt = tile + tstep;
         if (nt < a.ntiles) {
           const int ns = g * 2 + ((li + 1) & 1);
           tc::mbar_wait(&empty[ns], (((li + 1) >> 1) & 1) ^ 1);
-          tc::mbar_arrive_expect_tx(&full[ns], TC_STAGE_BYTES);
-          tc::tma_load_2d(stage0 + (size_t)ns * TC_STAGE_BYTES, &tmap_x, &full[ns], 0, (int)(nt * TC_TILE));
+          if (lane == 0) {
+            tc::mbar_arrive_expect_tx(&full[ns], TC_STAGE_BYTES);
+            tc::tma_load_2d(stage0 + (size_t)ns * TC_STAGE_BYTES, &tmap_x, &full[ns], 0, (int)(nt * TC_TILE));
+          }
+          __syncwarp();
         }
       }
     }

@@ -84,6 +84,8 @@ __device__ __forceinline__ float to_tf32(float v) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return __uint_as_float(r);
 }
+// the TF32 bits of v: what the tensor core reads of an FP32 word (it ignores the low 13 mantissa bits)
+__device__ __forceinline__ float trunc_tf32(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 }  // namespace tc
 
 // The tile sequence of a CTA: tiles of <= 128 positions that never straddle a key boundary.

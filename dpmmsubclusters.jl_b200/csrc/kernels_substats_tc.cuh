@@ -27,8 +27,8 @@
 //   sum y and the left count come from the permuting pass.  Everything is shifted back by c_k in
 //   Float64 by stats_finalize_kernel.
 //
-// Warp roles (608 threads, one CTA per SM; every CTA owns a contiguous range of the tile sequence):
-//   warps 0-3  gather + shift + split          warps 5-8 / 9-12  GEMM1 epilogue of the even / odd tiles:
+// Warp roles (736 threads, one CTA per SM; every CTA owns a contiguous range of the tile sequence):
+//   warps 0-3, 19-22  gather + shift + split         warps 5-8 / 9-12  GEMM1 epilogue of the even / odd tiles:
 //   warp  4    GEMM1 issuer                                      draw, permute, sum y
 //   warp  17   stages the next cluster's       warps 13-16       GEMM2 accumulator drain
 //              factors                         warp  18          GEMM2 issuer
@@ -41,7 +41,8 @@
 #define SS_TILE 128
 #define SS_RAW 5                         // ring of raw tiles: landing -> split -> permuting pass
 #define SS_PF 3                          // tiles of gather in flight
-#define SS_THREADS 608
+#define SS_THREADS 736
+#define SS_GATHER 256                    // gather threads: warps 0-3 and 19-22, 4 rows each
 #define SS_PANEL 16384                   // one [128][32] Float32 panel
 #define SS_PROWS 136                     // rows of a permuted panel: both runs padded to a multiple of 8
 #define SS_PPANEL (SS_PROWS * 128)
@@ -78,7 +79,7 @@ struct SubStatsSmem {
   __host__ __device__ explicit SubStatsSmem(int K) {
     size_t o = 0;
     raw = o;    o += (size_t)SS_RAW * SS_PANEL;
-    split = o;  o += (size_t)2 * SS_PANEL;           // h | l, K-major (lives from the split to the end of GEMM1)
+    split = o;  o += (size_t)2 * SS_PANEL;           // 2 x l panel, K-major (lives from the split to the end of GEMM1)
     perm = o;   o += (size_t)2 * 2 * SS_PPANEL;      // 2 x (h | l), permuted, MN-major
     wslot = o;  o += (size_t)SS_WSLOT;
     aaug = o;   o += 4096;
@@ -97,6 +98,25 @@ struct SubStatsSmem {
   }
 };
 
+__device__ __forceinline__ void ss_wait(int dbg, uint64_t* bar, uint32_t parity) {
+  if (dbg & 64) {   // experiment: spin on test_wait instead of the suspending try_wait
+    uint32_t done = 0;
+    do {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}"
+          : "=r"(done)
+          : "r"(tc::smem_u32(bar)), "r"(parity)
+          : "memory");
+    } while (!done);
+  } else {
+    tc::mbar_wait(bar, parity);
+  }
+}
+
 __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const SubStatsArgs a) {
   extern __shared__ __align__(1024) uint8_t ss_smem[];
   const SubStatsSmem L(a.K);
@@ -113,8 +133,8 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
   int32_t* B = reinterpret_cast<int32_t*>(ss_smem + L.bnd);
   int32_t* P = reinterpret_cast<int32_t*>(ss_smem + L.pre);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ss_smem + L.bars);
-  uint64_t* ready = bars;            // h | l of the tile split (K-major) and visible
-  uint64_t* sfree = bars + 1;        // ... read by GEMM1
+  uint64_t* ready = bars;            // [2] z (in its raw slot) and l of the tile written and visible
+  uint64_t* sfree = bars + 2;        // [2] l panel read by GEMM1
   uint64_t* landed = bars + 18;      // [5] raw tile in shared memory
   uint64_t* rfree = bars + 23;       // [5] ... consumed by the permuting pass
   uint64_t* d1full = bars + 4;       // [2] GEMM1 accumulator complete
@@ -153,11 +173,13 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       tc::mbar_init(&d2empty[b], 128);
     }
     for (int r = 0; r < SS_RAW; ++r) {
-      tc::mbar_init(&landed[r], 128);
+      tc::mbar_init(&landed[r], SS_GATHER);
       tc::mbar_init(&rfree[r], 128);
     }
-    tc::mbar_init(ready, 128);
-    tc::mbar_init(sfree, 1);
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&ready[b], SS_GATHER);
+      tc::mbar_init(&sfree[b], 1);
+    }
     tc::mbar_init(wfull, 32);
     tc::mbar_init(wempty, 1);
     tc::fence_barrier_init();
@@ -195,28 +217,31 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
   const int nt = t1 - t0;
 
   if (nt > 0) {
-    if (warp < 4) {
+    if (warp < 4 || warp >= 19) {
       // ======================= gather + shift + split =======================
-      const int c = tid & 7, r0 = tid >> 3;   // 16-byte chunk, first row; rows r0 + 16 j
-      const uint32_t offr = (uint32_t)(r0 * 128 + c * 16);                  // landing ring: plain rows
-      const uint32_t offk = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));   // K-major panels: 128B swizzle
+      const int gtid = warp < 4 ? tid : tid - 608 + 128;   // 0..255
+      const int c = gtid & 7, r0 = gtid >> 3;   // 16-byte chunk, first row; rows r0 + 32 j
+      // raw ring and l panels: K-major rows of 128 bytes with the 128B swizzle.  The raw slot is centred in
+      // place and IS the h operand of GEMM1: the tensor core reads the TF32 bits of z, i.e. h = trunc(z).
+      const uint32_t offk = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));
+      const uint32_t offr = offk;
       StcWalk wl, wc;
       stc_walk_init(wl, B, P, nkeys, t0, t1);
       wc = wl;
-      int idx[8];
+      int idx[4];
       auto load_idx = [&]() {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int p = wl.pos + r0 + 16 * j;
+        for (int j = 0; j < 4; ++j) {
+          const int p = wl.pos + r0 + 32 * j;
           idx[j] = p < wl.end ? __ldg(a.perm + p) : -1;
         }
       };
       auto issue = [&](int s) {
         uint8_t* dst = raw0 + (size_t)s * SS_PANEL + offr;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           const bool ok = idx[j] >= 0;
-          if (!(a.dbg & 16)) cp_async16(dst + j * 2048, a.x + (size_t)(ok ? idx[j] : 0) * SS_D + 4 * c, ok ? 16 : 0);
+          if (!(a.dbg & 16)) cp_async16(dst + j * 4096, a.x + (size_t)(ok ? idx[j] : 0) * SS_D + 4 * c, ok ? 16 : 0);
         }
       };
 #pragma unroll
@@ -232,40 +257,53 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       auto load_center = [&](int key) { return __ldg(reinterpret_cast<const float4*>(a.cen + (size_t)key * SS_D) + c); };
       int ckey = wc.key;
       float4 cen = load_center(ckey);
-      uint8_t* hk = split0 + offk;
       for (int li = 0; li < nt; ++li) {
+        const int b = li & 1;
         if (wc.key != ckey) {
           ckey = wc.key;
           cen = load_center(ckey);
         }
         const int npts = wc.end - wc.pos;   // rows >= npts are zero padding
         cp_async_wait_group<SS_PF - 1>();
-        tc::mbar_arrive(&landed[li % SS_RAW]);             // this thread's chunks of tile li are in shared memory
-        const uint8_t* src = raw0 + (size_t)(li % SS_RAW) * SS_PANEL + offr;
-        float4 v[8];
+        uint8_t* src = raw0 + (size_t)(li % SS_RAW) * SS_PANEL + offr;
+        float4 v[4];
+        if (a.dbg & 512) {
+          tc::mbar_arrive(&landed[li % SS_RAW]);
+          ss_wait(a.dbg, &sfree[b], ((li >> 1) & 1) ^ 1);
+          tc::fence_proxy_async();
+          tc::mbar_arrive(&ready[b]);
+          const int ln2 = li + SS_PF;
+          if (ln2 < nt) {
+            ss_wait(a.dbg, &rfree[ln2 % SS_RAW], ((ln2 / SS_RAW) & 1) ^ 1);
+            stc_advance(wl, B);
+          }
+          cp_async_commit();
+          stc_advance(wc, B);
+          continue;
+        }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(src + j * 2048);
-        float4 hi[8];
+        for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(src + j * 4096);
+        float4 lo[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (r0 + 16 * j < npts) {
+        for (int j = 0; j < 4; ++j) {
+          if (r0 + 32 * j < npts) {
             v[j].x -= cen.x; v[j].y -= cen.y; v[j].z -= cen.z; v[j].w -= cen.w;
           }
-          hi[j].x = tc::to_tf32(v[j].x); hi[j].y = tc::to_tf32(v[j].y); hi[j].z = tc::to_tf32(v[j].z); hi[j].w = tc::to_tf32(v[j].w);
-          v[j].x -= hi[j].x; v[j].y -= hi[j].y; v[j].z -= hi[j].z; v[j].w -= hi[j].w;
+          *reinterpret_cast<float4*>(src + j * 4096) = v[j];   // z, in place
+          lo[j].x = v[j].x - tc::trunc_tf32(v[j].x); lo[j].y = v[j].y - tc::trunc_tf32(v[j].y);
+          lo[j].z = v[j].z - tc::trunc_tf32(v[j].z); lo[j].w = v[j].w - tc::trunc_tf32(v[j].w);
         }
-        tc::mbar_wait(sfree, (li & 1) ^ 1);               // GEMM1 of tile li - 1 has read the panels
+        tc::mbar_arrive(&landed[li % SS_RAW]);             // this thread's chunks of z are in shared memory
+        ss_wait(a.dbg, &sfree[b], ((li >> 1) & 1) ^ 1);     // GEMM1 of tile li - 2 has read the l panel
+        uint8_t* lk = split0 + (size_t)b * SS_PANEL + offk;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          *reinterpret_cast<float4*>(hk + j * 2048) = hi[j];
-          *reinterpret_cast<float4*>(hk + SS_PANEL + j * 2048) = v[j];
-        }
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(lk + j * 4096) = lo[j];
         tc::fence_proxy_async();
-        tc::mbar_arrive(ready);
+        tc::mbar_arrive(&ready[b]);
         // next gather: tile li + PF goes into the slot of tile li + PF - RAW once its permuting pass is done
         const int ln = li + SS_PF;
         if (ln < nt) {
-          tc::mbar_wait(&rfree[ln % SS_RAW], ((ln / SS_RAW) & 1) ^ 1);
+          ss_wait(a.dbg, &rfree[ln % SS_RAW], ((ln / SS_RAW) & 1) ^ 1);
           issue(ln % SS_RAW);
           stc_advance(wl, B);
           if (ln + 1 < nt) load_idx();
@@ -283,13 +321,12 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         stc_walk_init(wm, B, P, nkeys, t0, t1);
         const uint32_t idesc1 = tc::idesc_tf32(64);
         const uint64_t aaug_desc = tc::smem_desc_k_noswz(tc::smem_u32(aaug));
-        const uint32_t ws = tc::smem_u32(wslot), hs = tc::smem_u32(split0);
+        const uint32_t ws = tc::smem_u32(wslot);
         const uint64_t baug_desc = tc::smem_desc_k_noswz(ws + 16384);
-        uint64_t hd[4], ld[4], whd[4], wld[4];
+        const uint64_t raw_desc = tc::smem_desc_k128(tc::smem_u32(raw0)), l_desc = tc::smem_desc_k128(tc::smem_u32(split0));
+        uint64_t whd[4], wld[4];
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          hd[ks] = tc::smem_desc_k128(hs) + ks * 2;
-          ld[ks] = tc::smem_desc_k128(hs + SS_PANEL) + ks * 2;
           whd[ks] = tc::smem_desc_k128(ws) + ks * 2;
           wld[ks] = tc::smem_desc_k128(ws + 8192) + ks * 2;
         }
@@ -299,11 +336,17 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           if (wm.key != prevkey) {
             prevkey = wm.key;
             ++kj;
-            tc::mbar_wait(wfull, kj & 1);
+            ss_wait(a.dbg, wfull, kj & 1);
           }
-          tc::mbar_wait(ready, li & 1);
-          tc::mbar_wait(&d1empty[b], ((li >> 1) & 1) ^ 1);
+          ss_wait(a.dbg, &ready[b], (li >> 1) & 1);
+          ss_wait(a.dbg, &d1empty[b], ((li >> 1) & 1) ^ 1);
           tc::tc_fence_after();
+          uint64_t hd[4], ld[4];
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            hd[ks] = raw_desc + (uint64_t)((li % SS_RAW) * (SS_PANEL >> 4) + ks * 2);   // z: h = its TF32 bits
+            ld[ks] = l_desc + (uint64_t)(b * (SS_PANEL >> 4) + ks * 2);
+          }
           const uint32_t tmem_d = tmem_u + b * 64;
           if (!(a.dbg & 8)) {
           tc::umma_tf32_first_w(tmem_d, hd[0], whd[0], idesc1);
@@ -315,7 +358,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           for (int ks = 0; ks < 4; ++ks) tc::umma_tf32_acc_w(tmem_d, hd[ks], wld[ks], idesc1);
           tc::umma_tf32_acc_w(tmem_d, aaug_desc, baug_desc, idesc1);   // Y -= b
           }
-          tc::umma_commit_w(sfree);
+          tc::umma_commit_w(&sfree[b]);
           tc::umma_commit_w(&d1full[b]);
           if (wm.pos + SS_TILE >= wm.end) tc::umma_commit_w(wempty);   // last tile of the cluster
           stc_advance(wm, B);
@@ -335,8 +378,8 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         for (int li = 0; li < nt; ++li) {
           const int b = li & 1;
           const bool first = wm.gcount == 0, last = stc_is_last(wm);
-          tc::mbar_wait(&permd[b], (li >> 1) & 1);
-          if (first) tc::mbar_wait(&d2empty[g2 & 1], ((g2 >> 1) & 1) ^ 1);
+          ss_wait(a.dbg, &permd[b], (li >> 1) & 1);
+          if (first) ss_wait(a.dbg, &d2empty[g2 & 1], ((g2 >> 1) & 1) ^ 1);
           tc::tc_fence_after();
           const int nkl = __shfl_sync(0xffffffffu, kcnt[b * 2], 0), ntotk = nkl + __shfl_sync(0xffffffffu, kcnt[b * 2 + 1], 0);
           const uint32_t tmem_l = tmem_u + 128 + (g2 & 1) * 64;
@@ -365,8 +408,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       volatile int32_t* const cnt_g = cnt_s + g * 4;
       int nacc = 0;
       const int c = gt & 7, r0 = gt >> 3;
-      const uint32_t offr = (uint32_t)(r0 * 128 + c * 16);
-      float4 cen = make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint32_t offr = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));   // the gather warps' swizzled rows
       const uint32_t lt_mask = (1u << lane) - 1u;
       StcWalk we;
       stc_walk_init(we, B, P, nkeys, t0, t1);
@@ -388,20 +430,23 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           ckey = key;
           cl = __ldg(a.cst + 3 * key + 1); cr = __ldg(a.cst + 3 * key + 2);
           lwl = __ldg(a.loglr + 2 * key); lwr = __ldg(a.loglr + 2 * key + 1);
-          cen = __ldg(reinterpret_cast<const float4*>(a.cen + (size_t)key * SS_D) + c);
+
         }
         double u = 0.0;
         if (valid && !(a.dbg & 1)) u = dpmm_uniform(a.u_inj, idx, a.seed, DPMM_STREAM_SUBLABEL, a.call, (uint64_t)(a.goff + idx));
-        tc::mbar_wait(&d1full[b], (li >> 1) & 1);
+        ss_wait(a.dbg, &d1full[b], (li >> 1) & 1);
         tc::tc_fence_after();
         uint32_t v0[32], v1[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + b * 64;
+        float ql = 1.f, qr = 2.f;
+        if (!(a.dbg & 128)) {
         tc::tmem_ld32(taddr, v0);
         tc::tmem_ld32(taddr + 32, v1);
         tc::tmem_ld_wait();
+        ql = gauss_tc_screen_q(v0), qr = gauss_tc_screen_q(v1);
+        }
         tc::tc_fence_before();
         tc::mbar_arrive(&d1empty[b]);
-        const float ql = gauss_tc_screen_q(v0), qr = gauss_tc_screen_q(v1);
         int side = 2;
         if (valid) {
           const float rl = gauss_finish(cl, ql, lwl), rr = gauss_finish(cr, qr, lwr);
@@ -411,6 +456,16 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           }
           side = (a.dbg & 1) ? (row & 1) : dpmm_draw_two(rl, rr, u);
           a.sub[idx] = (uint8_t)side;
+        }
+        if (a.dbg & 1024) {
+          ss_wait(a.dbg, &landed[li % SS_RAW], (li / SS_RAW) & 1);
+          ss_wait(a.dbg, &pfree[b], ((li >> 1) & 1) ^ 1);
+          if (gt == 0) { kcnt[b * 2] = 8; kcnt[b * 2 + 1] = 8; }
+          tc::fence_proxy_async();
+          tc::mbar_arrive(&permd[b]);
+          tc::mbar_arrive(&rfree[li % SS_RAW]);
+          stc_advance(we, B);
+          continue;
         }
         // ---- destination row of every point: left run first, right run from a multiple of 8 ----
         const uint32_t bl = __ballot_sync(0xffffffffu, side == 0), br = __ballot_sync(0xffffffffu, side == 1);
@@ -431,8 +486,8 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         dest_g[row] = side == 0 ? (uint8_t)(offl + __popc(bl & lt_mask))
                                 : (side == 1 ? (uint8_t)(nl8 + offr_ + __popc(br & lt_mask)) : (uint8_t)255);
         if (gt == 0 && nl > 0) atomicAdd(a.lcount + key, nl);
-        tc::mbar_wait(&landed[li % SS_RAW], (li / SS_RAW) & 1);   // the raw tile (gathered by the gather warps)
-        tc::mbar_wait(&pfree[b], ((li >> 1) & 1) ^ 1);    // the GEMM2 that read this slot two tiles ago
+        ss_wait(a.dbg, &landed[li % SS_RAW], (li / SS_RAW) & 1);   // z of the tile (gathered and centred by the gather warps)
+        ss_wait(a.dbg, &pfree[b], ((li >> 1) & 1) ^ 1);    // the GEMM2 that read this slot two tiles ago
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         if (gt == 0) {
           kcnt[b * 2] = nl8 >> 3;
@@ -444,8 +499,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         for (int j = 0; j < 8; ++j) {
           const int d = dest_g[r0 + 16 * j];
           if (d != 255 && !(a.dbg & 2)) {
-            float4 y4 = *reinterpret_cast<const float4*>(rp + j * 2048);   // the split of the gather warps, redone
-            y4.x -= cen.x; y4.y -= cen.y; y4.z -= cen.z; y4.w -= cen.w;
+            const float4 y4 = *reinterpret_cast<const float4*>(rp + j * 2048);   // z = x - c (centred in place)
             float4 h4, l4;
             h4.x = tc::to_tf32(y4.x); h4.y = tc::to_tf32(y4.y); h4.z = tc::to_tf32(y4.z); h4.w = tc::to_tf32(y4.w);
             l4.x = y4.x - h4.x; l4.y = y4.y - h4.y; l4.z = y4.z - h4.z; l4.w = y4.w - h4.w;
@@ -516,16 +570,19 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       for (int li = 0; li < nt; ++li) {
         if (stc_is_last(wd)) {
           const int buf = g2 & 1;
-          tc::mbar_wait(&d2full[buf], (g2 >> 1) & 1);
+          ss_wait(a.dbg, &d2full[buf], (g2 >> 1) & 1);
           ++g2;
           tc::tc_fence_after();
           uint32_t v0[32], v1[32];
           const uint32_t taddr = tmem_base + 128 + buf * 64 + ((uint32_t)(sub * 32) << 16);
+          if (!(a.dbg & 256)) {
           tc::tmem_ld32(taddr, v0);
           tc::tmem_ld32(taddr + 32, v1);
           tc::tmem_ld_wait();
+          }
           tc::tc_fence_before();
           tc::mbar_arrive(&d2empty[buf]);
+          if (a.dbg & 256) { stc_advance(wd, B); continue; }
           // M = 64: accumulator row m lives in lane (m % 16) of sub-partition m / 16
           if (lane < 16) {
             float* trow = T + (16 * sub + lane) * SS_TLD;
@@ -558,7 +615,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       for (int li = 0; li < nt; ++li) {
         if (wp.key != prevkey) {
           prevkey = wp.key;
-          tc::mbar_wait(wempty, (kj & 1) ^ 1);   // every GEMM1 of the previous cluster has retired
+          ss_wait(a.dbg, wempty, (kj & 1) ^ 1);   // every GEMM1 of the previous cluster has retired
           const float4* src = reinterpret_cast<const float4*>(a.w + (size_t)wp.key * 2 * SS_D * SS_D);
           for (int e = lane; e < 512; e += 32) {
             const int r = e >> 3, cc = e & 7;   // row (side, i), 16-byte chunk
