@@ -109,6 +109,24 @@ def test_niw_fused_sublabel_statistics_kernel(pkg, spread, K, n):
         check_stats(st1, st0, O.NIW, "fused vs separate statistics")
 
 
+@pytest.mark.parametrize("K,n,empty", [(3, 1, None), (5, 129, None), (4, 4000, 2), (2, 257, 0), (40, 900, None)])
+def test_niw_fused_kernel_edge_shapes(pkg, K, n, empty):
+    """Ragged and degenerate tile sequences of the fused D=32 kernel: a single point, one row past a tile,
+    an empty cluster in the middle / at the front of the label-sorted order, more clusters than tiles."""
+    case = make_niw_case(32, K, n, seed=K * 7 + n)
+    if empty is not None:
+        w = case["weights"].astype(np.float64)
+        w[empty] = 1e-30                      # nobody draws this label: its segment is empty
+        case["weights"] = (w / w.sum()).astype(np.float32)
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=11)
+    o = O.OracleSweep(case["x"], O.NIW, seed=11)
+    rep = compare_sweeps(g, o, case, np.random.default_rng(n))
+    fused, served, redone = g.fused_stats()
+    g.close()
+    assert fused >= 1 or n < 128          # contexts with fewer points than one tile stay on the FP32 kernels
+    print(f"K={K} n={n} empty={empty}: {rep}; fused {fused}, served {served}, recomputed {redone}")
+
+
 def test_niw_fused_statistics_fall_back_when_a_run_is_far_from_its_centre(pkg):
     """The fused kernel accumulates sums about the cluster's centre c.  When the points of a run are much
     closer to the origin than to c in some component (here: x_0 ~ 0.01 while every mean says 30), the
