@@ -613,7 +613,7 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
     pa.tc_w = tcp ? ctx->tc_w : nullptr; pa.tc_b = ctx->tc_b; pa.tc_mu = ctx->tc_mu; pa.tc_fro = ctx->tc_fro;
     pa.ss_w = ctx->tc_ok ? ctx->ss_w : nullptr; pa.ss_b = ctx->ss_b; pa.ss_c = ctx->ss_c;
     KernelTimer kt(ctx, TK_RELABEL);
-    niw_pack_kernel<<<(unsigned)nrec, 32, (size_t)D * (D + 1) * sizeof(double), ctx->stream>>>(pa);
+    niw_pack_kernel<<<(unsigned)nrec, NIW_PACK_THREADS, (size_t)D * (D + 1) * sizeof(double), ctx->stream>>>(pa);
     CK(cudaGetLastError());
   }
   ctx->tc_params = tcp;
@@ -896,17 +896,15 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
   const bool all = (indices == nullptr);
   rc = ensure_stage(ctx, std::max<size_t>((size_t)m * 4 + K, ((size_t)m * 3 * rec + 1) * 8));
   if (rc) return rc;
-  CK(cudaStreamSynchronize(ctx->stream));
-  {
+  if (!all) {   // "all" needs no index list (the finalise kernel then uses k = a) and hence no host round trip here
+    CK(cudaStreamSynchronize(ctx->stream));   // staging buffer reuse
     int32_t* h_idx = (int32_t*)ctx->hstage;
     uint8_t* h_w = (uint8_t*)(h_idx + m);
     memcpy(h_idx, idx.data(), (size_t)m * 4);
     CK(cudaMemcpyAsync(ctx->idx_list, h_idx, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (!all) {
-      memset(h_w, 0, K);
-      for (int v : idx) h_w[v] = 1;
-      CK(cudaMemcpyAsync(ctx->wanted, h_w, K, cudaMemcpyHostToDevice, ctx->stream));
-    }
+    memset(h_w, 0, K);
+    for (int v : idx) h_w[v] = 1;
+    CK(cudaMemcpyAsync(ctx->wanted, h_w, K, cudaMemcpyHostToDevice, ctx->stream));
   }
   // K5 on tcgen05: all clusters of a D = 32 NIW model (no work list: CTAs own ranges of the tile sequence)
   const bool stats_tc = !cached && ctx->prior == DPMM_PRIOR_NIW && D == STC_D && all && ctx->tc_ok &&
@@ -960,7 +958,7 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
     const int T = 256;
     dim3 grid((unsigned)std::min((rec + T - 1) / T, 64), (unsigned)m);
     if (cached) CK(cudaMemsetAsync(ctx->outbuf + (size_t)m * 3 * rec, 0, 8, ctx->stream));
-    stats_finalize_kernel<<<grid, T, 0, ctx->stream>>>(ctx->acc, ctx->seg_off, ctx->lr_cursor, ctx->idx_list, m, D, rec,
+    stats_finalize_kernel<<<grid, T, 0, ctx->stream>>>(ctx->acc, ctx->seg_off, ctx->lr_cursor, all ? nullptr : ctx->idx_list, m, D, rec,
                                                        ctx->prior == DPMM_PRIOR_NIW ? 1 : 0, ctx->outbuf,
                                                        (stats_tc || cached) ? ctx->centers : nullptr,
                                                        cached ? ctx->lcount : nullptr,

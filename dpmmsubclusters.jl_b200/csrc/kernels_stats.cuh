@@ -376,7 +376,7 @@ __global__ void stats_finalize_kernel(const double* __restrict__ acc, const int3
                                       const int32_t* __restrict__ lcount, double* risk) {
   const int a = blockIdx.y;
   if (a >= m) return;
-  const int k = idx_list[a];
+  const int k = idx_list != nullptr ? idx_list[a] : a;   // no list: every cluster in order
   const double* L = acc + (size_t)(2 * k) * rec;
   const double* R = acc + (size_t)(2 * k + 1) * rec;
   // left count: from the partition cursors, or as counted by the fused sub-label + statistics kernel
