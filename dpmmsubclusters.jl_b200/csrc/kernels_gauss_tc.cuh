@@ -210,6 +210,7 @@ struct GaussTcArgs {
   int final_iter;
   int64_t ntiles;
   int32_t* stats;      // optional [2]: #points, #candidate evaluations (diagnostics)
+  int dbg;             // development switches (timing experiments only; results are wrong when set)
 };
 
 // shared-memory carve-up (bytes), shared by host and device
@@ -453,11 +454,18 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
           for (int kl = 0; kl < TC_NCL; kl += 2) {
             if (kl < ncl) {
               uint32_t v0[32], v1[32];
+              if (!(a.dbg & 1)) {
               tc::tmem_ld32(taddr + kl * TC_D, v0);
               if (kl + 1 < ncl) tc::tmem_ld32(taddr + (kl + 1) * TC_D, v1);
               tc::tmem_ld_wait();
+              }
+              if (a.dbg & 3) {   // timing experiments only
+                qt[c * TC_NCL + kl] = (c * TC_NCL + kl) * 1000.f + ((a.dbg & 1) ? 0.f : __uint_as_float(v0[0] & 1u));
+                if (kl + 1 < ncl) qt[c * TC_NCL + kl + 1] = (c * TC_NCL + kl + 1) * 1000.f + ((a.dbg & 1) ? 0.f : __uint_as_float(v1[0] & 1u));
+              } else {
               qt[c * TC_NCL + kl] = gauss_tc_screen_q(v0);
               if (kl + 1 < ncl) qt[c * TC_NCL + kl + 1] = gauss_tc_screen_q(v1);
+              }
             }
           }
           tc::tc_fence_before();

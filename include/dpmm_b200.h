@@ -104,7 +104,9 @@ int dpmm_set_sampler(dpmm_ctx* ctx, int32_t sampler);
  * sample_log_cat_array! (utils.jl:19-31).  The N x K matrix is never written to memory. */
 int dpmm_sample_labels(dpmm_ctx* ctx, int32_t final_iter);
 /* sample_sub_clusters! -> sample_sub_clusters_worker! -> create_subclusters_labels! (:64-95):
- * each point, under the l/r distributions of its (fresh) label. */
+ * each point, under the l/r distributions of its (fresh) label.  For NIW models with D = 32 the same
+ * kernel also accumulates the left/right statistics of every cluster; a dpmm_suff_stats call that
+ * follows without a label / sub-label change in between is served from them. */
 int dpmm_sample_sublabels(dpmm_ctx* ctx);
 /* update_suff_stats_posterior! -> create_suff_stats_dict_worker (:149-169, :206-254) with
  * create_sufficient_statistics (niw.jl:42-51, multinomial_prior.jl:27-32) and the worker->leader->
