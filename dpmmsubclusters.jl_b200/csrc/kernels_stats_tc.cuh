@@ -79,6 +79,9 @@ __device__ __forceinline__ uint64_t smem_desc_mn128(uint32_t saddr, uint32_t lbo
 __device__ __forceinline__ uint32_t idesc_tf32_mn_m64(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
 }
+__device__ __forceinline__ uint32_t idesc_tf32_mn_m128(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
 __device__ __forceinline__ float to_tf32(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));

@@ -27,11 +27,11 @@
 //   sum y and the left count come from the permuting pass.  Everything is shifted back by c_k in
 //   Float64 by stats_finalize_kernel.
 //
-// Warp roles (736 threads, one CTA per SM; every CTA owns a contiguous range of the tile sequence):
+// Warp roles (768 threads, one CTA per SM; every CTA owns a contiguous range of the tile sequence):
 //   warps 0-3, 19-22  gather + shift + split         warps 5-8 / 9-12  GEMM1 epilogue of the even / odd tiles:
 //   warp  4    GEMM1 issuer                                      draw, permute, sum y
 //   warp  17   stages the next cluster's       warps 13-16       GEMM2 accumulator drain
-//              factors                         warp  18          GEMM2 issuer
+//              factors                         warps 18, 23      GEMM2 issuers (left / right k-steps)
 // (the epilogue is a long dependent instruction chain per tile -- a single warp per scheduler issues one
 // instruction every ~7 cycles -- so two groups work on alternate tiles.)
 #pragma once
@@ -41,7 +41,7 @@
 #define SS_TILE 128
 #define SS_RAW 5                         // ring of raw tiles: landing -> split -> permuting pass
 #define SS_PF 3                          // tiles of gather in flight
-#define SS_THREADS 736
+#define SS_THREADS 768
 #define SS_GATHER 256                    // gather threads: warps 0-3 and 19-22, 4 rows each
 #define SS_PANEL 16384                   // one [128][32] Float32 panel
 #define SS_PROWS 136                     // rows of a permuted panel: both runs padded to a multiple of 8
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       tc::mbar_init(&d1full[b], 1);
       tc::mbar_init(&d1empty[b], 128);
       tc::mbar_init(&permd[b], 128);
-      tc::mbar_init(&pfree[b], 1);
-      tc::mbar_init(&d2full[b], 1);
+      tc::mbar_init(&pfree[b], 2);      // one commit per GEMM2 issuer
+      tc::mbar_init(&d2full[b], 2);
       tc::mbar_init(&d2empty[b], 128);
     }
     for (int r = 0; r < SS_RAW; ++r) {
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
   const int nt = t1 - t0;
 
   if (nt > 0) {
-    if (warp < 4 || warp >= 19) {
+    if (warp < 4 || (warp >= 19 && warp < 23)) {
       // ======================= gather + shift + split =======================
       const int gtid = warp < 4 ? tid : tid - 608 + 128;   // 0..255
       const int c = gtid & 7, r0 = gtid >> 3;   // 16-byte chunk, first row; rows r0 + 32 j
@@ -364,13 +364,18 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           stc_advance(wm, B);
         }
       }
-    } else if (warp == 18) {
-      // ======================= GEMM2 issuer =======================
+    } else if (warp == 18 || warp == 23) {
+      // ======================= GEMM2 issuers: warp 18 the left k-steps, warp 23 the right ones =======================
+      // (the issue loop costs ~30 instructions per MMA in one dependent chain; each side's accumulator is
+      //  written by exactly one issuer, in order)
       {
+        const int right = warp == 23 ? 1 : 0;
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         StcWalk wm;
         stc_walk_init(wm, B, P, nkeys, t0, t1);
-        const uint32_t idesc2 = tc::idesc_tf32_mn_m64(32);
+        // M = 64.  (Experiment switch 2048: M = 128 with two garbage atoms after the panels, whose products
+        // land in accumulator rows 64-127 that nobody reads -- measured 4 % slower, not faster.)
+        const uint32_t idesc2 = (a.dbg & 2048) ? tc::idesc_tf32_mn_m128(32) : tc::idesc_tf32_mn_m64(32);
         // A = [h | l] (two 32-row atoms, one panel apart), B = h: the same descriptor, one k-step = 8 rows = 1024 B
         const uint64_t pd0 = tc::smem_desc_mn128(tc::smem_u32(perm0), SS_PPANEL);
         const uint64_t pd1 = tc::smem_desc_mn128(tc::smem_u32(perm0 + 2 * SS_PPANEL), SS_PPANEL);
@@ -381,15 +386,17 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           ss_wait(a.dbg, &permd[b], (li >> 1) & 1);
           if (first) ss_wait(a.dbg, &d2empty[g2 & 1], ((g2 >> 1) & 1) ^ 1);
           tc::tc_fence_after();
-          const int nkl = __shfl_sync(0xffffffffu, kcnt[b * 2], 0), ntotk = nkl + __shfl_sync(0xffffffffu, kcnt[b * 2 + 1], 0);
-          const uint32_t tmem_l = tmem_u + 128 + (g2 & 1) * 64;
-          uint64_t pd = b ? pd1 : pd0;
-          for (int ks = 0; ks < ((a.dbg & 4) ? 0 : ntotk); ++ks, pd += 64) {
-            const bool right = ks >= nkl;
-            const uint32_t tm = tmem_l + (right ? 32u : 0u);
-            if (first && (ks == 0 || ks == nkl)) tc::umma_tf32_first_w(tm, pd, pd, idesc2);
-            else tc::umma_tf32_acc_w(tm, pd, pd, idesc2);
+          const int nkl = __shfl_sync(0xffffffffu, kcnt[b * 2], 0), nkr = __shfl_sync(0xffffffffu, kcnt[b * 2 + 1], 0);
+          const int k0 = right ? nkl : 0, nk = (a.dbg & 4) ? 0 : (right ? nkr : nkl);
+          const uint32_t tm = tmem_u + 128 + (g2 & 1) * 64 + right * 32;
+          uint64_t pd = (b ? pd1 : pd0) + (uint64_t)(k0 * 64);
+          int ks = 0;
+          if (first && nk > 0) {
+            tc::umma_tf32_first_w(tm, pd, pd, idesc2);
+            pd += 64;
+            ks = 1;
           }
+          for (; ks < nk; ++ks, pd += 64) tc::umma_tf32_acc_w(tm, pd, pd, idesc2);
           tc::umma_commit_w(&pfree[b]);
           if (last) {
             tc::umma_commit_w(&d2full[g2 & 1]);
@@ -584,8 +591,10 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           tc::mbar_arrive(&d2empty[buf]);
           if (a.dbg & 256) { stc_advance(wd, B); continue; }
           // M = 64: accumulator row m lives in lane (m % 16) of sub-partition m / 16
-          if (lane < 16) {
-            float* trow = T + (16 * sub + lane) * SS_TLD;
+          // (M = 128, experiment switch: row m lives in TMEM lane m, rows 0-63 = sub-partitions 0 and 1)
+          const bool m64 = (a.dbg & 2048) == 0;
+          if (m64 ? lane < 16 : sub < 2) {
+            float* trow = T + (m64 ? 16 * sub + lane : 32 * sub + lane) * SS_TLD;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               trow[j] = __uint_as_float(v0[j]);

@@ -10,7 +10,7 @@ case = make_niw_case(32, 20, n, 1, spread=56)
 g = pkg.GpuSweep(case["x"], case["kind"], seed=1)
 set_params(g, case)
 g.sample_labels()
-for mode in [0, 63, 63+128, 63+256, 63+512, 63+1024, 63+128+1024, 63+128+256+512+1024, 128, 256, 512, 1024+2]:
+for mode in [0, 1, 2, 4, 8, 16, 32, 128, 256, 512, 1024 + 2, 15, 63]:
     os.environ["DPMM_SS_DEBUG"] = str(mode)
     for _ in range(2): g.sample_sublabels()
     g.sync(); g.timing_enable(True)
