@@ -404,11 +404,13 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
           const uint64_t bdesc = tc::smem_desc_k128(tc::smem_u32(wsm) + c * TC_CHUNK_BYTES);
           const uint32_t idesc = tc::idesc_tf32(ncl * TC_D);
           const uint32_t tmem_d = tmem_u + g * 256 + b * 128;
+          if (!(a.dbg & 4)) {
           tc::umma_tf32_first_w(tmem_d, adesc, bdesc, idesc);
 #pragma unroll
           for (int ks = 1; ks < TC_D / 8; ++ks)   // 32-byte k-steps inside the 128-byte swizzled rows
             tc::umma_tf32_acc_w(tmem_d, adesc + ks * 2, bdesc + ks * 2, idesc);
           tc::umma_tf32_acc_w(tmem_d, aaug_desc, tc::smem_desc_k_noswz(tc::smem_u32(baug) + c * 4096), idesc);   // Y -= U mu
+          }
           tc::umma_commit_w(&tfull[g * 2 + b]);
         }
         // prefetch this group's next tile into its other stage (freed when tile li-1 was finished)
