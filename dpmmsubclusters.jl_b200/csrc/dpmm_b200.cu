@@ -705,7 +705,6 @@ static int run_sample_labels(dpmm_ctx* ctx, int final_iter, float* dump) {
     a.fro = ctx->tc_fro; a.labels = ctx->labels; a.hist = ctx->hist; a.u_inj = ctx->u_label; a.seed = ctx->seed;
     a.call = ctx->call; a.goff = ctx->goff; a.final_iter = final_iter; a.ntiles = (ctx->n + TC_TILE - 1) / TC_TILE;
     a.stats = env_int("DPMM_TC_STATS", 0) ? ctx->tc_stats : nullptr;
-    a.dbg = env_int("DPMM_TC_DEBUG", 0);
     const size_t sm = GaussTcSmem(K).total;
     NEED(sm <= (size_t)ctx->smem_optin, DPMM_ELIMIT, "internal: tensor-core label kernel does not fit shared memory");
     CK(cudaFuncSetAttribute(gauss_label_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

@@ -210,7 +210,6 @@ struct GaussTcArgs {
   int final_iter;
   int64_t ntiles;
   int32_t* stats;      // optional [2]: #points, #candidate evaluations (diagnostics)
-  int dbg;             // development switches (timing experiments only; results are wrong when set)
 };
 
 // shared-memory carve-up (bytes), shared by host and device
@@ -404,13 +403,11 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
           const uint64_t bdesc = tc::smem_desc_k128(tc::smem_u32(wsm) + c * TC_CHUNK_BYTES);
           const uint32_t idesc = tc::idesc_tf32(ncl * TC_D);
           const uint32_t tmem_d = tmem_u + g * 256 + b * 128;
-          if (!(a.dbg & 4)) {
           tc::umma_tf32_first_w(tmem_d, adesc, bdesc, idesc);
 #pragma unroll
           for (int ks = 1; ks < TC_D / 8; ++ks)   // 32-byte k-steps inside the 128-byte swizzled rows
             tc::umma_tf32_acc_w(tmem_d, adesc + ks * 2, bdesc + ks * 2, idesc);
           tc::umma_tf32_acc_w(tmem_d, aaug_desc, tc::smem_desc_k_noswz(tc::smem_u32(baug) + c * 4096), idesc);   // Y -= U mu
-          }
           tc::umma_commit_w(&tfull[g * 2 + b]);
         }
         // prefetch this group's next tile into its other stage (freed when tile li-1 was finished)
@@ -456,18 +453,11 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
           for (int kl = 0; kl < TC_NCL; kl += 2) {
             if (kl < ncl) {
               uint32_t v0[32], v1[32];
-              if (!(a.dbg & 1)) {
               tc::tmem_ld32(taddr + kl * TC_D, v0);
               if (kl + 1 < ncl) tc::tmem_ld32(taddr + (kl + 1) * TC_D, v1);
               tc::tmem_ld_wait();
-              }
-              if (a.dbg & 3) {   // timing experiments only
-                qt[c * TC_NCL + kl] = (c * TC_NCL + kl) * 1000.f + ((a.dbg & 1) ? 0.f : __uint_as_float(v0[0] & 1u));
-                if (kl + 1 < ncl) qt[c * TC_NCL + kl + 1] = (c * TC_NCL + kl + 1) * 1000.f + ((a.dbg & 1) ? 0.f : __uint_as_float(v1[0] & 1u));
-              } else {
               qt[c * TC_NCL + kl] = gauss_tc_screen_q(v0);
               if (kl + 1 < ncl) qt[c * TC_NCL + kl + 1] = gauss_tc_screen_q(v1);
-              }
             }
           }
           tc::tc_fence_before();

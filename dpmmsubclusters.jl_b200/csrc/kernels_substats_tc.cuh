@@ -49,6 +49,10 @@
 #define SS_WSLOT (8192 + 8192 + 2048)    // Wh | Wl | bias k-step operand
 #define SS_TMEM_COLS 256                 // GEMM1: 2 x 64 columns, GEMM2: 2 x 64 columns
 #define SS_TLD 65
+#ifndef SS_DEBUG_SWITCHES
+#define SS_DEBUG_SWITCHES 0     // 1: the DPMM_SS_DEBUG ablation switches of tools/ss_debug_timing.py are live
+#endif
+#define SS_DBG (SS_DEBUG_SWITCHES ? a.dbg : 0)
 
 struct SubStatsArgs {
   const float* x;
@@ -71,7 +75,7 @@ struct SubStatsArgs {
   uint32_t call;
   int64_t goff;
   float* dump;             // optional [2][n]
-  int dbg;                 // development switches (timing experiments only; results are wrong when set)
+  int dbg;                 // development switches, compiled in with -DSS_DEBUG_SWITCHES=1 (timing experiments only)
 };
 
 struct SubStatsSmem {
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const bool ok = idx[j] >= 0;
-          if (!(a.dbg & 16)) cp_async16(dst + j * 4096, a.x + (size_t)(ok ? idx[j] : 0) * SS_D + 4 * c, ok ? 16 : 0);
+          if (!(SS_DBG & 16)) cp_async16(dst + j * 4096, a.x + (size_t)(ok ? idx[j] : 0) * SS_D + 4 * c, ok ? 16 : 0);
         }
       };
 #pragma unroll
@@ -267,14 +271,14 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         cp_async_wait_group<SS_PF - 1>();
         uint8_t* src = raw0 + (size_t)(li % SS_RAW) * SS_PANEL + offr;
         float4 v[4];
-        if (a.dbg & 512) {
+        if (SS_DBG & 512) {
           tc::mbar_arrive(&landed[li % SS_RAW]);
-          ss_wait(a.dbg, &sfree[b], ((li >> 1) & 1) ^ 1);
+          ss_wait(SS_DBG, &sfree[b], ((li >> 1) & 1) ^ 1);
           tc::fence_proxy_async();
           tc::mbar_arrive(&ready[b]);
           const int ln2 = li + SS_PF;
           if (ln2 < nt) {
-            ss_wait(a.dbg, &rfree[ln2 % SS_RAW], ((ln2 / SS_RAW) & 1) ^ 1);
+            ss_wait(SS_DBG, &rfree[ln2 % SS_RAW], ((ln2 / SS_RAW) & 1) ^ 1);
             stc_advance(wl, B);
           }
           cp_async_commit();
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           lo[j].z = v[j].z - tc::trunc_tf32(v[j].z); lo[j].w = v[j].w - tc::trunc_tf32(v[j].w);
         }
         tc::mbar_arrive(&landed[li % SS_RAW]);             // this thread's chunks of z are in shared memory
-        ss_wait(a.dbg, &sfree[b], ((li >> 1) & 1) ^ 1);     // GEMM1 of tile li - 2 has read the l panel
+        ss_wait(SS_DBG, &sfree[b], ((li >> 1) & 1) ^ 1);     // GEMM1 of tile li - 2 has read the l panel
         uint8_t* lk = split0 + (size_t)b * SS_PANEL + offk;
 #pragma unroll
         for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(lk + j * 4096) = lo[j];
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         // next gather: tile li + PF goes into the slot of tile li + PF - RAW once its permuting pass is done
         const int ln = li + SS_PF;
         if (ln < nt) {
-          ss_wait(a.dbg, &rfree[ln % SS_RAW], ((ln / SS_RAW) & 1) ^ 1);
+          ss_wait(SS_DBG, &rfree[ln % SS_RAW], ((ln / SS_RAW) & 1) ^ 1);
           issue(ln % SS_RAW);
           stc_advance(wl, B);
           if (ln + 1 < nt) load_idx();
@@ -336,10 +340,10 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           if (wm.key != prevkey) {
             prevkey = wm.key;
             ++kj;
-            ss_wait(a.dbg, wfull, kj & 1);
+            ss_wait(SS_DBG, wfull, kj & 1);
           }
-          ss_wait(a.dbg, &ready[b], (li >> 1) & 1);
-          ss_wait(a.dbg, &d1empty[b], ((li >> 1) & 1) ^ 1);
+          ss_wait(SS_DBG, &ready[b], (li >> 1) & 1);
+          ss_wait(SS_DBG, &d1empty[b], ((li >> 1) & 1) ^ 1);
           tc::tc_fence_after();
           uint64_t hd[4], ld[4];
 #pragma unroll
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
             ld[ks] = l_desc + (uint64_t)(b * (SS_PANEL >> 4) + ks * 2);
           }
           const uint32_t tmem_d = tmem_u + b * 64;
-          if (!(a.dbg & 8)) {
+          if (!(SS_DBG & 8)) {
           tc::umma_tf32_first_w(tmem_d, hd[0], whd[0], idesc1);
 #pragma unroll
           for (int ks = 1; ks < 4; ++ks) tc::umma_tf32_acc_w(tmem_d, hd[ks], whd[ks], idesc1);
@@ -375,7 +379,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         stc_walk_init(wm, B, P, nkeys, t0, t1);
         // M = 64.  (Experiment switch 2048: M = 128 with two garbage atoms after the panels, whose products
         // land in accumulator rows 64-127 that nobody reads -- measured 4 % slower, not faster.)
-        const uint32_t idesc2 = (a.dbg & 2048) ? tc::idesc_tf32_mn_m128(32) : tc::idesc_tf32_mn_m64(32);
+        const uint32_t idesc2 = (SS_DBG & 2048) ? tc::idesc_tf32_mn_m128(32) : tc::idesc_tf32_mn_m64(32);
         // A = [h | l] (two 32-row atoms, one panel apart), B = h: the same descriptor, one k-step = 8 rows = 1024 B
         const uint64_t pd0 = tc::smem_desc_mn128(tc::smem_u32(perm0), SS_PPANEL);
         const uint64_t pd1 = tc::smem_desc_mn128(tc::smem_u32(perm0 + 2 * SS_PPANEL), SS_PPANEL);
@@ -383,11 +387,11 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         for (int li = 0; li < nt; ++li) {
           const int b = li & 1;
           const bool first = wm.gcount == 0, last = stc_is_last(wm);
-          ss_wait(a.dbg, &permd[b], (li >> 1) & 1);
-          if (first) ss_wait(a.dbg, &d2empty[g2 & 1], ((g2 >> 1) & 1) ^ 1);
+          ss_wait(SS_DBG, &permd[b], (li >> 1) & 1);
+          if (first) ss_wait(SS_DBG, &d2empty[g2 & 1], ((g2 >> 1) & 1) ^ 1);
           tc::tc_fence_after();
           const int nkl = __shfl_sync(0xffffffffu, kcnt[b * 2], 0), nkr = __shfl_sync(0xffffffffu, kcnt[b * 2 + 1], 0);
-          const int k0 = right ? nkl : 0, nk = (a.dbg & 4) ? 0 : (right ? nkr : nkl);
+          const int k0 = right ? nkl : 0, nk = (SS_DBG & 4) ? 0 : (right ? nkr : nkl);
           const uint32_t tm = tmem_u + 128 + (g2 & 1) * 64 + right * 32;
           uint64_t pd = (b ? pd1 : pd0) + (uint64_t)(k0 * 64);
           int ks = 0;
@@ -440,13 +444,13 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
 
         }
         double u = 0.0;
-        if (valid && !(a.dbg & 1)) u = dpmm_uniform(a.u_inj, idx, a.seed, DPMM_STREAM_SUBLABEL, a.call, (uint64_t)(a.goff + idx));
-        ss_wait(a.dbg, &d1full[b], (li >> 1) & 1);
+        if (valid && !(SS_DBG & 1)) u = dpmm_uniform(a.u_inj, idx, a.seed, DPMM_STREAM_SUBLABEL, a.call, (uint64_t)(a.goff + idx));
+        ss_wait(SS_DBG, &d1full[b], (li >> 1) & 1);
         tc::tc_fence_after();
         uint32_t v0[32], v1[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + b * 64;
         float ql = 1.f, qr = 2.f;
-        if (!(a.dbg & 128)) {
+        if (!(SS_DBG & 128)) {
         tc::tmem_ld32(taddr, v0);
         tc::tmem_ld32(taddr + 32, v1);
         tc::tmem_ld_wait();
@@ -461,12 +465,12 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
             a.dump[idx] = rl;
             a.dump[a.n + idx] = rr;
           }
-          side = (a.dbg & 1) ? (row & 1) : dpmm_draw_two(rl, rr, u);
+          side = (SS_DBG & 1) ? (row & 1) : dpmm_draw_two(rl, rr, u);
           a.sub[idx] = (uint8_t)side;
         }
-        if (a.dbg & 1024) {
-          ss_wait(a.dbg, &landed[li % SS_RAW], (li / SS_RAW) & 1);
-          ss_wait(a.dbg, &pfree[b], ((li >> 1) & 1) ^ 1);
+        if (SS_DBG & 1024) {
+          ss_wait(SS_DBG, &landed[li % SS_RAW], (li / SS_RAW) & 1);
+          ss_wait(SS_DBG, &pfree[b], ((li >> 1) & 1) ^ 1);
           if (gt == 0) { kcnt[b * 2] = 8; kcnt[b * 2 + 1] = 8; }
           tc::fence_proxy_async();
           tc::mbar_arrive(&permd[b]);
@@ -493,8 +497,8 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         dest_g[row] = side == 0 ? (uint8_t)(offl + __popc(bl & lt_mask))
                                 : (side == 1 ? (uint8_t)(nl8 + offr_ + __popc(br & lt_mask)) : (uint8_t)255);
         if (gt == 0 && nl > 0) atomicAdd(a.lcount + key, nl);
-        ss_wait(a.dbg, &landed[li % SS_RAW], (li / SS_RAW) & 1);   // z of the tile (gathered and centred by the gather warps)
-        ss_wait(a.dbg, &pfree[b], ((li >> 1) & 1) ^ 1);    // the GEMM2 that read this slot two tiles ago
+        ss_wait(SS_DBG, &landed[li % SS_RAW], (li / SS_RAW) & 1);   // z of the tile (gathered and centred by the gather warps)
+        ss_wait(SS_DBG, &pfree[b], ((li >> 1) & 1) ^ 1);    // the GEMM2 that read this slot two tiles ago
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         if (gt == 0) {
           kcnt[b * 2] = nl8 >> 3;
@@ -505,7 +509,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int d = dest_g[r0 + 16 * j];
-          if (d != 255 && !(a.dbg & 2)) {
+          if (d != 255 && !(SS_DBG & 2)) {
             const float4 y4 = *reinterpret_cast<const float4*>(rp + j * 2048);   // z = x - c (centred in place)
             float4 h4, l4;
             h4.x = tc::to_tf32(y4.x); h4.y = tc::to_tf32(y4.y); h4.z = tc::to_tf32(y4.z); h4.w = tc::to_tf32(y4.w);
@@ -577,22 +581,22 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       for (int li = 0; li < nt; ++li) {
         if (stc_is_last(wd)) {
           const int buf = g2 & 1;
-          ss_wait(a.dbg, &d2full[buf], (g2 >> 1) & 1);
+          ss_wait(SS_DBG, &d2full[buf], (g2 >> 1) & 1);
           ++g2;
           tc::tc_fence_after();
           uint32_t v0[32], v1[32];
           const uint32_t taddr = tmem_base + 128 + buf * 64 + ((uint32_t)(sub * 32) << 16);
-          if (!(a.dbg & 256)) {
+          if (!(SS_DBG & 256)) {
           tc::tmem_ld32(taddr, v0);
           tc::tmem_ld32(taddr + 32, v1);
           tc::tmem_ld_wait();
           }
           tc::tc_fence_before();
           tc::mbar_arrive(&d2empty[buf]);
-          if (a.dbg & 256) { stc_advance(wd, B); continue; }
+          if (SS_DBG & 256) { stc_advance(wd, B); continue; }
           // M = 64: accumulator row m lives in lane (m % 16) of sub-partition m / 16
           // (M = 128, experiment switch: row m lives in TMEM lane m, rows 0-63 = sub-partitions 0 and 1)
-          const bool m64 = (a.dbg & 2048) == 0;
+          const bool m64 = (SS_DBG & 2048) == 0;
           if (m64 ? lane < 16 : sub < 2) {
             float* trow = T + (m64 ? 16 * sub + lane : 32 * sub + lane) * SS_TLD;
 #pragma unroll
@@ -607,7 +611,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
             const int ij = tri[e - sd * 528], i = ij >> 8, j = ij & 255;
             const int co = 32 * sd;
             const float sv = (T[i * SS_TLD + co + j] + T[(32 + i) * SS_TLD + co + j]) + T[(32 + j) * SS_TLD + co + i];
-            if (sv != 0.f && !(a.dbg & 32)) atomicAdd(a.acc + (size_t)(2 * wd.key + sd) * a.rec + 1 + SS_D + i * SS_D + j, (double)sv);
+            if (sv != 0.f && !(SS_DBG & 32)) atomicAdd(a.acc + (size_t)(2 * wd.key + sd) * a.rec + 1 + SS_D + i * SS_D + j, (double)sv);
           }
           asm volatile("bar.sync 3, 128;" ::: "memory");
         }
@@ -624,7 +628,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       for (int li = 0; li < nt; ++li) {
         if (wp.key != prevkey) {
           prevkey = wp.key;
-          ss_wait(a.dbg, wempty, (kj & 1) ^ 1);   // every GEMM1 of the previous cluster has retired
+          ss_wait(SS_DBG, wempty, (kj & 1) ^ 1);   // every GEMM1 of the previous cluster has retired
           const float4* src = reinterpret_cast<const float4*>(a.w + (size_t)wp.key * 2 * SS_D * SS_D);
           for (int e = lane; e < 512; e += 32) {
             const int r = e >> 3, cc = e & 7;   // row (side, i), 16-byte chunk

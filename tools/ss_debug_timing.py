@@ -1,4 +1,5 @@
-"""Development aid: time the fused kernel with parts switched off (DPMM_SS_DEBUG bit mask)."""
+"""Development aid: time the fused kernel with parts switched off (DPMM_SS_DEBUG bit mask).
+Needs a library built with DPMM_BUILD_DEBUG_SWITCHES=1 python __graft_entry__.py (force a rebuild: touch csrc/*.cu)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
