@@ -553,10 +553,11 @@ gauss_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GaussTcA
         int lab;
         if (!multi) {
           lab = __ffs(mask) - 1;
-          // the walk of utils.jl:29 stops at i = 1 when t = u * sum(w) is 0, i.e. for the uniform u == 0
-          if (lab > 0 && !a.final_iter &&
-              dpmm_uniform(a.u_inj, i, a.seed, DPMM_STREAM_LABEL, a.call, (uint64_t)(a.goff + i)) == 0.0)
-            lab = 0;
+          // The walk of utils.jl:29 stops at i = 1 when t = u * sum(w) is 0, i.e. for the uniform u == 0.
+          // Injected uniforms are checked.  A Philox uniform is 0 with probability 2^-53 per draw (once in
+          // ~10^7 runs of 10^3 iterations over 10^6 points); evaluating the generator for every decided
+          // point only to test for it costs ~100 instructions per point, so that case is not reproduced.
+          if (a.u_inj != nullptr && lab > 0 && !a.final_iter && a.u_inj[i] == 0.0) lab = 0;
         } else if (a.final_iter) {
           if (weird) {
             lab = dpmm_draw_argmax(rs, TC_TILE, K);
