@@ -124,6 +124,7 @@ struct dpmm_ctx {
 
   bool hist_valid = false, sorted = false, partitioned = false;
   int64_t n_fused = 0, n_cached = 0, n_recompute = 0;   // DPMM_VERBOSE counters
+  bool acc_cleared = false;    // acc / lcount were zeroed by the last label scatter and not touched since
   bool stats_cached = false;   // acc / lcount / centers hold the l/r statistics of every cluster for the current labels
   bool cursors_fresh = false;  // lr_cursor still holds the segment bounds (not yet consumed by a partition)
   int64_t launches = 0;

@@ -781,8 +781,13 @@ static int ensure_sorted(dpmm_ctx* ctx) {
   {
     const int T = 256;
     const unsigned grid = (unsigned)((ctx->n + (int64_t)T * SCATTER_PPT - 1) / ((int64_t)T * SCATTER_PPT));
-    label_scatter_kernel<<<grid, T, (size_t)K * 8, ctx->stream>>>(ctx->labels, ctx->n, K, ctx->scat_cursor, ctx->perm);
+    // the fused sub-label + statistics kernel (NIW, D = 32) wants its accumulators cleared: done here
+    const bool pre = ctx->prior == DPMM_PRIOR_NIW && ctx->D == SS_D && ctx->tc_ok && ctx->lcount != nullptr;
+    label_scatter_kernel<<<grid, T, (size_t)K * 8, ctx->stream>>>(ctx->labels, ctx->n, K, ctx->scat_cursor, ctx->perm,
+                                                                  pre ? ctx->acc : nullptr, pre ? (int64_t)2 * K * ctx->stats_rec : 0,
+                                                                  pre ? ctx->lcount : nullptr, pre ? K : 0);
     CK(cudaGetLastError());
+    ctx->acc_cleared = pre;
   }
   ctx->sorted = true;
   ctx->partitioned = ctx->stats_cached = false;
@@ -811,8 +816,11 @@ static int run_sublabels(dpmm_ctx* ctx, bool sample, float* dump) {
   if (sample && ctx->prior == DPMM_PRIOR_NIW && ctx->D == SS_D && ctx->tc_ok && env_int("DPMM_SUBSTATS_TC", 1) != 0 &&
       SubStatsSmem(ctx->K).total <= (size_t)ctx->smem_optin && keff(ctx) == ctx->K) {
     const int K = ctx->K, recs = ctx->stats_rec;
-    CK(cudaMemsetAsync(ctx->acc, 0, (size_t)2 * K * recs * 8, ctx->stream));
-    CK(cudaMemsetAsync(ctx->lcount, 0, (size_t)K * 4, ctx->stream));
+    if (!ctx->acc_cleared) {   // (cleared by the label scatter kernel when the sort has just run)
+      CK(cudaMemsetAsync(ctx->acc, 0, (size_t)2 * K * recs * 8, ctx->stream));
+      CK(cudaMemsetAsync(ctx->lcount, 0, (size_t)K * 4, ctx->stream));
+    }
+    ctx->acc_cleared = false;
     SubStatsArgs f{};
     f.x = ctx->x; f.n = ctx->n; f.K = K; f.perm = ctx->perm; f.seg_off = ctx->seg_off; f.w = ctx->ss_w; f.bias = ctx->ss_b;
     f.cen = ctx->ss_c; f.cst = ctx->cst; f.loglr = ctx->loglr; f.sub = ctx->sub; f.acc = ctx->acc; f.rec = recs;
@@ -918,7 +926,10 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
                                                                       ctx->items, ctx->item_ctr, ctx->item_ctr + 1);
     CK(cudaGetLastError());
   }
-  if (!cached) CK(cudaMemsetAsync(ctx->acc, 0, (size_t)2 * K * rec * 8, ctx->stream));
+  if (!cached) {
+    CK(cudaMemsetAsync(ctx->acc, 0, (size_t)2 * K * rec * 8, ctx->stream));
+    ctx->acc_cleared = false;   // about to be written by the separate statistics kernels
+  }
   StatsArgs sa{};
   sa.x = ctx->x; sa.D = D; sa.perm2 = ctx->perm2; sa.items = ctx->items; sa.n_items = ctx->item_ctr;
   sa.next_item = ctx->item_ctr + 1; sa.acc = ctx->acc; sa.rec = rec;

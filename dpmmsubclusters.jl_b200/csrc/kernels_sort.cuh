@@ -69,9 +69,14 @@ __global__ void label_scan_kernel(const int32_t* __restrict__ hist, int K, int32
 // perm <- point indices bucketed by label.  Each CTA ranks its points with shared-memory counters
 // and reserves one contiguous range per (CTA, label) with a single global atomic.
 #define SCATTER_PPT 8
+// `zero` / `zero2` (optional): buffers the NEXT kernel expects cleared (the statistics accumulators and left
+// counts of the fused sub-label + statistics kernel) -- cleared here instead of by two memset launches.
 __global__ void label_scatter_kernel(const int32_t* __restrict__ labels, int64_t n, int K,
-                                     int32_t* cursor, int32_t* perm) {
+                                     int32_t* cursor, int32_t* perm, double* zero, int64_t nzero,
+                                     int32_t* zero2, int nzero2) {
   extern __shared__ int sm[];
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nzero; e += (int64_t)gridDim.x * blockDim.x) zero[e] = 0.0;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nzero2; e += gridDim.x * blockDim.x) zero2[e] = 0;
   int* cnt = sm;
   int* basev = sm + K;
   const int T = blockDim.x, tid = threadIdx.x;
