@@ -87,9 +87,16 @@ __global__ void label_scatter_kernel(const int32_t* __restrict__ labels, int64_t
 #pragma unroll
   for (int j = 0; j < SCATTER_PPT; ++j) {
     const int64_t i = base + (int64_t)j * T + tid;
-    lab[j] = -1;
-    if (i < n) {
-      lab[j] = labels[i];
+    lab[j] = (i < n) ? labels[i] : -1;
+    // A warp whose 32 points share their label (label-sorted or blocked data) reserves its ranks with
+    // ONE shared-memory atomic instead of serialising 32 on the same counter; mixed warps rank per lane.
+    const int lane = tid & 31;
+    const int lab0 = __shfl_sync(0xffffffffu, lab[j], 0);
+    if (__all_sync(0xffffffffu, lab[j] == lab0)) {
+      int b0 = 0;
+      if (lane == 0 && lab0 >= 0) b0 = atomicAdd(&cnt[lab0], 32);
+      rank[j] = __shfl_sync(0xffffffffu, b0, 0) + lane;
+    } else if (lab[j] >= 0) {
       rank[j] = atomicAdd(&cnt[lab[j]], 1);
     }
   }
