@@ -87,7 +87,10 @@ __global__ void label_scatter_kernel(const int32_t* __restrict__ labels, int64_t
 #pragma unroll
   for (int j = 0; j < SCATTER_PPT; ++j) {
     const int64_t i = base + (int64_t)j * T + tid;
-    lab[j] = (i < n) ? labels[i] : -1;
+    lab[j] = (i < n) ? labels[i] : -1;   // all eight loads in flight before the (branchy) ranking below
+  }
+#pragma unroll
+  for (int j = 0; j < SCATTER_PPT; ++j) {
     // A warp whose 32 points share their label (label-sorted or blocked data) reserves its ranks with
     // ONE shared-memory atomic instead of serialising 32 on the same counter; mixed warps rank per lane.
     const int lane = tid & 31;
