@@ -133,8 +133,10 @@ class GpuSweep:
     def sample_sublabels(self):
         self._ck(self.lib.dpmm_sample_sublabels(self.h))
 
-    def suff_stats(self, indices=None, fetch=True):
-        """Returns (counts [m,3] i64, sum_x [m,3,D] f64, sum_xx [m,3,D,D] f64 or None)."""
+    def suff_stats(self, indices=None, fetch=True, out=None):
+        """Returns (counts [m,3] i64, sum_x [m,3,D] f64, sum_xx [m,3,D,D] f64 or None).
+        `out`: an earlier result of the same shape to be overwritten (saves the allocation and the
+        first-touch page faults of ~0.5 MB per call in a tight loop)."""
         if indices is None:
             m, idx_p, idx = max(self.K, 1), None, None
         else:
@@ -143,9 +145,19 @@ class GpuSweep:
         if not fetch:
             self._ck(self.lib.dpmm_suff_stats(self.h, idx_p, m, None, None, None))
             return None
-        counts = np.zeros((m, 3), np.int64)
-        sum_x = np.zeros((m, 3, self.D), np.float64)
-        sum_xx = np.zeros((m, 3, self.D, self.D), np.float64) if self.prior_kind == NIW else None
+        if out is not None:
+            counts, sum_x, sum_xx = out
+            ok = (counts.shape == (m, 3) and counts.dtype == np.int64 and counts.flags.c_contiguous
+                  and sum_x.shape == (m, 3, self.D) and sum_x.dtype == np.float64 and sum_x.flags.c_contiguous
+                  and (sum_xx is None) == (self.prior_kind != NIW)
+                  and (sum_xx is None or (sum_xx.shape == (m, 3, self.D, self.D) and sum_xx.dtype == np.float64
+                                          and sum_xx.flags.c_contiguous)))
+            if not ok:
+                raise ValueError("suff_stats(out=...): arrays of the wrong shape / dtype / layout")
+        else:
+            counts = np.zeros((m, 3), np.int64)
+            sum_x = np.zeros((m, 3, self.D), np.float64)
+            sum_xx = np.zeros((m, 3, self.D, self.D), np.float64) if self.prior_kind == NIW else None
         self._ck(self.lib.dpmm_suff_stats(self.h, idx_p, m, _ptr(counts, C.c_int64), _ptr(sum_x, C.c_double),
                                           _ptr(sum_xx, C.c_double)))
         return counts, sum_x, sum_xx

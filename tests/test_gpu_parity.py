@@ -127,6 +127,22 @@ def test_niw_fused_kernel_edge_shapes(pkg, K, n, empty):
     print(f"K={K} n={n} empty={empty}: {rep}; fused {fused}, served {served}, recomputed {redone}")
 
 
+def test_suff_stats_out_argument_reuses_the_result_arrays(pkg):
+    case = make_niw_case(32, 4, 3000, seed=2)
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=3)
+    set_params(g, case)
+    g.sample_labels(False); g.sample_sublabels()
+    a = g.suff_stats()
+    b = g.suff_stats(out=tuple(np.full_like(v, -1) for v in a))
+    for u, v in zip(a, b):
+        np.testing.assert_array_equal(u, v)
+    c = g.suff_stats(out=b)
+    assert all(u is v for u, v in zip(b, c))
+    with pytest.raises(ValueError):
+        g.suff_stats([1], out=b)
+    g.close()
+
+
 def test_niw_fused_statistics_fall_back_when_a_run_is_far_from_its_centre(pkg):
     """The fused kernel accumulates sums about the cluster's centre c.  When the points of a run are much
     closer to the origin than to c in some component (here: x_0 ~ 0.01 while every mean says 30), the
