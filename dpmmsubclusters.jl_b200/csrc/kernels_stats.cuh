@@ -295,6 +295,60 @@ niw_stats_kernel(const StatsArgs a) {
   }
 }
 
+// K5 for small D (<= 8): one WARP per work item, lane <-> point.  A row is D scalars (20 bytes at D = 5: not
+// worth staging through shared memory, and cp.async would need one 4-byte copy per scalar); each lane keeps
+// sum x and the upper triangle of sum x x' of its <= 32 points in Float32 registers, one transposed warp
+// reduction combines the lanes, and the totals go to the Float64 accumulator.
+template <int D>
+__global__ void __launch_bounds__(256) niw_stats_small_kernel(const StatsArgs a) {
+  constexpr int NV = D + D * (D + 1) / 2;          // sum x | upper triangle of S, row by row
+  constexpr int NVP = (NV + 31) / 32 * 32;
+  const int lane = threadIdx.x & 31;
+  const int n_items = *a.n_items;
+  for (;;) {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(a.next_item, 1);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= n_items) break;
+    const StatsItem item = a.items[it];
+    float v[NVP];
+#pragma unroll
+    for (int e = 0; e < NVP; ++e) v[e] = 0.f;
+    for (int p = item.begin + lane; p < item.end; p += 32) {
+      const float* xp = a.x + (size_t)__ldg(a.perm2 + p) * D;
+      float x[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) x[i] = __ldg(xp + i);
+      int e = D;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        v[i] += x[i];
+#pragma unroll
+        for (int j = i; j < D; ++j) {
+          v[e] = fmaf(x[i], x[j], v[e]);
+          ++e;
+        }
+      }
+    }
+    warp_transpose_reduce<NVP>(v, lane);
+    double* dst = a.acc + (size_t)item.key * a.rec + 1;
+#pragma unroll
+    for (int s = 0; s < NVP / 32; ++s) {
+      const int e = warp_transpose_entry<NVP>(lane, s);
+      if (e < D) {
+        if (v[s] != 0.f) atomicAdd(dst + e, (double)v[s]);
+      } else if (e < NV) {
+        int t = e - D, i = 0;
+        while (t >= D - i) {   // row i of the upper triangle holds D - i entries
+          t -= D - i;
+          ++i;
+        }
+        if (v[s] != 0.f) atomicAdd(dst + D + (size_t)i * D + (i + t), (double)v[s]);
+      }
+    }
+  }
+}
+
 #ifndef DPMM_TEMPLATES_ONLY
 // K6: multinomial.  sum x per key.  One warp per work item (a run of points with one (label, side)
 // key); lane l owns the features l, l+32, ... so every point is read as fully coalesced 128-byte

@@ -136,6 +136,16 @@ static int launch_gauss_sublabel(dpmm_ctx* ctx, const SubLabelArgs& a, bool samp
 template <int D>
 static int launch_niw_stats(dpmm_ctx* ctx, const StatsArgs& a) {
   using C = StatsCfg<D>;
+  if constexpr (D <= 8) {
+    // one warp per run chunk pays off once there are enough chunks to fill the machine (C4: 313 -> 82 us);
+    // on small inputs the CTA-cooperative kernel below has the shorter critical path (C1: 10 vs 19 us)
+    if (ctx->n >= ((int64_t)1 << 18) && env_int("DPMM_STATS_SMALL", 1) != 0) {
+      KernelTimer kt(ctx, TK_STATS);
+      niw_stats_small_kernel<D><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a);
+      CK(cudaGetLastError());
+      return 0;
+    }
+  }
   auto kern = niw_stats_kernel<D>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   int occ = 1;

@@ -127,6 +127,28 @@ def test_niw_fused_kernel_edge_shapes(pkg, K, n, empty):
     print(f"K={K} n={n} empty={empty}: {rep}; fused {fused}, served {served}, recomputed {redone}")
 
 
+def test_small_dimension_statistics_kernel_on_a_large_input(pkg):
+    """D <= 8 and n >= 2^18 points: the statistics run on niw_stats_small_kernel (one warp per run chunk)."""
+    n, D, K = 300_000, 5, 12
+    case = make_niw_case(D, K, n, seed=31)
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=4)
+    set_params(g, case)
+    g.sample_labels(False); g.sample_sublabels()
+    lab, sub = g.get_labels(), g.get_sublabels()
+    counts, sx, sxx = g.suff_stats()
+    o = O.OracleSweep(case["x"], O.NIW, seed=4)
+    o.K = K
+    o.set_labels(lab); o.set_sublabels(sub)
+    check_stats((counts, sx, sxx), o.suff_stats(), O.NIW, "small-D statistics kernel")
+    os.environ["DPMM_STATS_SMALL"] = "0"
+    try:
+        c2, sx2, sxx2 = g.suff_stats([2, 1])
+    finally:
+        os.environ.pop("DPMM_STATS_SMALL")
+    check_stats((c2, sx2, sxx2), (counts[[1, 0]], sx[[1, 0]], sxx[[1, 0]]), O.NIW, "small-D vs cooperative kernel")
+    g.close()
+
+
 def test_suff_stats_out_argument_reuses_the_result_arrays(pkg):
     case = make_niw_case(32, 4, 3000, seed=2)
     g = pkg.GpuSweep(case["x"], pkg.NIW, seed=3)
