@@ -135,8 +135,9 @@ def compare_sweeps(g, o, case, rng, final=False):
     gl, ol = g.get_labels(), o.get_labels()
     if final:
         bad = np.nonzero(gl != ol)[0]
-        srt = np.sort(LLo[bad], axis=1)
-        assert ((srt[:, -1] - srt[:, -2]) <= tie_tolerance(LLo[bad])).all(), "argmax mismatch that is not a tie"
+        if bad.size:   # (two different labels exist, so K >= 2)
+            srt = np.sort(LLo[bad], axis=1)
+            assert ((srt[:, -1] - srt[:, -2]) <= tie_tolerance(LLo[bad])).all(), "argmax mismatch that is not a tie"
         rep["label_ties"] = int(bad.size)
     else:
         rep["label_ties"] = check_draws(LLo, u_label, gl, ol, "labels")
