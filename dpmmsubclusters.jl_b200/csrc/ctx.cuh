@@ -26,9 +26,11 @@ enum TimingKind {
   TK_STATS_AUX,     // work list + finalise/pack
   TK_RELABEL,       // LUT relabel / init
   TK_ALLREDUCE,     // NCCL all-reduce of the packed statistics
+  TK_LABEL_OVF,     // full-K overflow kernel of the D = 32 / 64 tensor-core label path
+  TK_PARAMS,        // parameter packing / device-side parameter step
   TK_COUNT
 };
-static const char* const kTimingNames[TK_COUNT] = {"label", "sort", "sublabel", "stats", "stats_aux", "relabel", "allreduce"};
+static const char* const kTimingNames[TK_COUNT] = {"label", "sort", "sublabel", "stats", "stats_aux", "relabel", "allreduce", "label_ovf", "params"};
 
 struct TimedEvent {
   cudaEvent_t a, b;
@@ -87,6 +89,16 @@ struct dpmm_ctx {
   float* tc_mu = nullptr;
   float* tc_fro = nullptr;
   int32_t* tc_stats = nullptr;
+  // second-generation tensor-core label path (NIW, D == 32 or 64): operand images, rows of U, overflow counter
+  float* t2_piv = nullptr;
+  float* t2_scr = nullptr;
+  float* t2_u = nullptr;
+  float* t2_bias = nullptr;
+  float* t2_fro8 = nullptr;
+  int32_t* t2_ctr = nullptr;
+  bool t2_ok = false;       // shape supported
+  bool t2_params = false;   // t2_* describe the current parameters
+  int t2_KS = 0, t2_nch = 0;
   // fused sub-label + statistics tensor-core path (NIW, D == 32): U rows / bias / centre per cluster, left counts
   float* ss_w = nullptr;
   float* ss_b = nullptr;

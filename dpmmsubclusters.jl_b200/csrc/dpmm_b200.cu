@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "kernels_gauss.cuh"
 #include "kernels_gauss_tc.cuh"
+#include "kernels_gauss_tc2.cuh"
 #include "kernels_mnm.cuh"
 #include "kernels_mnm_tc.cuh"
 #include "kernels_pack.cuh"
@@ -53,13 +54,23 @@ static int ensure_k(dpmm_ctx* ctx, int K) {
     CK(dev_realloc(&ctx->mtc_w, (size_t)3 * ((D + 31) / 32) * MTC_N * 32));
     ctx->mtc_params = false;
   }
+  if (ctx->tc_ok || ctx->t2_ok) {
+    CK(dev_realloc(&ctx->tc_b, (size_t)cap * D));
+    CK(dev_realloc(&ctx->tc_mu, (size_t)cap * D));
+    CK(dev_realloc(&ctx->tc_fro, (size_t)cap));
+    ctx->tc_params = ctx->t2_params = false;
+  }
+  if (ctx->t2_ok) {
+    const int capt = std::min(cap, T2_MAX_K);   // beyond that the images do not fit shared memory anyway
+    CK(dev_realloc(&ctx->t2_piv, (size_t)capt * D * D));
+    CK(dev_realloc(&ctx->t2_u, (size_t)capt * D * D));
+    CK(dev_realloc(&ctx->t2_scr, (size_t)gauss_tc2_nch(D, capt) * (D / 8) * 1024));
+    CK(dev_realloc(&ctx->t2_bias, (size_t)capt * (gauss_tc2_nch(D, capt) * 512 + 32)));
+    CK(dev_realloc(&ctx->t2_fro8, (size_t)capt));
+  }
   if (ctx->tc_ok) {
     const int capc = std::min(cap, TC_MAX_K);
     CK(dev_realloc(&ctx->tc_w, (size_t)((capc + TC_NCL - 1) / TC_NCL) * TC_NCL * TC_D * TC_D));
-    CK(dev_realloc(&ctx->tc_b, (size_t)capc * TC_D));
-    CK(dev_realloc(&ctx->tc_mu, (size_t)capc * TC_D));
-    CK(dev_realloc(&ctx->tc_fro, (size_t)capc));
-    ctx->tc_params = false;
     CK(dev_realloc(&ctx->ss_w, (size_t)cap * 2 * SS_D * SS_D));
     CK(dev_realloc(&ctx->ss_b, (size_t)cap * 2 * SS_D));
     CK(dev_realloc(&ctx->ss_c, (size_t)cap * SS_D));
@@ -224,6 +235,11 @@ extern "C" int dpmm_create(dpmm_ctx** out, const float* x, int64_t n_local, int3
     }
     if (ctx->tc_ok) CKC(cudaMalloc((void**)&ctx->tc_stats, 2 * sizeof(int32_t)));
   }
+  if (prior_kind == DPMM_PRIOR_NIW && (d == 32 || d == 64) && n_local >= T2_TILE) {
+    ctx->t2_ok = true;
+    CKC(cudaMalloc((void**)&ctx->t2_ctr, 2 * sizeof(int32_t)));
+    if (ctx->tc_stats == nullptr) CKC(cudaMalloc((void**)&ctx->tc_stats, 2 * sizeof(int32_t)));
+  }
   if (prior_kind == DPMM_PRIOR_MULTINOMIAL && d % 4 == 0 && d <= MTC_MAX_D && n_local >= MTC_TILE) {
     // the tensor-core likelihood is exact only for TF32-exact counts: integral, |x| < 2^11
     bool exact = true;
@@ -271,7 +287,7 @@ extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
   }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   void* ptrs[] = {ctx->x, ctx->labels, ctx->sub, ctx->perm, ctx->perm2, ctx->u_label, ctx->u_sub, ctx->r_bits,
-                  ctx->raw_params, ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->tc_w, ctx->tc_b, ctx->tc_mu, ctx->tc_fro, ctx->tc_stats, ctx->ss_w, ctx->ss_b, ctx->ss_c, ctx->lcount, ctx->mtc_w, ctx->hist, ctx->seg_off,
+                  ctx->raw_params, ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->t2_piv, ctx->t2_scr, ctx->t2_u, ctx->t2_bias, ctx->t2_fro8, ctx->t2_ctr, ctx->tc_w, ctx->tc_b, ctx->tc_mu, ctx->tc_fro, ctx->tc_stats, ctx->ss_w, ctx->ss_b, ctx->ss_c, ctx->lcount, ctx->mtc_w, ctx->hist, ctx->seg_off,
                   ctx->scat_cursor, ctx->lr_cursor, ctx->lut_l, ctx->lut_r, ctx->rule, ctx->wanted,
                   ctx->idx_list, ctx->acc, ctx->centers, ctx->outbuf, ctx->items, ctx->item_ctr};
   for (void* p : ptrs)
@@ -600,10 +616,21 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
   CK(cudaMemcpyAsync(ctx->raw_params, h_mu, raw_floats * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->logw, h_logw, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->loglr, h_loglr, (size_t)2 * K * 4, cudaMemcpyHostToDevice, ctx->stream));
-  ctx->tc_params = false;
+  ctx->tc_params = ctx->t2_params = false;
   if (tcp) {
     const size_t wfl = (size_t)((K + TC_NCL - 1) / TC_NCL) * TC_NCL * TC_D * TC_D;
     CK(cudaMemsetAsync(ctx->tc_w, 0, wfl * 4, ctx->stream));   // zero padding of the last chunk
+  }
+  // second-generation label path: screen over all features while the images stay small, else over the last 8
+  bool t2p = false;
+  int t2_ks = 0, t2_nch = 0;
+  if (ctx->t2_ok) {
+    t2_nch = gauss_tc2_nch(D, K);
+    t2_ks = (D == 32 && t2_nch <= 4) ? D : 8;
+    const int ks_env = env_int("DPMM_TC2_KS", 0);
+    if (ks_env == 8 || ks_env == D) t2_ks = ks_env;
+    t2p = K <= T2_MAX_K && GaussTc2Smem(D, K, t2_ks, t2_nch, std::max(K, ctx->label_bound) + 8).total <= (size_t)ctx->smem_optin;
+    if (t2p) CK(cudaMemsetAsync(ctx->t2_scr, 0, (size_t)t2_nch * (t2_ks / 8) * 4096, ctx->stream));
   }
   {
     NiwPackArgs pa{};
@@ -612,11 +639,24 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
     pa.recs = ctx->recs; pa.cst = ctx->cst;
     pa.tc_w = tcp ? ctx->tc_w : nullptr; pa.tc_b = ctx->tc_b; pa.tc_mu = ctx->tc_mu; pa.tc_fro = ctx->tc_fro;
     pa.ss_w = ctx->tc_ok ? ctx->ss_w : nullptr; pa.ss_b = ctx->ss_b; pa.ss_c = ctx->ss_c;
-    KernelTimer kt(ctx, TK_RELABEL);
+    pa.t2_piv = t2p ? ctx->t2_piv : nullptr; pa.t2_scr = ctx->t2_scr; pa.t2_u = ctx->t2_u; pa.t2_KS = t2_ks;
+    pa.t2_n0 = gauss_tc2_n0(D); pa.t2_fro8 = ctx->t2_fro8;
+    KernelTimer kt(ctx, TK_PARAMS);
     niw_pack_kernel<<<(unsigned)nrec, NIW_PACK_THREADS, (size_t)D * (D + 1) * sizeof(double), ctx->stream>>>(pa);
     CK(cudaGetLastError());
   }
+  if (t2p) {
+    NiwT2BiasArgs ba{};
+    ba.D = D; ba.K = K; ba.KS = t2_ks; ba.n0 = gauss_tc2_n0(D); ba.nch = t2_nch; ba.u = ctx->t2_u; ba.mu = ctx->tc_mu;
+    ba.bias = ctx->t2_bias;
+    KernelTimer kt(ctx, TK_PARAMS);
+    niw_t2_bias_kernel<<<(unsigned)K, 256, 0, ctx->stream>>>(ba);
+    CK(cudaGetLastError());
+  }
   ctx->tc_params = tcp;
+  ctx->t2_params = t2p;
+  ctx->t2_KS = t2_ks;
+  ctx->t2_nch = t2_nch;
   ctx->K = K;
   ctx->params_set = true;
   return 0;
@@ -692,13 +732,68 @@ extern "C" int dpmm_set_params_multinomial(dpmm_ctx* ctx, int32_t K, const float
 // ------------------------------------------------------------------------------------------------
 // the sweep
 // ------------------------------------------------------------------------------------------------
+static int ensure_sorted(dpmm_ctx* ctx);
+
+template <int D>
+static int launch_label_tc2(dpmm_ctx* ctx, int final_iter, int nkeys) {
+  const int K = ctx->K;
+  GaussTc2Args a{};
+  a.x = ctx->x; a.n = ctx->n; a.K = K; a.KS = ctx->t2_KS; a.nch = ctx->t2_nch; a.n0 = gauss_tc2_n0(D);
+  a.perm = ctx->perm; a.seg_off = ctx->seg_off; a.nkeys = nkeys; a.wpiv = ctx->t2_piv; a.wscr = ctx->t2_scr;
+  a.wbias = ctx->t2_bias; a.fro8 = ctx->t2_fro8;
+  a.urows = ctx->t2_u; a.mu = ctx->tc_mu; a.cst = ctx->cst; a.logw = ctx->logw; a.fro = ctx->tc_fro;
+  a.labels = ctx->labels; a.hist = ctx->hist; a.ovf_list = ctx->perm2; a.ovf_count = ctx->t2_ctr;
+  a.u_inj = ctx->u_label; a.seed = ctx->seed; a.call = ctx->call; a.goff = ctx->goff; a.final_iter = final_iter;
+  a.stats = env_int("DPMM_TC_STATS", 0) ? ctx->tc_stats : nullptr;
+  const size_t sm = GaussTc2Smem(D, K, a.KS, a.nch, nkeys).total;
+  CK(cudaFuncSetAttribute(gauss_label_tc2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  CK(cudaMemsetAsync(ctx->t2_ctr, 0, 8, ctx->stream));
+  if (a.stats) CK(cudaMemsetAsync(ctx->tc_stats, 0, 8, ctx->stream));
+  const int64_t grid = std::min<int64_t>((ctx->n + T2_TILE - 1) / T2_TILE, (int64_t)ctx->sm_count);
+  {
+    KernelTimer kt(ctx, TK_LABEL);
+    gauss_label_tc2_kernel<D><<<(unsigned)grid, T2_THREADS, sm, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+  }
+  // the (normally empty) overflow list: points with a NaN / Inf screen value or more than 7 candidates
+  GaussListArgs l{};
+  l.x = ctx->x; l.K = K; l.list = ctx->perm2; l.count = ctx->t2_ctr; l.urows = ctx->t2_u; l.mu = ctx->tc_mu;
+  l.cst = ctx->cst; l.logw = ctx->logw; l.labels = ctx->labels; l.hist = ctx->hist; l.u_inj = ctx->u_label;
+  l.seed = ctx->seed; l.call = ctx->call; l.goff = ctx->goff; l.final_iter = final_iter; l.stats = a.stats;
+  const size_t lsm = (size_t)8 * K * 4;
+  if (lsm > 48 * 1024) CK(cudaFuncSetAttribute(gauss_label_list_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+  {
+    KernelTimer kt(ctx, TK_LABEL_OVF);
+    gauss_label_list_kernel<D><<<(unsigned)ctx->sm_count * 2, 256, lsm, ctx->stream>>>(l);
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
 static int run_sample_labels(dpmm_ctx* ctx, int final_iter, float* dump) {
   NEED(ctx->params_set, DPMM_ESTATE, "set_params must precede sample_labels");
   const int K = ctx->K;
   ctx->call += 1;
+  // K2 second generation (tcgen05, D = 32 / 64, any K that fits): walks the points in the order of the
+  // CURRENT label sort, so that sort has to be valid (it is, from the previous iteration, unless a relabel
+  // operation ran since)
+  bool use_t2 = ctx->prior == DPMM_PRIOR_NIW && ctx->t2_params && dump == nullptr &&
+                ctx->sampler == DPMM_SAMPLER_INVERSE_CDF && env_int("DPMM_LABEL_TC", 2) == 2;
+  int nkeys = 0;
+  if (use_t2) {
+    nkeys = keff(ctx);
+    use_t2 = GaussTc2Smem(ctx->D, K, ctx->t2_KS, ctx->t2_nch, nkeys).total <= (size_t)ctx->smem_optin;
+  }
+  if (use_t2) {
+    int rc = ensure_sorted(ctx);
+    if (rc) return rc;
+  }
   CK(cudaMemsetAsync(ctx->hist, 0, (size_t)K * 4, ctx->stream));
-  if (ctx->prior == DPMM_PRIOR_NIW && ctx->tc_params && dump == nullptr && ctx->sampler == DPMM_SAMPLER_INVERSE_CDF &&
-      env_int("DPMM_LABEL_TC", 1) != 0) {
+  if (use_t2) {
+    int rc = ctx->D == 32 ? launch_label_tc2<32>(ctx, final_iter, nkeys) : launch_label_tc2<64>(ctx, final_iter, nkeys);
+    if (rc) return rc;
+  } else if (ctx->prior == DPMM_PRIOR_NIW && ctx->tc_params && dump == nullptr && ctx->sampler == DPMM_SAMPLER_INVERSE_CDF &&
+      env_int("DPMM_LABEL_TC", 2) != 0) {
     // K2: tcgen05 TF32 screen + FP32 refine
     GaussTcArgs a{};
     a.n = ctx->n; a.K = K; a.wmat = ctx->tc_w; a.bvec = ctx->tc_b; a.mu = ctx->tc_mu; a.cst = ctx->cst; a.logw = ctx->logw;
@@ -1061,16 +1156,20 @@ extern "C" int dpmm_debug_loglik(dpmm_ctx* ctx, int32_t which, float* out) {
   return rc;
 }
 
-extern "C" int dpmm_debug_tc_stats(dpmm_ctx* ctx, int64_t* out2) {
-  NEED(ctx && out2, DPMM_EINVAL, "NULL argument");
+extern "C" int dpmm_debug_tc_stats(dpmm_ctx* ctx, int64_t* out3) {
+  NEED(ctx && out3, DPMM_EINVAL, "NULL argument");
   CK(cudaSetDevice(ctx->device));
-  out2[0] = out2[1] = 0;
+  out3[0] = out3[1] = out3[2] = 0;
   if (ctx->tc_stats == nullptr) return 0;
   int32_t h[2] = {0, 0};
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpy(h, ctx->tc_stats, 8, cudaMemcpyDeviceToHost));
-  out2[0] = h[0];
-  out2[1] = h[1];
+  out3[0] = h[0];
+  out3[1] = h[1];
+  if (ctx->t2_ctr != nullptr) {
+    CK(cudaMemcpy(h, ctx->t2_ctr, 4, cudaMemcpyDeviceToHost));
+    out3[2] = h[0];
+  }
   return 0;
 }
 

@@ -176,6 +176,10 @@ __device__ __forceinline__ uint64_t smem_desc_k128(uint32_t saddr) {
 __device__ __forceinline__ uint64_t smem_desc_k_noswz(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
 }
+// the same with explicit strides: LBO between the two k halves, SBO between 8-row groups
+__device__ __forceinline__ uint64_t smem_desc_k_noswz2(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
 // Instruction descriptor: FP32 accumulator, TF32 A and B, both K-major, M = 128, N = n.
 __device__ __forceinline__ uint32_t idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);

@@ -1,0 +1,695 @@
+// K2 (second generation): fused Gaussian log-likelihood + label draw on tcgen05 for D = 32 and D = 64,
+// any K that fits the shared-memory images (K <= ~250 at D = 32, ~110 at D = 64).
+//
+//   sample_labels_worker!        src/local_clusters_actions.jl:112-134
+//   log_likelihood!(mv_gaussian) src/distributions/mv_gaussian.jl:21-25
+//   sample_log_cat_array!        src/utils.jl:19-31
+//
+// The points are visited in the order of the CURRENT label sort (perm / seg_off of kernels_sort.cuh), so a
+// tile = 128 consecutive positions of ONE old cluster p, the tile's PIVOT.  At every iteration but the first
+// few almost every point keeps its label, so the pivot is the cluster that decides the draw, and because it
+// is uniform over the tile everything below is warp-uniform:
+//
+//  0. CENTRE: the gather warps shift the tile by the pivot's mean in shared memory, z = x - mu_p.  The TF32
+//     error of everything below is proportional to |z| (the spread of a cluster), not to |x|.
+//  1. PIVOT (tcgen05, kind::tf32): Y_p = Z U_p' for the full factor of the pivot (D columns).
+//     q~_p = |y|^2 carries a bounded TF32 error, so it yields a LOWER bound of r_p (see kernels_gauss_tc.cuh).
+//  2. SCREEN (tcgen05): for EVERY cluster k only R = 8 rows of its factor:  q_k >= |rows of U_k (x - mu_k)|^2.
+//     Either the first 8 rows of U_k over all features (KS = D) or the last 8 rows, which only involve the
+//     last 8 features (KS = 8: the marginal Mahalanobis distance in those features; 1 k-step instead of D/8).
+//     Y = Z U_k[rows]' - U_k[rows] (mu_k - mu_p), the second term from a per-pivot bias table (niw_t2_bias_kernel)
+//     folded in as one more k-step.  That gives an UPPER bound of r_k from 8 accumulator columns instead of D.
+//     Cluster k is a candidate of the point iff that upper bound reaches within DELTA = 30 of the pivot's
+//     lower bound.
+//  3. A point without candidates keeps the pivot: every other weight is < e^-30 of the pivot's, and no
+//     uniform is drawn.  Otherwise the pivot and the <= 7 candidates are evaluated EXACTLY on the FMA pipe
+//     (z = x - mu in Float32, |U z|^2, the reference's final operations) and drawn with the reference's
+//     inverse-CDF walk over those entries (all others contribute exact zeros to every sum).
+//  4. Points with a NaN / Inf screen value or more than 7 candidates go to an overflow list that
+//     gauss_label_list_kernel finishes with the full K-cluster evaluation (one warp per point).
+//
+// Per tile the tensor core therefore produces D + 8K accumulator columns (C2: 192 instead of 640) and the
+// epilogue reads exactly those.  The factor images live in shared memory in the un-swizzled K-major core
+// matrix layout (8 rows x 16 bytes), written in that layout by niw_pack_kernel, so any K is a matter of
+// more 16-cluster chunks, not of a resident K x D x D block.
+//
+// Warp roles (384 threads, one CTA per SM, contiguous range of the tile sequence per CTA):
+//   warps 0/1   control of point-group 0/1 (pivot image staging + tcgen05.mma issue)
+//   warps 2-5 / 6-9  epilogue (TMEM lane = point) of group 0/1, alternate tiles
+//   warps 10-11 gather: cp.async of the 128 rows of a tile into a 128B-swizzled K-major stage ring
+#pragma once
+#include "kernels_gauss_tc.cuh"
+#include "kernels_stats.cuh"   // cp_async16 / commit / wait_group
+
+#define T2_TILE 128
+#define T2_THREADS 384
+#define T2_CMAX 8          // exact evaluations per point handled in the kernel (pivot included)
+#define T2_R 8             // screen rows per cluster
+#define T2_DELTA 30.0f
+#define T2_MAX_K 256        // bias tables are K x K
+
+struct GaussTc2Args {
+  const float* x;          // [n][D]
+  int64_t n;
+  int K, KS, nch, n0;      // KS = features of the screen (8 or D); nch chunks; n0 clusters in chunk 0
+  const int32_t* perm;     // [n] point indices sorted by the labels at call time
+  const int32_t* seg_off;  // [nkeys + 1]
+  int nkeys;
+  const float* wpiv;       // [K][D*D]  pivot image: D/8 k-step slabs
+  const float* wscr;       // [nch][(KS/8) * 1024] screen images
+  const float* wbias;      // [K pivots][nch * 512 + 32] bias tables (compact B operand of the bias k-step)
+  const float* urows;      // [K][D][D] rows of U_k (zero below the diagonal)
+  const float* mu;         // [K][D]
+  const float* cst;        // [3K]
+  const float* logw;       // [K]
+  const float* fro;        // [K] |U_k|_F
+  const float* fro8;       // [K] |screen rows of U_k|_F
+  int32_t* labels;
+  int32_t* hist;
+  int32_t* ovf_list;       // [n]
+  int32_t* ovf_count;      // [1]
+  const double* u_inj;
+  uint64_t seed;
+  uint32_t call;
+  int64_t goff;
+  int final_iter;
+  int32_t* stats;          // optional [2]: points, exact evaluations
+};
+
+struct GaussTc2Smem {
+  int ns, pf;
+  size_t stage_bytes, piv_bytes, scr_bytes, bias_bytes;
+  size_t stages, piv, scr, bias, aaug, ccfro, cfin, lists, rlists, pairs, misc, bnd, pre, hist, bars, total;
+  __host__ __device__ GaussTc2Smem(int D, int K, int KS, int nch, int nkeys) {
+    ns = D == 32 ? 4 : 3;
+    pf = ns - 2;
+    stage_bytes = (size_t)T2_TILE * D * 4;
+    piv_bytes = (size_t)(D * D) * 4;
+    scr_bytes = (size_t)(KS / 8) * 4096;
+    bias_bytes = (size_t)nch * 2048 + 128;
+    size_t o = 0;
+    stages = o;  o += ns * stage_bytes;
+    piv = o;     o += 2 * piv_bytes;
+    scr = o;     o += (size_t)nch * scr_bytes;
+    bias = o;    o += 2 * bias_bytes;
+    aaug = o;    o += 4096;
+    ccfro = o;   o += (size_t)K * 16;
+    cfin = o;    o += (size_t)K * 8;
+    o = (o + 15) & ~(size_t)15;
+    lists = o;   o += 2 * T2_TILE * T2_CMAX * 2;
+    rlists = o;  o += 2 * T2_TILE * T2_CMAX * 4;
+    pairs = o;   o += 2 * T2_TILE * T2_CMAX * 2;
+    misc = o;    o += 2 * 16 * 4;
+    bnd = o;     o += (size_t)(nkeys + 1) * 4;
+    pre = o;     o += (size_t)(nkeys + 1) * 4;
+    hist = o;    o += (size_t)((K + 3) & ~3) * 4;
+    o = (o + 15) & ~(size_t)15;
+    bars = o;    o += 32 * 8 + 16;
+    total = o;
+  }
+};
+__host__ __device__ inline int gauss_tc2_n0(int D) { return (128 - D) / T2_R; }
+__host__ __device__ inline int gauss_tc2_nch(int D, int K) {
+  const int n0 = gauss_tc2_n0(D);
+  return K <= n0 ? 1 : 1 + (K - n0 + 15) / 16;
+}
+
+struct T2Walk {
+  int key, pos, end, tleft;
+};
+__device__ __forceinline__ void t2_walk_init(T2Walk& w, const int32_t* B, const int32_t* P, int nkeys, int t0, int t1) {
+  int lo = 0, hi = nkeys - 1;   // first key with P[key + 1] > t0
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (P[mid + 1] > t0) hi = mid;
+    else lo = mid + 1;
+  }
+  w.key = lo;
+  w.pos = B[lo] + (t0 - P[lo]) * T2_TILE;
+  w.end = B[lo + 1];
+  w.tleft = t1 - t0;
+}
+__device__ __forceinline__ void t2_advance(T2Walk& w, const int32_t* B) {
+  --w.tleft;
+  w.pos += T2_TILE;
+  if (w.pos >= w.end && w.tleft > 0) {
+    do ++w.key; while (B[w.key + 1] == B[w.key]);
+    w.pos = B[w.key];
+    w.end = B[w.key + 1];
+  }
+}
+
+// exact q = |U_k (x - mu_k)|^2, rows of U_k and mu_k read through the read-only path; the point is supplied
+// as 16-byte chunks by `ld4(c)`.  Same arithmetic and order as gauss_tc_exact_q.
+template <int D, typename LD4>
+__device__ __forceinline__ float gauss_tc2_exact_q_impl(const float* __restrict__ U, const float* __restrict__ mu, LD4 ld4) {
+  f32x2_t z2[D / 2];
+#pragma unroll
+  for (int c = 0; c < D / 4; ++c) {
+    const float4 v = ld4(c);
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mu) + c);
+    z2[2 * c] = f2_pack(v.x - m.x, v.y - m.y);
+    z2[2 * c + 1] = f2_pack(v.z - m.z, v.w - m.w);
+  }
+  float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const float* row = U + i * D;
+    f32x2_t acc = 0ull;
+    float4 uf[D / 4];   // the whole row first: the loads are independent, the FMA chain is not
+#pragma unroll
+    for (int c = i >> 2; c < D / 4; ++c) uf[c] = __ldg(reinterpret_cast<const float4*>(row) + c);
+#pragma unroll
+    for (int c = i >> 2; c < D / 4; ++c) {
+      acc = f2_fma(f2_pack(uf[c].x, uf[c].y), z2[2 * c], acc);
+      acc = f2_fma(f2_pack(uf[c].z, uf[c].w), z2[2 * c + 1], acc);
+    }
+    float lo, hi;
+    f2_unpack(acc, lo, hi);
+    const float y = lo + hi;
+    if (i & 1) q1 = fmaf(y, y, q1); else q0 = fmaf(y, y, q0);
+  }
+  return q0 + q1;
+}
+// the point = a row of X in global memory (the staged tile holds z = x - mu_pivot, not x)
+template <int D>
+__device__ __noinline__ float gauss_tc2_exact_q_row(const float* __restrict__ U, const float* __restrict__ mu,
+                                                    const float* __restrict__ xr) {
+  return gauss_tc2_exact_q_impl<D>(U, mu, [&](int c) { return __ldg(reinterpret_cast<const float4*>(xr) + c); });
+}
+
+// sample_log_cat_array! (utils.jl:19-31) over the m listed clusters (ascending indices ks[], values rs[]);
+// every unlisted cluster has weight exactly 0.  Mirrors dpmm_draw_inverse_cdf_masked.
+__device__ __forceinline__ int gauss_tc2_draw_list(const uint16_t* ks, float* rs, int m, int K, double u) {
+  float mx = -CUDART_INF_F;
+  for (int j = 0; j < m; ++j) mx = fmaxf(mx, rs[j]);
+  float s = 0.f;
+  for (int j = 0; j < m; ++j) {
+    const float e = expf(rs[j] - mx);
+    rs[j] = e;
+    s = __fadd_rn(s, e);
+  }
+  const bool s_regular = (s > 0.f) && (s < CUDART_INF_F);
+  float cw = 0.f;
+  for (int j = 0; j < m; ++j) {
+    const float e = rs[j];
+    const bool zero = (e < 1.17549435e-38f) && s_regular;
+    const float quo = __fdiv_rn(zero ? 1.f : e, s);
+    cw = __fadd_rn(cw, zero ? 0.f : quo);
+    rs[j] = cw;
+  }
+  const double t = u * (double)cw;
+  if (!(0.0 < t) && ks[0] != 0) return 0;   // cw_1 = w_1 = 0 is not < t: the walk stops at i = 1
+  for (int j = 0; j < m; ++j) {
+    const int k = ks[j];
+    if (k >= K - 1) break;
+    if (!((double)rs[j] < t)) return k;
+  }
+  return K - 1;
+}
+
+__device__ __forceinline__ float t2_sum8(const uint32_t* v) {
+  const f32x2_t p0 = f2_pack(__uint_as_float(v[0]), __uint_as_float(v[1]));
+  const f32x2_t p1 = f2_pack(__uint_as_float(v[2]), __uint_as_float(v[3]));
+  const f32x2_t p2 = f2_pack(__uint_as_float(v[4]), __uint_as_float(v[5]));
+  const f32x2_t p3 = f2_pack(__uint_as_float(v[6]), __uint_as_float(v[7]));
+  f32x2_t a0 = f2_fma(p0, p0, 0ull), a1 = f2_fma(p1, p1, 0ull);
+  a0 = f2_fma(p2, p2, a0);
+  a1 = f2_fma(p3, p3, a1);
+  float x0, x1, y0, y1;
+  f2_unpack(a0, x0, x1);
+  f2_unpack(a1, y0, y1);
+  return (x0 + x1) + (y0 + y1);
+}
+
+template <int D>
+__global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const GaussTc2Args a) {
+  extern __shared__ __align__(1024) uint8_t t2_smem[];
+  uint8_t* const smem = t2_smem;
+  const int K = a.K, KS = a.KS, nch = a.nch, n0 = a.n0, nkeys = a.nkeys;
+  const GaussTc2Smem L(D, K, KS, nch, nkeys);
+  constexpr int NS = D == 32 ? 4 : 3;
+  constexpr int PF = NS - 2;
+  constexpr int PIVF = D * D;                     // floats of a pivot image
+  uint8_t* stage0 = smem + L.stages;
+  float* pivsm = reinterpret_cast<float*>(smem + L.piv);
+  float* scrsm = reinterpret_cast<float*>(smem + L.scr);
+  float* aaug = reinterpret_cast<float*>(smem + L.aaug);
+  float4* ccfro = reinterpret_cast<float4*>(smem + L.ccfro);    // (log w_k - c_k, |U_k|_F, |screen rows|_F, -)
+  uint8_t* biassm = smem + L.bias;
+  float2* cfin = reinterpret_cast<float2*>(smem + L.cfin);      // (c_k, log w_k)
+  uint16_t* lists_all = reinterpret_cast<uint16_t*>(smem + L.lists);
+  float* rl_all = reinterpret_cast<float*>(smem + L.rlists);
+  uint16_t* pairs_all = reinterpret_cast<uint16_t*>(smem + L.pairs);
+  int* misc_all = reinterpret_cast<int*>(smem + L.misc);
+  int32_t* B = reinterpret_cast<int32_t*>(smem + L.bnd);
+  int32_t* P = reinterpret_cast<int32_t*>(smem + L.pre);
+  int* hs = reinterpret_cast<int*>(smem + L.hist);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* full = bars;              // [NS]    tile gathered into stage s
+  uint64_t* empty = bars + 4;         // [NS]    stage s released by the 128 epilogue threads of its tile
+  uint64_t* tfull = bars + 8;         // [2][2]  accumulator buffer (group, b) ready
+  uint64_t* tempty = bars + 12;       // [2][2]  ... drained
+  uint64_t* wdone = bars + 16;        // [2]     all MMAs of the group's previous tile retired
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 32);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) {
+      tc::mbar_init(&full[i], 64);
+      tc::mbar_init(&empty[i], 128);
+    }
+    for (int i = 0; i < 4; ++i) {
+      tc::mbar_init(&tfull[i], 1);
+      tc::mbar_init(&tempty[i], 128);
+    }
+    tc::mbar_init(&wdone[0], 1);
+    tc::mbar_init(&wdone[1], 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
+  for (int j = tid; j <= nkeys; j += T2_THREADS) B[j] = __ldg(a.seg_off + j);
+  {   // screen images: already in the shared-memory layout
+    const int nf4 = nch * (KS / 8 + 1) * 256;
+    const float4* src = reinterpret_cast<const float4*>(a.wscr);
+    float4* dst = reinterpret_cast<float4*>(scrsm);
+    for (int e = tid; e < nf4; e += T2_THREADS) dst[e] = __ldg(src + e);
+  }
+  for (int e = tid; e < 1024; e += T2_THREADS) aaug[e] = 0.f;
+  for (int k = tid; k < K; k += T2_THREADS) {
+    const float c = __ldg(a.cst + 3 * k), lw = __ldg(a.logw + k);
+    ccfro[k] = make_float4(lw - c, __ldg(a.fro + k), __ldg(a.fro8 + k), 0.f);
+    cfin[k] = make_float2(c, lw);
+    hs[k] = 0;
+  }
+  __syncthreads();
+  for (int r = tid; r < T2_TILE; r += T2_THREADS) {   // bias k-step A operand: (1, 1, 0, ...) per row
+    float* p = aaug + (r >> 3) * 64 + (r & 7) * 4;
+    p[0] = 1.f;
+    p[1] = 1.f;
+  }
+  if (warp == 0) {   // exclusive prefix of tiles per key
+    int carry = 0;
+    if (lane == 0) P[0] = 0;
+    for (int base = 0; base < nkeys; base += 32) {
+      const int j = base + lane;
+      int v = j < nkeys ? (B[j + 1] - B[j] + T2_TILE - 1) / T2_TILE : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+      }
+      if (j < nkeys) P[j + 1] = carry + v;
+      carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+  tc::fence_proxy_async();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int ntot = P[nkeys];
+  const int t0 = (int)(((int64_t)ntot * blockIdx.x) / gridDim.x);
+  const int t1 = (int)(((int64_t)ntot * (blockIdx.x + 1)) / gridDim.x);
+  const int nt = t1 - t0;
+
+  if (nt > 0) {
+    if (warp < 2) {
+      // =============================== control warp of group g ===============================
+      const int g = warp;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      float* pivs = pivsm + (size_t)g * PIVF;
+      float* biasg = reinterpret_cast<float*>(biassm + (size_t)g * L.bias_bytes);
+      const int bias_f4 = (int)(L.bias_bytes / 16);
+      const uint32_t pivs_a = tc::smem_u32(pivs), scr_a = tc::smem_u32(scrsm), bias_a = tc::smem_u32(biasg);
+      const uint64_t aaug_desc = tc::smem_desc_k_noswz(tc::smem_u32(aaug));
+      const uint32_t scr_stride = (uint32_t)L.scr_bytes;
+      T2Walk w;
+      t2_walk_init(w, B, P, nkeys, t0, t1);
+      uint32_t cc = 0;
+      int prevkey = -1, ntile_g = 0;
+      for (int li = 0; li < nt; ++li, t2_advance(w, B)) {
+        if ((li & 1) != g) continue;
+        const int s = li % NS;
+        const int key = min(w.key, K - 1);
+        tc::mbar_wait(&full[s], (li / NS) & 1);
+        tc::tc_fence_after();
+        const uint32_t st_a = tc::smem_u32(stage0 + (size_t)s * L.stage_bytes);
+        for (int c = 0; c < nch; ++c, ++cc) {
+          const int b = cc & 1;
+          tc::mbar_wait(&tempty[g * 2 + b], ((cc >> 1) & 1) ^ 1);   // epilogue drained this buffer
+          tc::tc_fence_after();
+          const uint32_t tmem_d = tmem_u + g * 256 + b * 128;
+          int col = 0;
+          if (c == 0) {
+            if (key != prevkey) {
+              // (at most the previous tile's MMAs are outstanding here: the buffer wait above ordered the rest)
+              if (ntile_g > 0) tc::mbar_wait(&wdone[g], (ntile_g - 1) & 1);
+              const float4* src = reinterpret_cast<const float4*>(a.wpiv + (size_t)key * PIVF);
+              float4* dst = reinterpret_cast<float4*>(pivs);
+              for (int e = lane; e < PIVF / 4; e += 32) dst[e] = __ldg(src + e);
+              const float4* bsrc = reinterpret_cast<const float4*>(a.wbias + (size_t)key * (bias_f4 * 4));
+              float4* bdst = reinterpret_cast<float4*>(biasg);
+              for (int e = lane; e < bias_f4; e += 32) bdst[e] = __ldg(bsrc + e);
+              tc::fence_proxy_async();
+              __syncwarp();
+              prevkey = key;
+            }
+            const uint32_t idp = tc::idesc_tf32(D);
+#pragma unroll
+            for (int ks = 0; ks < D / 8; ++ks) {
+              const uint64_t ad = tc::smem_desc_k128(st_a + (ks >> 2) * 16384) + (uint64_t)((ks & 3) * 2);
+              const uint64_t bd = tc::smem_desc_k_noswz(pivs_a + ks * (D * 32));
+              if (ks == 0) tc::umma_tf32_first_w(tmem_d, ad, bd, idp);
+              else tc::umma_tf32_acc_w(tmem_d, ad, bd, idp);
+            }
+            col = D;   // (no bias: the tile is centred by the pivot's own mean)
+          }
+          const int ncl = c == 0 ? min(K, n0) : min(16, K - n0 - (c - 1) * 16);
+          const uint32_t ids = tc::idesc_tf32((ncl * T2_R + 15) & ~15);
+          const uint32_t sc = scr_a + c * scr_stride;
+          const int nks = KS >> 3;
+          for (int ks = 0; ks < nks; ++ks) {
+            const int ka = (KS == D) ? ks : (D / 8 - 1);   // KS = 8: the last 8 features
+            const uint64_t ad = tc::smem_desc_k128(st_a + (ka >> 2) * 16384) + (uint64_t)((ka & 3) * 2);
+            const uint64_t bd = tc::smem_desc_k_noswz(sc + ks * 4096);
+            if (ks == 0) tc::umma_tf32_first_w(tmem_d + col, ad, bd, ids);
+            else tc::umma_tf32_acc_w(tmem_d + col, ad, bd, ids);
+          }
+          // bias k-step: B = compact [128 rows][4] table; its second k half (LBO = 128 B) aliases the next row
+          // group, finite values that meet the zero half of the A operand
+          tc::umma_tf32_acc_w(tmem_d + col, aaug_desc, tc::smem_desc_k_noswz2(bias_a + c * 2048, 128, 128), ids);
+          tc::umma_commit_w(&tfull[g * 2 + b]);
+        }
+        tc::umma_commit_w(&wdone[g]);
+        ++ntile_g;
+      }
+    } else if (warp < 10) {
+      // ======================= epilogue: bounds, candidates, refine, draw =======================
+      const int g = (warp - 2) >> 2;
+      const int gt = tid - 64 - g * 128;                     // thread index within the group
+      const int wq = gt >> 5;                                // warp within the group
+      const int row = ((warp & 3) << 5) | lane;              // TMEM lane == point within the tile
+      const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) << 5) << 16) + g * 256;
+      uint16_t* lists = lists_all + (size_t)g * T2_TILE * T2_CMAX;
+      float* rl = rl_all + (size_t)g * T2_TILE * T2_CMAX;
+      uint16_t* pairs = pairs_all + (size_t)g * T2_TILE * T2_CMAX;
+      int* misc = misc_all + g * 16;
+      uint16_t* mylist = lists + row * T2_CMAX;
+      float* myrl = rl + row * T2_CMAX;
+      T2Walk w;
+      t2_walk_init(w, B, P, nkeys, t0, t1);
+      uint32_t cc = 0;
+      int ncand_total = 0, npts_total = 0;
+      for (int li = 0; li < nt; ++li, t2_advance(w, B)) {
+        if ((li & 1) != g) continue;
+        const int s = li % NS;
+        const int key = min(w.key, K - 1);
+        const int npts = min(T2_TILE, w.end - w.pos);
+        const bool valid = row < npts;
+        const int32_t idx = valid ? __ldg(a.perm + w.pos + row) : 0;
+        const float* stage = reinterpret_cast<const float*>(stage0 + (size_t)s * L.stage_bytes);
+        tc::mbar_wait(&full[s], (li / NS) & 1);
+        float xnorm;
+        {
+          float xn = 0.f;
+#pragma unroll
+          for (int c = 0; c < D / 4; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(stage + (c >> 3) * 4096 + row * 32 + (((c & 7) ^ (row & 7)) << 2));
+            xn = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, xn))));
+          }
+          xnorm = sqrtf(xn) * (1.f / 512.f);   // 2^-9 |x|
+        }
+        float thr = 0.f;
+        bool weird = false;
+        int cnt = 0;
+        for (int c = 0; c < nch; ++c, ++cc) {
+          const int b = cc & 1;
+          tc::mbar_wait(&tfull[g * 2 + b], (cc >> 1) & 1);
+          tc::tc_fence_after();
+          const uint32_t taddr = tmem_row + b * 128;
+          int col = 0;
+          if (c == 0) {
+            float qp = 0.f;
+#pragma unroll
+            for (int h = 0; h < D / 32; ++h) {
+              uint32_t v[32];
+              tc::tmem_ld32(taddr + 32 * h, v);
+              tc::tmem_ld_wait();
+              qp += gauss_tc_screen_q(v);
+            }
+            const float4 cf = ccfro[key];
+            const float e = xnorm * cf.y;
+            float sq;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(fmaxf(qp, 0.f)));
+            const float dr = fmaf(1.01f * sq, e, fmaf(0.5f * e, e, 0.01f));   // |r~ - r| <= sqrt(q~) e + e^2/2
+            const float rt = fmaf(-0.5f, qp, cf.x);
+            weird = !(fabsf(rt) < CUDART_INF_F) || !(dr < CUDART_INF_F);
+            thr = (rt - dr) - T2_DELTA;
+            col = D;
+          }
+          const int ncl = c == 0 ? min(K, n0) : min(16, K - n0 - (c - 1) * 16);
+          const int kbase = c == 0 ? 0 : n0 + (c - 1) * 16;
+          for (int j0 = 0; j0 < ncl; j0 += 4) {
+            uint32_t v[32];
+            tc::tmem_ld32(taddr + col + j0 * T2_R, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int k = kbase + j0 + jj;
+              if (j0 + jj < ncl) {
+                const float q8 = t2_sum8(v + 8 * jj);
+                const float4 cf = ccfro[k];
+                float sq;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(fmaxf(q8, 0.f)));
+                const float lo = fmaxf(fmaf(-xnorm, cf.z, 0.99f * sq) - 0.01f, 0.f);   // |rows of U z| >= sqrt(q~8) - e
+                const float rhi = fmaf(-0.5f * lo, lo, cf.x) + 0.01f;          // upper bound of r_k
+                weird |= !(q8 < CUDART_INF_F);
+                if (rhi >= thr && k != key) {
+                  if (cnt < T2_CMAX) mylist[cnt] = (uint16_t)k;
+                  ++cnt;
+                }
+              }
+            }
+          }
+          tc::tc_fence_before();
+          tc::mbar_arrive(&tempty[g * 2 + b]);
+        }
+        bool multi = valid && !weird && cnt > 0 && cnt < T2_CMAX;
+        bool ovf = valid && (weird || cnt >= T2_CMAX);
+        if (multi) {   // insert the pivot at its place (the list is ascending)
+          int j = cnt;
+          while (j > 0 && mylist[j - 1] > key) {
+            mylist[j] = mylist[j - 1];
+            --j;
+          }
+          mylist[j] = (uint16_t)key;
+          ++cnt;
+        }
+        // ---- exact evaluation of the listed (point, cluster) pairs, spread over the 128 threads ----
+        if (group_any(g, multi)) {
+          const int mine = multi ? cnt : 0;
+          int inc = mine;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+          }
+          if (lane == 31) misc[wq] = inc;
+          group_barrier(g);
+          int off = inc - mine, total = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int t = misc[q];
+            if (q < wq) off += t;
+            total += t;
+          }
+          for (int j = 0; j < mine; ++j) pairs[off + j] = (uint16_t)((row << 3) | j);
+          group_barrier(g);
+          for (int p = gt; p < total; p += 128) {
+            const int pr = pairs[p], prow = pr >> 3, slot = pr & 7;
+            const int k = lists[prow * T2_CMAX + slot];
+            const int32_t pidx = __ldg(a.perm + w.pos + prow);
+            const float q = gauss_tc2_exact_q_row<D>(a.urows + (size_t)k * D * D, a.mu + (size_t)k * D, a.x + (size_t)pidx * D);
+            const float2 cf = cfin[k];
+            rl[prow * T2_CMAX + slot] = gauss_finish(cf.x, q, cf.y);
+            ++ncand_total;
+          }
+          group_barrier(g);
+        }
+        tc::mbar_arrive(&empty[s]);   // the stage can be refilled now
+        // ---- draw ----
+        if (valid) {
+          int lab = key;
+          if (multi) {
+            bool bad = false;
+            for (int j = 0; j < cnt; ++j) bad |= (myrl[j] != myrl[j]);
+            if (bad) {
+              ovf = true;
+            } else if (a.final_iter) {   // first maximum among the candidates (a non-candidate is > 30 below it)
+              float bv = -CUDART_INF_F;
+              lab = mylist[0];
+              for (int j = 0; j < cnt; ++j)
+                if (myrl[j] > bv) {
+                  bv = myrl[j];
+                  lab = mylist[j];
+                }
+            } else {
+              const double u = dpmm_uniform(a.u_inj, idx, a.seed, DPMM_STREAM_LABEL, a.call, (uint64_t)(a.goff + idx));
+              lab = gauss_tc2_draw_list(mylist, myrl, cnt, K, u);
+            }
+          } else if (!ovf) {
+            // utils.jl:29 stops at i = 1 for the uniform u == 0; reproduced for injected uniforms only
+            // (a Philox uniform is 0 with probability 2^-53 per draw), see kernels_gauss_tc.cuh
+            if (a.u_inj != nullptr && lab > 0 && !a.final_iter && a.u_inj[idx] == 0.0) lab = 0;
+          }
+          if (ovf) {
+            a.ovf_list[atomicAdd(a.ovf_count, 1)] = idx;
+          } else {
+            a.labels[idx] = lab;
+            atomicAdd(&hs[lab], 1);
+          }
+          ++npts_total;
+        }
+      }
+      if (a.stats != nullptr) {
+        atomicAdd(&a.stats[0], npts_total);
+        atomicAdd(&a.stats[1], ncand_total);
+      }
+    } else {
+      // =============================== gather warps ===============================
+      const int t64 = tid - 320;
+      constexpr int CPR = D / 4;            // 16-byte chunks per row
+      constexpr int RS = 64 / CPR;          // rows covered by the 64 threads per pass
+      constexpr int NJ = T2_TILE / RS;      // passes per tile
+      const int c = t64 % CPR, r0 = t64 / CPR;
+      T2Walk wl, wc;
+      t2_walk_init(wl, B, P, nkeys, t0, t1);
+      wc = wl;
+      int ckey = -1;
+      float4 cen = make_float4(0.f, 0.f, 0.f, 0.f);
+      // the indices of a tile are loaded one tile ahead of the copies that need them: a perm miss is a DRAM
+      // round trip, which must not sit between "stage free" and "gather issued"
+      int32_t idx[NJ];
+      auto load_idx = [&]() {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int p = wl.pos + r0 + RS * j;
+          idx[j] = p < wl.end ? __ldg(a.perm + p) : -1;
+        }
+      };
+      auto issue = [&](int s) {
+        uint8_t* dst0 = stage0 + (size_t)s * L.stage_bytes + (c >> 3) * 16384;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int r = r0 + RS * j;
+          const bool ok = idx[j] >= 0;
+          cp_async16(dst0 + r * 128 + (((c & 7) ^ (r & 7)) << 4), a.x + (size_t)(ok ? idx[j] : 0) * D + 4 * c, ok ? 16 : 0);
+        }
+      };
+      load_idx();
+#pragma unroll
+      for (int q = 0; q < PF; ++q) {
+        if (q < nt) {
+          issue(q % NS);
+          t2_advance(wl, B);
+          if (q + 1 < nt) load_idx();
+        }
+        cp_async_commit();
+      }
+      for (int li = 0; li < nt; ++li) {
+        cp_async_wait_group<PF - 1>();
+        {   // centre this thread's chunks of the landed tile by the pivot's mean (rows beyond the tile stay zero)
+          const int key = min(wc.key, K - 1);
+          if (key != ckey) {
+            ckey = key;
+            cen = __ldg(reinterpret_cast<const float4*>(a.mu + (size_t)key * D) + c);
+          }
+          uint8_t* base = stage0 + (size_t)(li % NS) * L.stage_bytes + (c >> 3) * 16384;
+          const int nrow = wc.end - wc.pos;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const int r = r0 + RS * j;
+            float4* q = reinterpret_cast<float4*>(base + r * 128 + (((c & 7) ^ (r & 7)) << 4));
+            float4 v = *q;
+            if (r < nrow) {
+              v.x -= cen.x; v.y -= cen.y; v.z -= cen.z; v.w -= cen.w;
+              *q = v;
+            }
+          }
+          t2_advance(wc, B);
+        }
+        tc::fence_proxy_async();
+        tc::mbar_arrive(&full[li % NS]);
+        const int nx = li + PF;
+        if (nx < nt) {
+          tc::mbar_wait(&empty[nx % NS], ((nx / NS) & 1) ^ 1);
+          issue(nx % NS);
+          t2_advance(wl, B);
+          if (nx + 1 < nt) load_idx();
+        }
+        cp_async_commit();
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+  for (int k = tid; k < K; k += T2_THREADS)
+    if (hs[k] != 0) atomicAdd(&a.hist[k], hs[k]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Overflow points of the kernel above (and any list of points): the full K-cluster evaluation, one warp
+// per point, lanes <-> clusters, then the reference's draw over the whole row (NaN rules included).
+// ------------------------------------------------------------------------------------------------
+struct GaussListArgs {
+  const float* x;
+  int K;
+  const int32_t* list;
+  const int32_t* count;
+  const float* urows;
+  const float* mu;
+  const float* cst;
+  const float* logw;
+  int32_t* labels;
+  int32_t* hist;
+  const double* u_inj;
+  uint64_t seed;
+  uint32_t call;
+  int64_t goff;
+  int final_iter;
+  int32_t* stats;          // optional [2]: [1] += K per listed point
+};
+
+template <int D>
+__global__ void __launch_bounds__(256) gauss_label_list_kernel(const GaussListArgs a) {
+  extern __shared__ float gl_rs[];   // [8][K]
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const int nlist = *a.count;
+  float* rs = gl_rs + (size_t)wl * a.K;
+  for (int e = blockIdx.x * 8 + wl; e < nlist; e += gridDim.x * 8) {
+    const int32_t idx = a.list[e];
+    const float* xr = a.x + (size_t)idx * D;
+    for (int k = lane; k < a.K; k += 32) {
+      const float q = gauss_tc2_exact_q_impl<D>(a.urows + (size_t)k * D * D, a.mu + (size_t)k * D,
+                                                [&](int c) { return __ldg(reinterpret_cast<const float4*>(xr) + c); });
+      rs[k] = gauss_finish(__ldg(a.cst + 3 * k), q, __ldg(a.logw + k));
+    }
+    __syncwarp();
+    if (lane == 0) {
+      int lab;
+      if (a.final_iter) {
+        lab = dpmm_draw_argmax(rs, 1, a.K);
+      } else {
+        const double u = dpmm_uniform(a.u_inj, idx, a.seed, DPMM_STREAM_LABEL, a.call, (uint64_t)(a.goff + idx));
+        lab = dpmm_draw_inverse_cdf(rs, 1, a.K, u);
+      }
+      a.labels[idx] = lab;
+      atomicAdd(a.hist + lab, 1);
+      if (a.stats != nullptr) atomicAdd(&a.stats[1], a.K);
+    }
+    __syncwarp();
+  }
+}

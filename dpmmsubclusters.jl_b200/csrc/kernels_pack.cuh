@@ -25,6 +25,14 @@ struct NiwPackArgs {
   float* ss_w;             // [K][2][D][D] rows of U of the left / right distributions
   float* ss_b;             // [K][2][D]    U_s (mu_s - c_k)
   float* ss_c;             // [K][D]       c_k = cluster mean rounded to 12 significant bits
+  // second-generation tensor-core label path (kernels_gauss_tc2.cuh), or t2_piv == nullptr:
+  // operand images in the un-swizzled K-major core-matrix layout [k-step][row / 8][k half][row % 8][4]
+  float* t2_piv;           // [K][D*D]  all D rows of U_k as D/8 k-step slabs
+  float* t2_scr;           // [nch][(KS/8) * 1024]  8 screen rows of every cluster, 16 clusters per chunk
+  float* t2_u;             // [K][D][D] rows of U_k (exact refinement, bias tables)
+  float* t2_fro8;          // [K] Frobenius norm of the 8 screen rows
+  int t2_KS;               // features of the screen: D (first 8 rows of U_k) or 8 (last 8 rows = last 8 features)
+  int t2_n0;               // clusters in chunk 0 (behind the pivot's D columns)
 };
 
 // The centre every point of cluster k is shifted by before it meets the tensor core: the cluster mean
@@ -93,9 +101,9 @@ __global__ void __launch_bounds__(NIW_PACK_THREADS) niw_pack_kernel(const NiwPac
     const float log2pi = 1.8378770664093453f;   // Float32(log(2pi)), mv_gaussian.jl:24
     a.cst[t] = __fmul_rn(__fadd_rn(__fmul_rn((float)(D * D), log2pi), a.logdet[t]), 0.5f);
   }
-  if (a.tc_w != nullptr && t % 3 == 0) {
+  if ((a.tc_w != nullptr || a.t2_piv != nullptr) && t % 3 == 0) {
     const int k = t / 3;
-    for (int e = tid; e < D * D; e += NT) {
+    if (a.tc_w != nullptr) for (int e = tid; e < D * D; e += NT) {
       const int i = e / D, j = e - i * D;
       a.tc_w[((size_t)k * D + i) * D + j] = (j >= i) ? (ok ? (float)Ls[j * LD + i] : nanv) : 0.f;   // U[i][j] = L[j][i]
     }
@@ -118,6 +126,36 @@ __global__ void __launch_bounds__(NIW_PACK_THREADS) niw_pack_kernel(const NiwPac
     __syncthreads();
     if (tid == 0) a.tc_fro[k] = (float)sqrt(fro_s[0] + fro_s[1]);
   }
+  if (a.t2_piv != nullptr && t % 3 == 0) {
+    const int k = t / 3;
+    auto uval = [&](int i, int j) { return (j >= i) ? (ok ? (float)Ls[j * LD + i] : nanv) : 0.f; };   // U[i][j] = L[j][i]
+    float* piv = a.t2_piv + (size_t)k * (D * D);
+    float* urow = a.t2_u + (size_t)k * D * D;
+    for (int e = tid; e < D * D; e += NT) {
+      const int i = e / D, j = e - i * D;
+      const float u = uval(i, j);
+      urow[e] = u;
+      piv[(j >> 3) * (D * 8) + (i >> 3) * 64 + ((j & 7) >> 2) * 32 + (i & 7) * 4 + (j & 3)] = u;
+    }
+    const int KS = a.t2_KS;
+    const int row0 = (KS == D) ? 0 : D - 8, f0 = (KS == D) ? 0 : D - 8;
+    const int ch = k < a.t2_n0 ? 0 : 1 + (k - a.t2_n0) / 16, rg = k < a.t2_n0 ? k : (k - a.t2_n0) % 16;
+    float* scr = a.t2_scr + (size_t)ch * (KS / 8) * 1024;
+    for (int e = tid; e < 8 * KS; e += NT) {
+      const int r = e / KS, jj = e - r * KS;
+      scr[(jj >> 3) * 1024 + rg * 64 + ((jj & 7) >> 2) * 32 + r * 4 + (jj & 3)] = uval(row0 + r, f0 + jj);
+    }
+    if (tid < 32) {   // |screen rows|_F
+      double f8 = 0.0;
+      for (int e = tid; e < 8 * D; e += 32) {
+        const float u = uval(row0 + e / D, e % D);
+        f8 += (double)u * (double)u;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) f8 += __shfl_xor_sync(0xffffffffu, f8, o);
+      if (tid == 0) a.t2_fro8[k] = (float)sqrt(f8);
+    }
+  }
   if (a.ss_w != nullptr) {
     const int k = t / 3, side = t % 3 - 1;
     const float* mu0 = a.mu + (size_t)(3 * k) * D;
@@ -138,5 +176,43 @@ __global__ void __launch_bounds__(NIW_PACK_THREADS) niw_pack_kernel(const NiwPac
         a.ss_b[((size_t)k * 2 + side) * D + i] = (float)bi;
       }
     }
+  }
+}
+
+// Bias tables of the second-generation label kernel.  Its tiles are centred by the pivot's mean,
+// z = x - mu_p, so the screen rows of cluster k see  U_k (x - mu_k) = U_k z - U_k (mu_k - mu_p):
+// one table per pivot p with b[k][r] = (U_k (mu_k - mu_p))_{row0 + r}, Float64 accumulation, stored as the
+// compact B operand of the bias k-step: [chunk][128 rows][4] = (-b_hi, -b_lo, 0, 0) with b_hi TF32-exact.
+// One CTA per pivot.
+struct NiwT2BiasArgs {
+  int D, K, KS, n0, nch;
+  const float* u;      // [K][D][D]
+  const float* mu;     // [K][D]
+  float* bias;         // [K][nch * 512 + 32]
+};
+__global__ void __launch_bounds__(256) niw_t2_bias_kernel(const NiwT2BiasArgs a) {
+  const int p = blockIdx.x, D = a.D, K = a.K;
+  const int row0 = (a.KS == D) ? 0 : D - 8;
+  const int stride = a.nch * 512 + 32;
+  float* out = a.bias + (size_t)p * stride;
+  for (int e = threadIdx.x; e < stride; e += blockDim.x) out[e] = 0.f;
+  __syncthreads();
+  const float* mup = a.mu + (size_t)p * D;
+  for (int e = threadIdx.x; e < K * 8; e += blockDim.x) {
+    const int k = e >> 3, r = e & 7, i = row0 + r;
+    const float* urow = a.u + ((size_t)k * D + i) * D;
+    const float* muk = a.mu + (size_t)k * D;
+    double b = 0.0;
+    for (int j = i; j < D; ++j) b += (double)urow[j] * ((double)muk[j] - (double)mup[j]);
+    const float bf = (float)b;
+    uint32_t ub = __float_as_uint(bf);
+    ub += 0xFFFu + ((ub >> 13) & 1u);
+    ub &= 0xFFFFE000u;                                // round to TF32 (10 explicit mantissa bits)
+    const float hi = (bf == bf && fabsf(bf) < CUDART_INF_F) ? __uint_as_float(ub) : bf;
+    const float lo = bf - hi;
+    const int ch = k < a.n0 ? 0 : 1 + (k - a.n0) / 16, rg = k < a.n0 ? k : (k - a.n0) % 16;
+    float* q = out + ch * 512 + (rg * 8 + r) * 4;
+    q[0] = -hi;
+    q[1] = -lo;
   }
 }

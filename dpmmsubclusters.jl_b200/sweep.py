@@ -202,10 +202,12 @@ class GpuSweep:
         self._ck(self.lib.dpmm_debug_loglik(self.h, int(which), _ptr(out, C.c_float)))
         return np.ascontiguousarray(out.T)  # n x cols, as the reference's parr
 
-    def tc_stats(self):
-        out = np.zeros(2, np.int64)
+    def tc_stats(self, overflow=False):
+        """(points drawn, exact cluster evaluations[, points finished by the overflow kernel]) of the last
+        sample_labels on the tensor-core path (needs DPMM_TC_STATS=1)."""
+        out = np.zeros(3, np.int64)
         self._ck(self.lib.dpmm_debug_tc_stats(self.h, _ptr(out, C.c_int64)))
-        return int(out[0]), int(out[1])
+        return (int(out[0]), int(out[1]), int(out[2])) if overflow else (int(out[0]), int(out[1]))
 
     def fused_stats(self):
         """(fused sub-label+statistics launches, suff_stats calls served from them, exact recomputations)."""

@@ -147,8 +147,10 @@ int dpmm_set_uniforms(dpmm_ctx* ctx, const double* u_label, const double* u_sub,
  * each point's current label. */
 int dpmm_debug_loglik(dpmm_ctx* ctx, int32_t which, float* out);
 /* Tensor-core label path diagnostics (set DPMM_TC_STATS=1): out[0] = points drawn, out[1] = exact
- * (FP32-refined) cluster evaluations of the last dpmm_sample_labels; both 0 when the FMA path ran. */
-int dpmm_debug_tc_stats(dpmm_ctx* ctx, int64_t* out2);
+ * (FP32-refined) cluster evaluations of the last dpmm_sample_labels (both 0 when the FMA path ran),
+ * out[2] = points of that call finished by the full-K overflow kernel (NaN screen values or more than
+ * 7 candidate clusters; D = 32 / 64 path). */
+int dpmm_debug_tc_stats(dpmm_ctx* ctx, int64_t* out3);
 /* Fused sub-label + statistics path diagnostics (NIW, D = 32): out[0] = launches of the fused kernel by
  * dpmm_sample_sublabels, out[1] = dpmm_suff_stats calls served from its accumulators, out[2] = calls that
  * fell back to the separate statistics kernel because a run lay far from its cluster's centre. */

@@ -71,6 +71,49 @@ def test_niw_tensor_core_refine_path_with_overlapping_clusters(pkg, spread, K, n
         assert ncand > npts          # the refine path really was exercised
 
 
+TC2_CASES = [  # (D, K, n, spread)
+    (32, 20, 20000, 10.0),    # C2 shape, well separated: almost every point is decided by its pivot
+    (32, 20, 20000, 2.5),     # moderately separated: several candidates per point
+    (32, 40, 30000, 10.0),    # K > 23 (the limit of the first-generation kernel)
+    (32, 100, 20000, 10.0),   # screen over the last 8 features (KS = 8), 7 chunks
+    (32, 200, 30000, 10.0),
+    (32, 3, 300, 2.5),        # ragged tiles, more tiles than points per cluster
+    (32, 12, 20000, 0.3),     # everything overlaps: the overflow kernel decides
+    (64, 12, 6000, 10.0),
+    (64, 100, 20000, 10.0),   # config C5 shape
+    (64, 30, 10000, 1.0),
+]
+
+
+@pytest.mark.parametrize("D,K,n,spread", TC2_CASES)
+def test_niw_tc2_label_kernel_from_warm_labels(pkg, D, K, n, spread):
+    """D = 32 / 64: gauss_label_tc2_kernel walks the points in the order of their CURRENT labels and uses the
+    tile's old cluster as the pivot.  compare_sweeps(warm=True) starts from the labels of an argmax pass,
+    as an iteration deep inside a run would, so the pivot / partial-screen / exact-candidate path decides
+    the draws (cold starts, covered by test_niw_full_sweep_parity, mostly take the overflow kernel)."""
+    case = make_niw_case(D, K, n, seed=1000 + D + K, spread=spread)
+    for final in (False, True):
+        g = pkg.GpuSweep(case["x"], pkg.NIW, seed=7)
+        o = O.OracleSweep(case["x"], O.NIW, seed=7)
+        rep = compare_sweeps(g, o, case, np.random.default_rng(K + D), final=final, warm=True)
+        g.close()
+    os.environ["DPMM_TC_STATS"] = "1"
+    try:
+        g = pkg.GpuSweep(case["x"], pkg.NIW, seed=7)
+        set_params(g, case)
+        g.sample_labels(True)
+        g.sample_labels(False)
+        npts, ncand, novf = g.tc_stats(overflow=True)
+        g.close()
+    finally:
+        os.environ.pop("DPMM_TC_STATS")
+    assert npts == n, "the tensor-core path did not run"
+    print(f"D={D} K={K} n={n} spread={spread}: {rep}; exact evaluations per point {ncand / npts:.3f}, "
+          f"overflow points {novf} ({novf / npts:.4f})")
+    if spread >= 10.0:
+        assert novf <= 0.02 * npts, "well separated clusters must be decided by the pivot path"
+
+
 @pytest.mark.parametrize("spread,K,n", [(2.5, 20, 30000), (10.0, 20, 100000), (10.0, 3, 40000)])
 def test_niw_fused_sublabel_statistics_kernel(pkg, spread, K, n):
     """D=32: dpmm_sample_sublabels runs niw_substats_tc_kernel (sub-label draw + left/right statistics in one

@@ -116,16 +116,22 @@ def check_stats(gpu, ora, prior_kind, what):
     return float(worst)
 
 
-def compare_sweeps(g, o, case, rng, final=False):
+def compare_sweeps(g, o, case, rng, final=False, warm=False):
     """Drive the GPU sweep `g` and the oracle `o` through one full iteration on the same injected
     randomness and compare every stage.  After each stage the GPU state is copied into the oracle so
-    that a near-tie at one stage cannot cascade into the next comparison."""
+    that a near-tie at one stage cannot cascade into the next comparison.
+    warm: first give both sides the labels of an argmax pass, as an iteration deep inside a run would find
+    them (the D = 32 / 64 tensor-core label kernel walks the points in the order of the current labels and
+    uses each tile's old cluster as its pivot; cold = every point starts in cluster 1)."""
     n, K = case["n"], case["K"]
     u_label, u_sub = rng.random(n), rng.random(n)
     bits = rng.integers(0, 2, n).astype(np.uint8)
     for s in (g, o):
         s.set_uniforms(u_label, u_sub, bits)
         set_params(s, case)
+    if warm:
+        g.sample_labels(True); o.sample_labels(True)
+        o.set_labels(g.get_labels())
     rep = {}
     # stage 1: log-likelihood matrices (labels phase)
     LLo = o.debug_loglik(0)
