@@ -752,7 +752,7 @@ static int launch_label_tc2(dpmm_ctx* ctx, int final_iter, int nkeys) {
   const int64_t grid = std::min<int64_t>((ctx->n + T2_TILE - 1) / T2_TILE, (int64_t)ctx->sm_count);
   {
     KernelTimer kt(ctx, TK_LABEL);
-    gauss_label_tc2_kernel<D><<<(unsigned)grid, T2_THREADS, sm, ctx->stream>>>(a);
+    gauss_label_tc2_kernel<D><<<(unsigned)grid, T2_THREADS(D), sm, ctx->stream>>>(a);
     CK(cudaGetLastError());
   }
   // the (normally empty) overflow list: points with a NaN / Inf screen value or more than 7 candidates

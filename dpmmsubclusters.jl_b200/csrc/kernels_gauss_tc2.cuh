@@ -36,17 +36,32 @@
 // Warp roles (384 threads, one CTA per SM, contiguous range of the tile sequence per CTA):
 //   warps 0/1   control of point-group 0/1 (pivot image staging + tcgen05.mma issue)
 //   warps 2-5 / 6-9  epilogue (TMEM lane = point) of group 0/1, alternate tiles
-//   warps 10-11 gather: cp.async of the 128 rows of a tile into a 128B-swizzled K-major stage ring
+//   warps 10-13 gather: cp.async of the 128 rows of a tile into a 128B-swizzled K-major stage ring
 #pragma once
 #include "kernels_gauss_tc.cuh"
 #include "kernels_stats.cuh"   // cp_async16 / commit / wait_group
 
 #define T2_TILE 128
-#define T2_THREADS 384
+#define T2_PRODUCERS(D) ((D) == 32 ? 128 : 64)   // gather threads (warps 10-13 / 10-11): D = 64 needs the registers
+#define T2_THREADS(D) (320 + T2_PRODUCERS(D))
 #define T2_CMAX 8          // exact evaluations per point handled in the kernel (pivot included)
 #define T2_R 8             // screen rows per cluster
 #define T2_DELTA 30.0f
 #define T2_MAX_K 256        // bias tables are K x K
+#ifndef T2_NS32
+#define T2_NS32 4          // stage ring at D = 32 (D = 64: 3)
+#endif
+#ifndef T2_ABL
+#define T2_ABL 0           // development: ablation bits (timing experiments only, results are wrong)
+#endif
+#ifndef T2_PROF
+#define T2_PROF 0          // 1: CTA 0 prints the cycles its role leaders spent in each wait (development only)
+#endif
+#if T2_PROF
+#define T2_WAIT(slot, stmt) do { const long long t__ = clock64(); stmt; prof[slot] += clock64() - t__; } while (0)
+#else
+#define T2_WAIT(slot, stmt) do { stmt; } while (0)
+#endif
 
 struct GaussTc2Args {
   const float* x;          // [n][D]
@@ -79,9 +94,9 @@ struct GaussTc2Args {
 struct GaussTc2Smem {
   int ns, pf;
   size_t stage_bytes, piv_bytes, scr_bytes, bias_bytes;
-  size_t stages, piv, scr, bias, aaug, ccfro, cfin, lists, rlists, pairs, misc, bnd, pre, hist, bars, total;
+  size_t stages, piv, scr, bias, aaug, ccfro, scrc, cfin, lists, rlists, pairs, misc, bnd, pre, hist, bars, total;
   __host__ __device__ GaussTc2Smem(int D, int K, int KS, int nch, int nkeys) {
-    ns = D == 32 ? 4 : 3;
+    ns = D == 32 ? T2_NS32 : 3;
     pf = ns - 2;
     stage_bytes = (size_t)T2_TILE * D * 4;
     piv_bytes = (size_t)(D * D) * 4;
@@ -93,7 +108,9 @@ struct GaussTc2Smem {
     scr = o;     o += (size_t)nch * scr_bytes;
     bias = o;    o += 2 * bias_bytes;
     aaug = o;    o += 4096;
-    ccfro = o;   o += (size_t)K * 16;
+    ccfro = o;   o += (size_t)K * 8;
+    o = (o + 15) & ~(size_t)15;
+    scrc = o;    o += (size_t)(nch * 8 + 8) * 16;
     cfin = o;    o += (size_t)K * 8;
     o = (o + 15) & ~(size_t)15;
     lists = o;   o += 2 * T2_TILE * T2_CMAX * 2;
@@ -223,41 +240,43 @@ __device__ __forceinline__ float t2_sum8(const uint32_t* v) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const GaussTc2Args a) {
+__global__ void __launch_bounds__(T2_THREADS(D), 1) gauss_label_tc2_kernel(const GaussTc2Args a) {
   extern __shared__ __align__(1024) uint8_t t2_smem[];
   uint8_t* const smem = t2_smem;
   const int K = a.K, KS = a.KS, nch = a.nch, n0 = a.n0, nkeys = a.nkeys;
   const GaussTc2Smem L(D, K, KS, nch, nkeys);
-  constexpr int NS = D == 32 ? 4 : 3;
+  constexpr int NS = D == 32 ? T2_NS32 : 3;
+  [[maybe_unused]] long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  [[maybe_unused]] const long long t_start = T2_PROF ? clock64() : 0;
   constexpr int PF = NS - 2;
   constexpr int PIVF = D * D;                     // floats of a pivot image
   uint8_t* stage0 = smem + L.stages;
   float* pivsm = reinterpret_cast<float*>(smem + L.piv);
   float* scrsm = reinterpret_cast<float*>(smem + L.scr);
   float* aaug = reinterpret_cast<float*>(smem + L.aaug);
-  float4* ccfro = reinterpret_cast<float4*>(smem + L.ccfro);    // (log w_k - c_k, |U_k|_F, |screen rows|_F, -)
+  float2* ccfro = reinterpret_cast<float2*>(smem + L.ccfro);    // (log w_k - c_k, |U_k|_F)
+  float4* scrc = reinterpret_cast<float4*>(smem + L.scrc);      // by slot pair (A, B): (4.0816 cc_A, 4.0816 cc_B, |rows_A|_F, |rows_B|_F); pad: (-inf, 0)
   uint8_t* biassm = smem + L.bias;
   float2* cfin = reinterpret_cast<float2*>(smem + L.cfin);      // (c_k, log w_k)
   uint16_t* lists_all = reinterpret_cast<uint16_t*>(smem + L.lists);
   float* rl_all = reinterpret_cast<float*>(smem + L.rlists);
   uint16_t* pairs_all = reinterpret_cast<uint16_t*>(smem + L.pairs);
-  int* misc_all = reinterpret_cast<int*>(smem + L.misc);
   int32_t* B = reinterpret_cast<int32_t*>(smem + L.bnd);
   int32_t* P = reinterpret_cast<int32_t*>(smem + L.pre);
   int* hs = reinterpret_cast<int*>(smem + L.hist);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* full = bars;              // [NS]    tile gathered into stage s
-  uint64_t* empty = bars + 4;         // [NS]    stage s released by the 128 epilogue threads of its tile
-  uint64_t* tfull = bars + 8;         // [2][2]  accumulator buffer (group, b) ready
-  uint64_t* tempty = bars + 12;       // [2][2]  ... drained
-  uint64_t* wdone = bars + 16;        // [2]     all MMAs of the group's previous tile retired
+  uint64_t* empty = bars + 8;         // [NS]    stage s released by the 128 epilogue threads of its tile
+  uint64_t* tfull = bars + 16;        // [2][2]  accumulator buffer (group, b) ready
+  uint64_t* tempty = bars + 20;       // [2][2]  ... drained
+  uint64_t* wdone = bars + 24;        // [2]     all MMAs of the group's previous tile retired
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 32);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
-      tc::mbar_init(&full[i], 64);
+      tc::mbar_init(&full[i], T2_PRODUCERS(D));
       tc::mbar_init(&empty[i], 128);
     }
     for (int i = 0; i < 4; ++i) {
@@ -269,22 +288,29 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const Ga
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
-  for (int j = tid; j <= nkeys; j += T2_THREADS) B[j] = __ldg(a.seg_off + j);
+  for (int j = tid; j <= nkeys; j += T2_THREADS(D)) B[j] = __ldg(a.seg_off + j);
   {   // screen images: already in the shared-memory layout
     const int nf4 = nch * (KS / 8 + 1) * 256;
     const float4* src = reinterpret_cast<const float4*>(a.wscr);
     float4* dst = reinterpret_cast<float4*>(scrsm);
-    for (int e = tid; e < nf4; e += T2_THREADS) dst[e] = __ldg(src + e);
+    for (int e = tid; e < nf4; e += T2_THREADS(D)) dst[e] = __ldg(src + e);
   }
-  for (int e = tid; e < 1024; e += T2_THREADS) aaug[e] = 0.f;
-  for (int k = tid; k < K; k += T2_THREADS) {
+  for (int e = tid; e < 1024; e += T2_THREADS(D)) aaug[e] = 0.f;
+  for (int k = tid; k < K; k += T2_THREADS(D)) {
     const float c = __ldg(a.cst + 3 * k), lw = __ldg(a.logw + k);
-    ccfro[k] = make_float4(lw - c, __ldg(a.fro + k), __ldg(a.fro8 + k), 0.f);
+    ccfro[k] = make_float2(lw - c, __ldg(a.fro + k));
     cfin[k] = make_float2(c, lw);
     hs[k] = 0;
   }
+  for (int e = tid; e < nch * 16 + 16; e += T2_THREADS(D)) {   // screen slot e: chunk 0 holds n0 clusters, the others 16
+    const int ch = e >> 4, j = e & 15;
+    const int k = ch == 0 ? (j < n0 ? j : K) : n0 + (ch - 1) * 16 + j;
+    float* q = reinterpret_cast<float*>(scrc + (e >> 1)) + (e & 1);
+    q[0] = k < K ? 4.0816f * (__ldg(a.logw + k) - __ldg(a.cst + 3 * k)) : -CUDART_INF_F;
+    q[2] = k < K ? __ldg(a.fro8 + k) : 0.f;
+  }
   __syncthreads();
-  for (int r = tid; r < T2_TILE; r += T2_THREADS) {   // bias k-step A operand: (1, 1, 0, ...) per row
+  for (int r = tid; r < T2_TILE; r += T2_THREADS(D)) {   // bias k-step A operand: (1, 1, 0, ...) per row
     float* p = aaug + (r >> 3) * 64 + (r & 7) * 4;
     p[0] = 1.f;
     p[1] = 1.f;
@@ -333,19 +359,19 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const Ga
         if ((li & 1) != g) continue;
         const int s = li % NS;
         const int key = min(w.key, K - 1);
-        tc::mbar_wait(&full[s], (li / NS) & 1);
+        T2_WAIT(0, tc::mbar_wait(&full[s], (li / NS) & 1));
         tc::tc_fence_after();
         const uint32_t st_a = tc::smem_u32(stage0 + (size_t)s * L.stage_bytes);
         for (int c = 0; c < nch; ++c, ++cc) {
           const int b = cc & 1;
-          tc::mbar_wait(&tempty[g * 2 + b], ((cc >> 1) & 1) ^ 1);   // epilogue drained this buffer
+          T2_WAIT(1, tc::mbar_wait(&tempty[g * 2 + b], ((cc >> 1) & 1) ^ 1));   // epilogue drained this buffer
           tc::tc_fence_after();
           const uint32_t tmem_d = tmem_u + g * 256 + b * 128;
           int col = 0;
           if (c == 0) {
             if (key != prevkey) {
               // (at most the previous tile's MMAs are outstanding here: the buffer wait above ordered the rest)
-              if (ntile_g > 0) tc::mbar_wait(&wdone[g], (ntile_g - 1) & 1);
+              if (ntile_g > 0) T2_WAIT(2, tc::mbar_wait(&wdone[g], (ntile_g - 1) & 1));
               const float4* src = reinterpret_cast<const float4*>(a.wpiv + (size_t)key * PIVF);
               float4* dst = reinterpret_cast<float4*>(pivs);
               for (int e = lane; e < PIVF / 4; e += 32) dst[e] = __ldg(src + e);
@@ -395,7 +421,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const Ga
       uint16_t* lists = lists_all + (size_t)g * T2_TILE * T2_CMAX;
       float* rl = rl_all + (size_t)g * T2_TILE * T2_CMAX;
       uint16_t* pairs = pairs_all + (size_t)g * T2_TILE * T2_CMAX;
-      int* misc = misc_all + g * 16;
       uint16_t* mylist = lists + row * T2_CMAX;
       float* myrl = rl + row * T2_CMAX;
       T2Walk w;
@@ -410,36 +435,95 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const Ga
         const bool valid = row < npts;
         const int32_t idx = valid ? __ldg(a.perm + w.pos + row) : 0;
         const float* stage = reinterpret_cast<const float*>(stage0 + (size_t)s * L.stage_bytes);
-        tc::mbar_wait(&full[s], (li / NS) & 1);
+        T2_WAIT(0, tc::mbar_wait(&full[s], (li / NS) & 1));
+        [[maybe_unused]] const long long tp0 = T2_PROF ? clock64() : 0;
         float xnorm;
         {
-          float xn = 0.f;
+          f32x2_t nn0 = 0ull, nn1 = 0ull;
 #pragma unroll
           for (int c = 0; c < D / 4; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(stage + (c >> 3) * 4096 + row * 32 + (((c & 7) ^ (row & 7)) << 2));
-            xn = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, xn))));
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(stage + (c >> 3) * 4096 + row * 32 + (((c & 7) ^ (row & 7)) << 2));
+            nn0 = f2_fma(v.x, v.x, nn0);
+            nn1 = f2_fma(v.y, v.y, nn1);
           }
-          xnorm = sqrtf(xn) * (1.f / 512.f);   // 2^-9 |x|
+          float x0, x1, x2, x3;
+          f2_unpack(nn0, x0, x1);
+          f2_unpack(nn1, x2, x3);
+          float sq;
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"((x0 + x1) + (x2 + x3)));
+          xnorm = sq * (1.002f / 512.f);   // 2^-9 |z| (the approximate root, rounded up)
         }
-        float thr = 0.f;
+        // Candidate test without a square root.  With s = e8 + 0.01 (e8 = 2^-9 |screen rows|_F |z|: the TF32 error
+        // of the 8 columns), |rows of U_k (x - mu_k)| >= 0.99 sqrt(q8) - s, and cluster k is NOT a candidate when
+        // that exceeds sqrt(T), T = 2 (cc_k + 0.01 - thr); (a + b)^2 <= 2 a^2 + 2 b^2 turns it into
+        //   q8 > 4.0816 (cc_k + 0.01 - thr) + 2.0408 s^2     (a NaN on either side keeps the candidate).
+        if (T2_PROF) prof[4] += clock64() - tp0;
+        float thr = 0.f, A4 = 0.f;
         bool weird = false;
         int cnt = 0;
+        // (the columns of two clusters A, B of a slot pair are interleaved: v[2 i] = A_i, v[2 i + 1] = B_i)
+        const f32x2_t xn2 = f2_pack(xnorm, xnorm), c01 = f2_pack(0.01f, 0.01f), c204 = f2_pack(2.0408f, 2.0408f);
+        f32x2_t A42 = 0ull;
+        // hit bits of the 4 clusters of one 32-column batch, branch-free so that the pairs overlap in the pipe
+        auto screen4 = [&](const uint32_t* v, int slot0) -> uint32_t {
+          uint32_t hits = 0;
+#pragma unroll
+          for (int pp = 0; pp < 2; ++pp) {
+            const uint32_t* w = v + 16 * pp;
+            f32x2_t p[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) p[i] = f2_pack(__uint_as_float(w[2 * i]), __uint_as_float(w[2 * i + 1]));
+            f32x2_t a0 = f2_fma(p[0], p[0], 0ull), a1 = f2_fma(p[1], p[1], 0ull);
+            a0 = f2_fma(p[2], p[2], a0); a1 = f2_fma(p[3], p[3], a1);
+            a0 = f2_fma(p[4], p[4], a0); a1 = f2_fma(p[5], p[5], a1);
+            a0 = f2_fma(p[6], p[6], a0); a1 = f2_fma(p[7], p[7], a1);
+            const float4 sc = scrc[(slot0 >> 1) + pp];
+            const f32x2_t sv = f2_fma(xn2, f2_pack(sc.z, sc.w), c01);
+            // q8 > bnd  with  bnd = 2.0408 sv^2 + 4.0816 cc + A4
+            const f32x2_t t1 = f2_fma(f2_fma(c204, sv, 0ull), sv, f2_fma(f2_pack(sc.x, sc.y), f2_pack(1.f, 1.f), A42));
+            float qa, qb, ba, bb, ra, rb;
+            f2_unpack(a0, qa, qb);
+            f2_unpack(a1, ra, rb);
+            f2_unpack(t1, ba, bb);
+            hits |= (!((qa + ra) > ba) ? 1u : 0u) << (2 * pp);
+            hits |= (!((qb + rb) > bb) ? 1u : 0u) << (2 * pp + 1);
+          }
+          return hits;
+        };
+        auto append = [&](uint32_t hits, int k0) {   // rare: the pivot's own bit is masked out by the caller
+          for (; hits; hits &= hits - 1) {
+            const int k = k0 + __ffs(hits) - 1;
+            if (k < K) {
+              if (cnt < T2_CMAX) mylist[cnt] = (uint16_t)k;
+              ++cnt;
+            }
+          }
+        };
         for (int c = 0; c < nch; ++c, ++cc) {
           const int b = cc & 1;
-          tc::mbar_wait(&tfull[g * 2 + b], (cc >> 1) & 1);
+          T2_WAIT(1, tc::mbar_wait(&tfull[g * 2 + b], (cc >> 1) & 1));
           tc::tc_fence_after();
+          [[maybe_unused]] const long long tp1 = T2_PROF ? clock64() : 0;
           const uint32_t taddr = tmem_row + b * 128;
-          int col = 0;
+          const int ncl = c == 0 ? min(K, n0) : min(16, K - n0 - (c - 1) * 16);
+          const int kbase = c == 0 ? 0 : n0 + (c - 1) * 16;
+          const int nb = (ncl + 3) >> 2;          // batches of 4 clusters = 32 accumulator columns
+          int col = 0, b0 = 0;
           if (c == 0) {
+            uint32_t v[32], v1[32];
             float qp = 0.f;
-#pragma unroll
-            for (int h = 0; h < D / 32; ++h) {
-              uint32_t v[32];
-              tc::tmem_ld32(taddr + 32 * h, v);
+            if constexpr (D == 64) {
+              tc::tmem_ld32(taddr, v);
+              tc::tmem_ld32(taddr + 32, v1);
               tc::tmem_ld_wait();
-              qp += gauss_tc_screen_q(v);
+              qp = gauss_tc_screen_q(v) + gauss_tc_screen_q(v1);
+            } else {
+              tc::tmem_ld32(taddr, v);
+              tc::tmem_ld32(taddr + 32, v1);          // first screen batch rides along
+              T2_WAIT(2, tc::tmem_ld_wait());
+              qp = gauss_tc_screen_q(v);
             }
-            const float4 cf = ccfro[key];
+            const float2 cf = ccfro[key];
             const float e = xnorm * cf.y;
             float sq;
             asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(fmaxf(qp, 0.f)));
@@ -447,35 +531,37 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const Ga
             const float rt = fmaf(-0.5f, qp, cf.x);
             weird = !(fabsf(rt) < CUDART_INF_F) || !(dr < CUDART_INF_F);
             thr = (rt - dr) - T2_DELTA;
+            A4 = 4.0816f * (0.01f - thr);
+            A42 = f2_pack(A4, A4);
             col = D;
-          }
-          const int ncl = c == 0 ? min(K, n0) : min(16, K - n0 - (c - 1) * 16);
-          const int kbase = c == 0 ? 0 : n0 + (c - 1) * 16;
-          for (int j0 = 0; j0 < ncl; j0 += 4) {
-            uint32_t v[32];
-            tc::tmem_ld32(taddr + col + j0 * T2_R, v);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int k = kbase + j0 + jj;
-              if (j0 + jj < ncl) {
-                const float q8 = t2_sum8(v + 8 * jj);
-                const float4 cf = ccfro[k];
-                float sq;
-                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(fmaxf(q8, 0.f)));
-                const float lo = fmaxf(fmaf(-xnorm, cf.z, 0.99f * sq) - 0.01f, 0.f);   // |rows of U z| >= sqrt(q~8) - e
-                const float rhi = fmaf(-0.5f * lo, lo, cf.x) + 0.01f;          // upper bound of r_k
-                weird |= !(q8 < CUDART_INF_F);
-                if (rhi >= thr && k != key) {
-                  if (cnt < T2_CMAX) mylist[cnt] = (uint16_t)k;
-                  ++cnt;
-                }
-              }
+            if constexpr (D == 32) {
+              uint32_t h = screen4(v1, 0);
+              if ((unsigned)key < 4u) h &= ~(1u << key);
+              if (h) append(h, 0);
+              b0 = 1;
             }
+          }
+          for (; b0 < nb; b0 += 2) {
+            uint32_t v[32], v1[32];
+            tc::tmem_ld32(taddr + col + b0 * 32, v);
+            if (b0 + 1 < nb) tc::tmem_ld32(taddr + col + b0 * 32 + 32, v1);
+            T2_WAIT(2, tc::tmem_ld_wait());
+            uint32_t h = screen4(v, c * 16 + b0 * 4);
+            if (b0 + 1 < nb) h |= screen4(v1, c * 16 + b0 * 4 + 4) << 4;
+            if (T2_ABL & 1) {   // the same work once more (timing experiment)
+              asm volatile("" : "+r"(v[0]), "+r"(v1[0]));
+              h |= screen4(v, c * 16 + b0 * 4);
+              if (b0 + 1 < nb) h |= screen4(v1, c * 16 + b0 * 4 + 4) << 4;
+            }
+            const int k0 = kbase + b0 * 4;
+            if ((unsigned)(key - k0) < 8u) h &= ~(1u << (key - k0));
+            if (h) append(h, k0);
           }
           tc::tc_fence_before();
           tc::mbar_arrive(&tempty[g * 2 + b]);
+          if (T2_PROF) prof[5] += clock64() - tp1;
         }
+        [[maybe_unused]] const long long tp2 = T2_PROF ? clock64() : 0;
         bool multi = valid && !weird && cnt > 0 && cnt < T2_CMAX;
         bool ovf = valid && (weird || cnt >= T2_CMAX);
         if (multi) {   // insert the pivot at its place (the list is ascending)
@@ -488,7 +574,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const Ga
           ++cnt;
         }
         // ---- exact evaluation of the listed (point, cluster) pairs, spread over the 128 threads ----
-        if (group_any(g, multi)) {
+        // ---- exact evaluation of the listed (point, cluster) pairs, spread over the lanes of the warp ----
+        if (__any_sync(0xffffffffu, multi)) {
           const int mine = multi ? cnt : 0;
           int inc = mine;
 #pragma unroll
@@ -496,19 +583,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const Ga
             const int t = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += t;
           }
-          if (lane == 31) misc[wq] = inc;
-          group_barrier(g);
-          int off = inc - mine, total = 0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int t = misc[q];
-            if (q < wq) off += t;
-            total += t;
-          }
-          for (int j = 0; j < mine; ++j) pairs[off + j] = (uint16_t)((row << 3) | j);
-          group_barrier(g);
-          for (int p = gt; p < total; p += 128) {
-            const int pr = pairs[p], prow = pr >> 3, slot = pr & 7;
+          const int total = __shfl_sync(0xffffffffu, inc, 31), off = inc - mine;
+          uint16_t* wpairs = pairs + wq * 32 * T2_CMAX;
+          for (int j = 0; j < mine; ++j) wpairs[off + j] = (uint16_t)((row << 3) | j);
+          __syncwarp();
+          for (int p = lane; p < total; p += 32) {
+            const int pr = wpairs[p], prow = pr >> 3, slot = pr & 7;
             const int k = lists[prow * T2_CMAX + slot];
             const int32_t pidx = __ldg(a.perm + w.pos + prow);
             const float q = gauss_tc2_exact_q_row<D>(a.urows + (size_t)k * D * D, a.mu + (size_t)k * D, a.x + (size_t)pidx * D);
@@ -516,7 +596,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const Ga
             rl[prow * T2_CMAX + slot] = gauss_finish(cf.x, q, cf.y);
             ++ncand_total;
           }
-          group_barrier(g);
+          __syncwarp();
         }
         tc::mbar_arrive(&empty[s]);   // the stage can be refilled now
         // ---- draw ----
@@ -552,6 +632,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const Ga
           }
           ++npts_total;
         }
+        if (T2_PROF) prof[6] += clock64() - tp2;
       }
       if (a.stats != nullptr) {
         atomicAdd(&a.stats[0], npts_total);
@@ -559,9 +640,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const Ga
       }
     } else {
       // =============================== gather warps ===============================
-      const int t64 = tid - 320;
+      const int t64 = tid - 320;               // 0 .. T2_PRODUCERS - 1
       constexpr int CPR = D / 4;            // 16-byte chunks per row
-      constexpr int RS = 64 / CPR;          // rows covered by the 64 threads per pass
+      constexpr int RS = T2_PRODUCERS(D) / CPR; // rows covered by the gather threads per pass
       constexpr int NJ = T2_TILE / RS;      // passes per tile
       const int c = t64 % CPR, r0 = t64 / CPR;
       T2Walk wl, wc;
@@ -599,7 +680,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const Ga
         cp_async_commit();
       }
       for (int li = 0; li < nt; ++li) {
-        cp_async_wait_group<PF - 1>();
+        T2_WAIT(0, cp_async_wait_group<PF - 1>());
         {   // centre this thread's chunks of the landed tile by the pivot's mean (rows beyond the tile stay zero)
           const int key = min(wc.key, K - 1);
           if (key != ckey) {
@@ -616,6 +697,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const Ga
             if (r < nrow) {
               v.x -= cen.x; v.y -= cen.y; v.z -= cen.z; v.w -= cen.w;
               *q = v;
+              if (T2_ABL & 2) {   // the same work once more (timing experiment)
+                asm volatile("" ::: "memory");
+                float4 u = *q;
+                u.x += cen.x; u.y += cen.y; u.z += cen.z; u.w += cen.w;
+                *q = u;
+                asm volatile("" ::: "memory");
+                u = *q;
+                u.x -= cen.x; u.y -= cen.y; u.z -= cen.z; u.w -= cen.w;
+                *q = u;
+              }
             }
           }
           t2_advance(wc, B);
@@ -624,7 +715,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const Ga
         tc::mbar_arrive(&full[li % NS]);
         const int nx = li + PF;
         if (nx < nt) {
-          tc::mbar_wait(&empty[nx % NS], ((nx / NS) & 1) ^ 1);
+          T2_WAIT(1, tc::mbar_wait(&empty[nx % NS], ((nx / NS) & 1) ^ 1));
           issue(nx % NS);
           t2_advance(wl, B);
           if (nx + 1 < nt) load_idx();
@@ -633,10 +724,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gauss_label_tc2_kernel(const Ga
       }
     }
   }
+#if T2_PROF
+  if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 2 || warp == 10))
+    printf("[t2 prof] warp %d tiles %d total %lld: wait0 %lld wait1 %lld wait2 %lld wait3 %lld | xnorm %lld chunks %lld post %lld\n", warp, nt, clock64() - t_start, prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6]);
+#endif
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
-  for (int k = tid; k < K; k += T2_THREADS)
+  for (int k = tid; k < K; k += T2_THREADS(D))
     if (hs[k] != 0) atomicAdd(&a.hist[k], hs[k]);
 }
 

@@ -139,11 +139,14 @@ __global__ void __launch_bounds__(NIW_PACK_THREADS) niw_pack_kernel(const NiwPac
     }
     const int KS = a.t2_KS;
     const int row0 = (KS == D) ? 0 : D - 8, f0 = (KS == D) ? 0 : D - 8;
-    const int ch = k < a.t2_n0 ? 0 : 1 + (k - a.t2_n0) / 16, rg = k < a.t2_n0 ? k : (k - a.t2_n0) % 16;
+    // slot of the cluster in its chunk; the rows of the two clusters of a slot pair are INTERLEAVED (row of the
+    // image = 16 (slot / 2) + 2 r + slot % 2) so that the label kernel squares two clusters per packed FFMA2
+    const int ch = k < a.t2_n0 ? 0 : 1 + (k - a.t2_n0) / 16, slot = k < a.t2_n0 ? k : (k - a.t2_n0) % 16;
     float* scr = a.t2_scr + (size_t)ch * (KS / 8) * 1024;
     for (int e = tid; e < 8 * KS; e += NT) {
       const int r = e / KS, jj = e - r * KS;
-      scr[(jj >> 3) * 1024 + rg * 64 + ((jj & 7) >> 2) * 32 + r * 4 + (jj & 3)] = uval(row0 + r, f0 + jj);
+      const int n = 16 * (slot >> 1) + 2 * r + (slot & 1);
+      scr[(jj >> 3) * 1024 + (n >> 3) * 64 + ((jj & 7) >> 2) * 32 + (n & 7) * 4 + (jj & 3)] = uval(row0 + r, f0 + jj);
     }
     if (tid < 32) {   // |screen rows|_F
       double f8 = 0.0;
@@ -210,8 +213,8 @@ __global__ void __launch_bounds__(256) niw_t2_bias_kernel(const NiwT2BiasArgs a)
     ub &= 0xFFFFE000u;                                // round to TF32 (10 explicit mantissa bits)
     const float hi = (bf == bf && fabsf(bf) < CUDART_INF_F) ? __uint_as_float(ub) : bf;
     const float lo = bf - hi;
-    const int ch = k < a.n0 ? 0 : 1 + (k - a.n0) / 16, rg = k < a.n0 ? k : (k - a.n0) % 16;
-    float* q = out + ch * 512 + (rg * 8 + r) * 4;
+    const int ch = k < a.n0 ? 0 : 1 + (k - a.n0) / 16, slot = k < a.n0 ? k : (k - a.n0) % 16;
+    float* q = out + ch * 512 + (16 * (slot >> 1) + 2 * r + (slot & 1)) * 4;
     q[0] = -hi;
     q[1] = -lo;
   }
