@@ -146,6 +146,23 @@ struct dpmm_ctx {
   double t_ms[TK_COUNT] = {0};
   int64_t t_n[TK_COUNT] = {0};
 
+  // device-side parameter step (NIW): hyper-parameters, persistent statistics / posterior tables, factors
+  bool dev_params = false;
+  double alpha = 0.0;
+  double* hyper_d = nullptr;     // [NIW_HYPER_DOUBLES]
+  double* ptab = nullptr;        // [Kcap][3][stats_rec]
+  double* ptab_alt = nullptr;
+  double* post = nullptr;        // [Kcap][3][NIW_POST_DOUBLES]
+  double* post_alt = nullptr;
+  double* lfac = nullptr;        // [3 Kcap][D][D]
+  double* pm_out = nullptr;      // [Kcap*3*2 + Kcap*Kcap + 2] results of the posterior step for the host
+  uint8_t* splittable_d = nullptr;
+  int32_t* newof_d = nullptr;
+  float* w_out = nullptr;        // [Kcap] Float32 mixture weights of the last dpmm_sample_params
+  float* lr_out = nullptr;       // [2 Kcap]
+  uint32_t pcall = 0;
+  int Kcap_tab = 0;
+
   NcclApi nccl;
   void* comm = nullptr;
   int world = 1, rank = 0;

@@ -19,6 +19,7 @@
 #include "kernels_mnm.cuh"
 #include "kernels_mnm_tc.cuh"
 #include "kernels_pack.cuh"
+#include "kernels_params.cuh"
 #include "kernels_sort.cuh"
 #include "kernels_stats.cuh"
 #include "kernels_stats_tc.cuh"
@@ -31,6 +32,37 @@ static int nrec_floats(const dpmm_ctx* c) {
   if (c->prior == DPMM_PRIOR_MULTINOMIAL) return c->D;
   const int D = c->D;
   return gauss_col_off(D) + ((D + 3) & ~3);
+}
+
+// tables of the device-side parameter step: grown with their contents preserved
+template <typename T>
+static cudaError_t dev_grow_keep(T** p, size_t old_count, size_t new_count) {
+  T* q = nullptr;
+  cudaError_t e = cudaMalloc((void**)&q, std::max<size_t>(new_count, 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  e = cudaMemset(q, 0, std::max<size_t>(new_count, 1) * sizeof(T));
+  if (e == cudaSuccess && *p && old_count) e = cudaMemcpy(q, *p, old_count * sizeof(T), cudaMemcpyDeviceToDevice);
+  if (*p) cudaFree(*p);
+  *p = q;
+  return e;
+}
+static int ensure_tables(dpmm_ctx* ctx, int cap) {
+  if (cap <= ctx->Kcap_tab) return 0;
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int D = ctx->D, old = ctx->Kcap_tab;
+  const size_t rec3 = (size_t)3 * (1 + D + D * D), post3 = (size_t)3 * NIW_POST_DOUBLES(D);
+  CK(dev_grow_keep(&ctx->ptab, old * rec3, cap * rec3));
+  CK(dev_grow_keep(&ctx->ptab_alt, 0, cap * rec3));
+  CK(dev_grow_keep(&ctx->post, old * post3, cap * post3));
+  CK(dev_grow_keep(&ctx->post_alt, 0, cap * post3));
+  CK(dev_grow_keep(&ctx->lfac, (size_t)3 * old * D * D, (size_t)3 * cap * D * D));
+  CK(dev_grow_keep(&ctx->pm_out, 0, (size_t)cap * 6 + (size_t)cap * cap + 2));
+  CK(dev_grow_keep(&ctx->splittable_d, 0, (size_t)cap));
+  CK(dev_grow_keep(&ctx->newof_d, 0, (size_t)cap));
+  CK(dev_grow_keep(&ctx->w_out, (size_t)old, (size_t)cap));
+  CK(dev_grow_keep(&ctx->lr_out, (size_t)2 * old, (size_t)2 * cap));
+  ctx->Kcap_tab = cap;
+  return 0;
 }
 
 static int ensure_k(dpmm_ctx* ctx, int K) {
@@ -92,6 +124,12 @@ static int ensure_k(dpmm_ctx* ctx, int K) {
   CK(dev_realloc(&ctx->items, (size_t)ctx->items_cap));
   ctx->Kcap = cap;
   ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
+  ctx->params_set = false;   // every parameter buffer above was reallocated: set_params must run again
+  ctx->acc_cleared = ctx->cursors_fresh = false;
+  if (ctx->dev_params) {
+    int rc = ensure_tables(ctx, cap);
+    if (rc) return rc;
+  }
   return 0;
 }
 
@@ -289,7 +327,9 @@ extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
   void* ptrs[] = {ctx->x, ctx->labels, ctx->sub, ctx->perm, ctx->perm2, ctx->u_label, ctx->u_sub, ctx->r_bits,
                   ctx->raw_params, ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->t2_piv, ctx->t2_scr, ctx->t2_u, ctx->t2_bias, ctx->t2_fro8, ctx->t2_ctr, ctx->tc_w, ctx->tc_b, ctx->tc_mu, ctx->tc_fro, ctx->tc_stats, ctx->ss_w, ctx->ss_b, ctx->ss_c, ctx->lcount, ctx->mtc_w, ctx->hist, ctx->seg_off,
                   ctx->scat_cursor, ctx->lr_cursor, ctx->lut_l, ctx->lut_r, ctx->rule, ctx->wanted,
-                  ctx->idx_list, ctx->acc, ctx->centers, ctx->outbuf, ctx->items, ctx->item_ctr};
+                  ctx->idx_list, ctx->acc, ctx->centers, ctx->outbuf, ctx->items, ctx->item_ctr, ctx->hyper_d, ctx->ptab,
+                  ctx->ptab_alt, ctx->post, ctx->post_alt, ctx->lfac, ctx->pm_out, ctx->splittable_d, ctx->newof_d,
+                  ctx->w_out, ctx->lr_out};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (ctx->hstage) cudaFreeHost(ctx->hstage);
@@ -479,6 +519,27 @@ extern "C" int dpmm_remove_empty(dpmm_ctx* ctx, const int64_t* pts_count, int32_
   }
   if (!any) return 0;
   NEED(ctx->label_bound <= k, DPMM_EINVAL, "pts_count is shorter than the number of label values in use");
+  if (ctx->dev_params && ctx->Kcap_tab > 0) {
+    // the persistent statistics / posterior tables follow the compaction
+    const int kt_ = std::min(k, ctx->Kcap_tab);
+    std::vector<int32_t> newof(kt_);
+    for (int i = 0, r2 = 0; i < kt_; ++i) {
+      newof[i] = pts_count[i] == 0 ? -1 : i - r2;
+      if (pts_count[i] == 0) ++r2;
+    }
+    int rc2 = ensure_stage(ctx, (size_t)kt_ * 4);
+    if (rc2) return rc2;
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->hstage, newof.data(), (size_t)kt_ * 4);
+    CK(cudaMemcpyAsync(ctx->newof_d, ctx->hstage, (size_t)kt_ * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const int rec3 = 3 * ctx->stats_rec, post3 = 3 * NIW_POST_DOUBLES(ctx->D);
+    KernelTimer kt(ctx, TK_PARAMS, 2);
+    table_gather_kernel<<<dim3(8, (unsigned)kt_), 256, 0, ctx->stream>>>(ctx->ptab, ctx->newof_d, kt_, rec3, ctx->ptab_alt);
+    table_gather_kernel<<<dim3(8, (unsigned)kt_), 256, 0, ctx->stream>>>(ctx->post, ctx->newof_d, kt_, post3, ctx->post_alt);
+    CK(cudaGetLastError());
+    std::swap(ctx->ptab, ctx->ptab_alt);
+    std::swap(ctx->post, ctx->post_alt);
+  }
   ctx->label_bound = std::max(1, k - removed);
   ctx->K = std::min(ctx->K, ctx->label_bound);  // parameters of the dropped clusters are stale anyway
   ctx->params_set = false;
@@ -586,36 +647,12 @@ static void common_weights(dpmm_ctx* ctx, int K, const float* weights, const flo
   for (int k = 0; k < 2 * K; ++k) h_loglr[k] = (float)std::log((double)lr_weights[k]);
 }
 
-extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, const float* inv_sigma,
-                                   const float* logdet, const float* weights, const float* lr_weights) {
-  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
-  NEED(ctx->prior == DPMM_PRIOR_NIW, DPMM_ESTATE, "context was created with the multinomial prior");
-  NEED(K >= 1 && K <= DPMM_MAX_K, DPMM_ELIMIT, "K out of range");
-  NEED(mu && inv_sigma && logdet && weights && lr_weights, DPMM_EINVAL, "NULL parameter array");
-  CK(cudaSetDevice(ctx->device));
-  int rc = ensure_k(ctx, K);
-  if (rc) return rc;
+// Factor (unless `lfac` is given), pack and derive every parameter image of the sweep kernels from
+// ctx->raw_params = [mu | invSigma | logdet] (device) for K clusters; logw / loglr are already in place.
+static int niw_pack_launch(dpmm_ctx* ctx, int K, const double* lfac) {
   const int D = ctx->D, REC = ctx->rec_f, TRIP = gauss_col_off(D);
   const size_t nrec = (size_t)3 * K;
   const bool tcp = ctx->tc_ok && K <= TC_MAX_K;
-  // raw parameters -> pinned staging -> device; the factorisation and packing run on the device
-  const size_t raw_floats = nrec * D + nrec * D * D + nrec;
-  const size_t bytes = (raw_floats + K + 2 * K) * sizeof(float);
-  rc = ensure_stage(ctx, bytes);
-  if (rc) return rc;
-  CK(cudaStreamSynchronize(ctx->stream));  // staging buffer reuse
-  float* h_mu = (float*)ctx->hstage;
-  float* h_inv = h_mu + nrec * D;
-  float* h_ld = h_inv + nrec * D * D;
-  float* h_logw = h_ld + nrec;
-  float* h_loglr = h_logw + K;
-  memcpy(h_mu, mu, nrec * D * 4);
-  memcpy(h_inv, inv_sigma, nrec * D * D * 4);
-  memcpy(h_ld, logdet, nrec * 4);
-  common_weights(ctx, K, weights, lr_weights, h_logw, h_loglr);
-  CK(cudaMemcpyAsync(ctx->raw_params, h_mu, raw_floats * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->logw, h_logw, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->loglr, h_loglr, (size_t)2 * K * 4, cudaMemcpyHostToDevice, ctx->stream));
   ctx->tc_params = ctx->t2_params = false;
   if (tcp) {
     const size_t wfl = (size_t)((K + TC_NCL - 1) / TC_NCL) * TC_NCL * TC_D * TC_D;
@@ -640,7 +677,7 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
     pa.tc_w = tcp ? ctx->tc_w : nullptr; pa.tc_b = ctx->tc_b; pa.tc_mu = ctx->tc_mu; pa.tc_fro = ctx->tc_fro;
     pa.ss_w = ctx->tc_ok ? ctx->ss_w : nullptr; pa.ss_b = ctx->ss_b; pa.ss_c = ctx->ss_c;
     pa.t2_piv = t2p ? ctx->t2_piv : nullptr; pa.t2_scr = ctx->t2_scr; pa.t2_u = ctx->t2_u; pa.t2_KS = t2_ks;
-    pa.t2_n0 = gauss_tc2_n0(D); pa.t2_fro8 = ctx->t2_fro8;
+    pa.t2_n0 = gauss_tc2_n0(D); pa.t2_fro8 = ctx->t2_fro8; pa.lfac = lfac;
     KernelTimer kt(ctx, TK_PARAMS);
     niw_pack_kernel<<<(unsigned)nrec, NIW_PACK_THREADS, (size_t)D * (D + 1) * sizeof(double), ctx->stream>>>(pa);
     CK(cudaGetLastError());
@@ -659,6 +696,40 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
   ctx->t2_nch = t2_nch;
   ctx->K = K;
   ctx->params_set = true;
+  return 0;
+}
+
+extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, const float* inv_sigma,
+                                   const float* logdet, const float* weights, const float* lr_weights) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  NEED(ctx->prior == DPMM_PRIOR_NIW, DPMM_ESTATE, "context was created with the multinomial prior");
+  NEED(K >= 1 && K <= DPMM_MAX_K, DPMM_ELIMIT, "K out of range");
+  NEED(mu && inv_sigma && logdet && weights && lr_weights, DPMM_EINVAL, "NULL parameter array");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_k(ctx, K);
+  if (rc) return rc;
+  const int D = ctx->D;
+  const size_t nrec = (size_t)3 * K;
+  // raw parameters -> pinned staging -> device; the factorisation and packing run on the device
+  const size_t raw_floats = nrec * D + nrec * D * D + nrec;
+  const size_t bytes = (raw_floats + K + 2 * K) * sizeof(float);
+  rc = ensure_stage(ctx, bytes);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));  // staging buffer reuse
+  float* h_mu = (float*)ctx->hstage;
+  float* h_inv = h_mu + nrec * D;
+  float* h_ld = h_inv + nrec * D * D;
+  float* h_logw = h_ld + nrec;
+  float* h_loglr = h_logw + K;
+  memcpy(h_mu, mu, nrec * D * 4);
+  memcpy(h_inv, inv_sigma, nrec * D * D * 4);
+  memcpy(h_ld, logdet, nrec * 4);
+  common_weights(ctx, K, weights, lr_weights, h_logw, h_loglr);
+  CK(cudaMemcpyAsync(ctx->raw_params, h_mu, raw_floats * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->logw, h_logw, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->loglr, h_loglr, (size_t)2 * K * 4, cudaMemcpyHostToDevice, ctx->stream));
+  rc = niw_pack_launch(ctx, K, nullptr);
+  if (rc) return rc;
   return 0;
 }
 
@@ -968,10 +1039,13 @@ extern "C" int dpmm_sample_sublabels(dpmm_ctx* ctx) {
   return run_sublabels(ctx, true, nullptr);
 }
 
-extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_indices, int64_t* counts,
-                               double* sum_x, double* sum_xx) {
-  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
-  CK(cudaSetDevice(ctx->device));
+// The device part of a statistics call: accumulate, finalise into ctx->outbuf ([m][3][rec] (+ the risk counter of
+// the fused path)) and all-reduce.  m = 0 when the index list is empty.
+struct StatsCall {
+  int m = 0;
+  bool all = false, cached = false;
+};
+static int stats_compute(dpmm_ctx* ctx, const int64_t* indices, int32_t n_indices, StatsCall* sc) {
   const int K = keff(ctx);
   int rc = ensure_k(ctx, K);
   if (rc) return rc;
@@ -989,6 +1063,7 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
     }
   }
   const int m = (int)idx.size();
+  sc->m = m;
   if (m == 0) return 0;
   NEED(m <= ctx->Kcap, DPMM_EINVAL, "more indices than clusters");
   const bool cached = ctx->stats_cached;   // accumulators of every cluster left by the fused sub-label kernel
@@ -997,6 +1072,8 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
     if (rc) return rc;
   }
   const bool all = (indices == nullptr);
+  sc->all = all;
+  sc->cached = cached;
   rc = ensure_stage(ctx, std::max<size_t>((size_t)m * 4 + K, ((size_t)m * 3 * rec + 1) * 8));
   if (rc) return rc;
   if (!all) {   // "all" needs no index list (the finalise kernel then uses k = a) and hence no host round trip here
@@ -1063,7 +1140,7 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
     KernelTimer kt(ctx, TK_STATS_AUX);
     const int T = 256;
     dim3 grid((unsigned)std::min((rec + T - 1) / T, 64), (unsigned)m);
-    if (cached) CK(cudaMemsetAsync(ctx->outbuf + (size_t)m * 3 * rec, 0, 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->outbuf + (size_t)m * 3 * rec, 0, 8, ctx->stream));
     stats_finalize_kernel<<<grid, T, 0, ctx->stream>>>(ctx->acc, ctx->seg_off, ctx->lr_cursor, all ? nullptr : ctx->idx_list, m, D, rec,
                                                        ctx->prior == DPMM_PRIOR_NIW ? 1 : 0, ctx->outbuf,
                                                        (stats_tc || cached) ? ctx->centers : nullptr,
@@ -1074,10 +1151,28 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
   if (ctx->comm != nullptr) {
     KernelTimer kt(ctx, TK_ALLREDUCE);
     // aggregate_suff_stats across workers (niw.jl:64-66; local_clusters_actions.jl:194-196, 246-248)
-    const int r = ctx->nccl.AllReduce(ctx->outbuf, ctx->outbuf, (size_t)m * 3 * rec + (cached ? 1 : 0), /*ncclFloat64*/ 8, /*ncclSum*/ 0,
+    // (the risk slot always travels, so the element count cannot differ between ranks)
+    const int r = ctx->nccl.AllReduce(ctx->outbuf, ctx->outbuf, (size_t)m * 3 * rec + 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0,
                                       ctx->comm, ctx->stream);
     if (r != 0) return fail(ctx, DPMM_ENCCL, std::string("ncclAllReduce: ") + ctx->nccl.GetErrorString(r));
   }
+  return 0;
+}
+
+extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_indices, int64_t* counts,
+                               double* sum_x, double* sum_xx) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  if (indices == nullptr && n_indices > 0)
+    NEED(n_indices == keff(ctx), DPMM_EINVAL,
+         "indices == NULL means every cluster: n_indices must be 0 or the number of label values in use "
+         "(max of the K of set_params and the largest label); the output arrays hold that many rows");
+  StatsCall sc;
+  int rc = stats_compute(ctx, indices, n_indices, &sc);
+  if (rc) return rc;
+  const int m = sc.m, D = ctx->D, rec = ctx->stats_rec;
+  const bool cached = sc.cached;
+  if (m == 0) return 0;
   if (counts == nullptr && sum_x == nullptr && sum_xx == nullptr) return 0;
   double* h = (double*)ctx->hstage;
   CK(cudaMemcpyAsync(h, ctx->outbuf, ((size_t)m * 3 * rec + (cached ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1098,6 +1193,208 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
       if (sum_xx && ctx->prior == DPMM_PRIOR_NIW)
         memcpy(sum_xx + ((size_t)a * 3 + s) * D * D, r + 1 + D, (size_t)D * D * 8);
     }
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// device-side parameter step (NIW): SURVEY.md 8f-1
+// ------------------------------------------------------------------------------------------------
+extern "C" int dpmm_num_clusters(const dpmm_ctx* ctx) { return ctx ? keff(ctx) : 0; }
+
+extern "C" int dpmm_set_hyper_niw(dpmm_ctx* ctx, double kappa, const double* m, double nu, const double* psi, double alpha) {
+  NEED(ctx && m && psi, DPMM_EINVAL, "NULL argument");
+  NEED(ctx->prior == DPMM_PRIOR_NIW, DPMM_ESTATE, "context was created with the multinomial prior");
+  NEED(kappa > 0 && nu > ctx->D - 1 && alpha > 0, DPMM_EINVAL, "need kappa > 0, nu > D - 1, alpha > 0");
+  CK(cudaSetDevice(ctx->device));
+  const int D = ctx->D;
+  std::vector<double> h(NIW_HYPER_DOUBLES(D));
+  // logdet psi by a host Cholesky of the symmetrised matrix (one-time, D <= 64)
+  std::vector<double> A((size_t)D * D);
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) A[(size_t)i * D + j] = 0.5 * (psi[(size_t)i * D + j] + psi[(size_t)j * D + i]);
+  double logdet = 0.0;
+  for (int j = 0; j < D; ++j) {
+    double d = A[(size_t)j * D + j];
+    for (int k = 0; k < j; ++k) d -= A[(size_t)j * D + k] * A[(size_t)j * D + k];
+    NEED(d > 0 && std::isfinite(d), DPMM_EINVAL, "psi must be positive definite");
+    const double l = std::sqrt(d);
+    A[(size_t)j * D + j] = l;
+    logdet += 2.0 * std::log(l);
+    for (int i = j + 1; i < D; ++i) {
+      double v = A[(size_t)i * D + j];
+      for (int k = 0; k < j; ++k) v -= A[(size_t)i * D + k] * A[(size_t)j * D + k];
+      A[(size_t)i * D + j] = v / l;
+    }
+  }
+  // niw_hyperparams stores kappa and nu as Float32 (niw.jl:6-11)
+  const double kf = (double)(float)kappa, nf = (double)(float)nu;
+  float lmv = (float)((double)D * (D - 1) / 4.0 * 1.1447298858494002);
+  for (int j = 1; j <= D; ++j) lmv = (float)((double)lmv + std::lgamma(nf / 2.0 + (1.0 - j) / 2.0));
+  h[0] = kf; h[1] = nf; h[2] = logdet; h[3] = (double)lmv;
+  for (int i = 0; i < D; ++i) h[4 + i] = m[i];
+  for (int e = 0; e < D * D; ++e) h[4 + D + e] = psi[e];
+  if (!ctx->hyper_d) CK(cudaMalloc((void**)&ctx->hyper_d, h.size() * 8));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(ctx->hyper_d, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+  ctx->alpha = (double)(float)alpha;   // model_hyper_params.alpha is Float32 (ds.jl:9)
+  ctx->dev_params = true;
+  return ensure_tables(ctx, std::max(ctx->Kcap, 8));
+}
+
+static size_t niw_post_smem(int D) { return ((size_t)D * (D + 1) + 2 * D) * sizeof(double); }
+
+// posterior + log marginal likelihood of the listed clusters (device list idx_d, or all m = K in order) from the table
+static int launch_post(dpmm_ctx* ctx, const int32_t* idx_d, int m, double* out) {
+  NiwPostArgs pa{};
+  pa.D = ctx->D; pa.rec = ctx->stats_rec; pa.hyper = ctx->hyper_d; pa.ptab = ctx->ptab; pa.idx_list = idx_d;
+  pa.post = ctx->post; pa.out = out;
+  const size_t sm = niw_post_smem(ctx->D);
+  if (sm > 48 * 1024) CK(cudaFuncSetAttribute(niw_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  KernelTimer kt(ctx, TK_PARAMS);
+  niw_post_kernel<<<dim3((unsigned)m, 3), 256, sm, ctx->stream>>>(pa);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dpmm_posterior_step(dpmm_ctx* ctx, const int64_t* indices, int32_t n_indices, int32_t from_table,
+                                   const uint8_t* splittable, int32_t k_merge, int64_t* counts, double* logml,
+                                   double* merge_logml) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->dev_params, DPMM_ESTATE, "dpmm_set_hyper_niw must precede dpmm_posterior_step");
+  const int rec = ctx->stats_rec;
+  int m = 0;
+  bool all = indices == nullptr;
+  bool cached = false;
+  if (!from_table) {
+    StatsCall sc;
+    int rc = stats_compute(ctx, indices, n_indices, &sc);
+    if (rc) return rc;
+    m = sc.m;
+    cached = sc.cached;
+    if (m == 0) return 0;
+    rc = ensure_tables(ctx, ctx->Kcap);
+    if (rc) return rc;
+    const int rec3 = 3 * rec;
+    dim3 grid((unsigned)std::min((rec3 + 255) / 256, 32), (unsigned)m);
+    KernelTimer kt(ctx, TK_PARAMS);
+    ptab_scatter_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->outbuf, all ? nullptr : ctx->idx_list, m, rec3, ctx->ptab);
+    CK(cudaGetLastError());
+  } else {
+    // re-evaluate table rows (after dpmm_params_merge): the index list goes up by itself
+    NEED(indices != nullptr && n_indices >= 0, DPMM_EINVAL, "from_table needs an index list");
+    m = n_indices;
+    if (m == 0) return 0;
+    NEED(m <= ctx->Kcap_tab, DPMM_EINVAL, "more indices than clusters");
+    int rc = ensure_stage(ctx, (size_t)m * 4);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    int32_t* h_idx = (int32_t*)ctx->hstage;
+    for (int i = 0; i < m; ++i) {
+      NEED(indices[i] >= 1 && indices[i] <= ctx->Kcap_tab, DPMM_EINVAL, "cluster index out of range");
+      h_idx[i] = (int32_t)indices[i] - 1;
+    }
+    CK(cudaMemcpyAsync(ctx->idx_list, h_idx, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+    all = false;
+  }
+  int rc = launch_post(ctx, all ? nullptr : ctx->idx_list, m, ctx->pm_out);
+  if (rc) return rc;
+  const bool want_merge = merge_logml != nullptr && splittable != nullptr && k_merge > 1;
+  double* merge_d = ctx->pm_out + (size_t)m * 6;
+  if (want_merge) {
+    NEED(k_merge <= ctx->Kcap_tab, DPMM_EINVAL, "k_merge exceeds the number of clusters");
+    CK(cudaMemcpyAsync(ctx->splittable_d, splittable, (size_t)k_merge, cudaMemcpyHostToDevice, ctx->stream));
+    NiwMergeArgs ma{};
+    ma.D = ctx->D; ma.rec = rec; ma.K = k_merge; ma.hyper = ctx->hyper_d; ma.ptab = ctx->ptab;
+    ma.splittable = ctx->splittable_d; ma.out = merge_d;
+    const size_t sm = niw_post_smem(ctx->D);
+    if (sm > 48 * 1024) CK(cudaFuncSetAttribute(niw_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    KernelTimer kt(ctx, TK_PARAMS);
+    niw_merge_kernel<<<dim3((unsigned)k_merge, (unsigned)k_merge), 256, sm, ctx->stream>>>(ma);
+    CK(cudaGetLastError());
+  }
+  if (counts == nullptr && logml == nullptr && !want_merge) return 0;
+  const size_t nd = (size_t)m * 6 + (want_merge ? (size_t)k_merge * k_merge : 0);
+  rc = ensure_stage(ctx, (nd + 1) * 8);
+  if (rc) return rc;
+  double* h = (double*)ctx->hstage;
+  CK(cudaMemcpyAsync(h, ctx->pm_out, nd * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cached) CK(cudaMemcpyAsync(h + nd, ctx->outbuf + (size_t)m * 3 * rec, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (cached && h[nd] != 0.0) {
+    // the fused accumulators were rejected (see dpmm_suff_stats): recompute exactly, on every rank
+    ctx->stats_cached = false;
+    ++ctx->n_recompute;
+    return dpmm_posterior_step(ctx, indices, n_indices, from_table, splittable, k_merge, counts, logml, merge_logml);
+  }
+  if (cached) ++ctx->n_cached;
+  for (int a = 0; a < m * 3; ++a) {
+    if (counts) counts[a] = (int64_t)llround(h[2 * a]);
+    if (logml) logml[a] = h[2 * a + 1];
+  }
+  if (want_merge) memcpy(merge_logml, h + (size_t)m * 6, (size_t)k_merge * k_merge * 8);
+  return 0;
+}
+
+extern "C" int dpmm_sample_params(dpmm_ctx* ctx, int32_t K, int32_t from_prior, int32_t unit_weights) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->dev_params, DPMM_ESTATE, "dpmm_set_hyper_niw must precede dpmm_sample_params");
+  NEED(K >= 1 && K <= DPMM_MAX_K, DPMM_ELIMIT, "K out of range");
+  int rc = ensure_k(ctx, K);
+  if (rc) return rc;
+  rc = ensure_tables(ctx, ctx->Kcap);
+  if (rc) return rc;
+  const int D = ctx->D;
+  const size_t nrec = (size_t)3 * K;
+  ctx->pcall += 1;
+  {
+    NiwDrawArgs da{};
+    da.D = D; da.mu = ctx->raw_params; da.logdet = ctx->raw_params + nrec * D + nrec * D * D; da.hyper = ctx->hyper_d;
+    da.post = ctx->post; da.lfac = ctx->lfac; da.seed = ctx->seed; da.call = ctx->pcall; da.first = from_prior;
+    const size_t sm = ((size_t)3 * D * (D + 1) + 2 * D) * sizeof(double);
+    if (sm > 48 * 1024) CK(cudaFuncSetAttribute(niw_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    KernelTimer kt(ctx, TK_PARAMS);
+    niw_draw_kernel<<<(unsigned)nrec, NIW_PACK_THREADS, sm, ctx->stream>>>(da);
+    CK(cudaGetLastError());
+  }
+  {
+    WeightsArgs wa{};
+    wa.K = K; wa.D = D; wa.post = ctx->post; wa.stride = NIW_POST_DOUBLES(D); wa.alpha = ctx->alpha; wa.logw = ctx->logw;
+    wa.loglr = ctx->loglr; wa.w_out = ctx->w_out; wa.lr_out = ctx->lr_out; wa.seed = ctx->seed; wa.call = ctx->pcall;
+    wa.unit = unit_weights;
+    KernelTimer kt(ctx, TK_PARAMS);
+    dpmm_weights_kernel<<<1, 256, (size_t)(K + 1) * 8, ctx->stream>>>(wa);
+    CK(cudaGetLastError());
+  }
+  return niw_pack_launch(ctx, K, ctx->lfac);
+}
+
+extern "C" int dpmm_params_merge(dpmm_ctx* ctx, int64_t i, int64_t j) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->dev_params, DPMM_ESTATE, "dpmm_set_hyper_niw must precede dpmm_params_merge");
+  NEED(i >= 1 && j >= 1 && i != j && i <= ctx->Kcap_tab && j <= ctx->Kcap_tab, DPMM_EINVAL, "bad cluster pair");
+  KernelTimer kt(ctx, TK_PARAMS);
+  ptab_merge_kernel<<<1, 256, 0, ctx->stream>>>(ctx->ptab, ctx->stats_rec, (int)i - 1, (int)j - 1);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dpmm_get_params_niw(dpmm_ctx* ctx, int32_t K, float* mu, double* lfac, float* logdet, float* weights,
+                                   float* lr_weights) {
+  NEED(ctx, DPMM_EINVAL, "ctx is NULL");
+  CK(cudaSetDevice(ctx->device));
+  NEED(ctx->dev_params && ctx->params_set && K == ctx->K, DPMM_ESTATE, "no device-sampled parameters for this K");
+  const int D = ctx->D;
+  const size_t nrec = (size_t)3 * K;
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (mu) CK(cudaMemcpy(mu, ctx->raw_params, nrec * D * 4, cudaMemcpyDeviceToHost));
+  if (logdet) CK(cudaMemcpy(logdet, ctx->raw_params + nrec * D + nrec * D * D, nrec * 4, cudaMemcpyDeviceToHost));
+  if (lfac) CK(cudaMemcpy(lfac, ctx->lfac, nrec * D * D * 8, cudaMemcpyDeviceToHost));
+  if (weights) CK(cudaMemcpy(weights, ctx->w_out, (size_t)K * 4, cudaMemcpyDeviceToHost));
+  if (lr_weights) CK(cudaMemcpy(lr_weights, ctx->lr_out, (size_t)2 * K * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -33,6 +33,9 @@ struct NiwPackArgs {
   float* t2_fro8;          // [K] Frobenius norm of the 8 screen rows
   int t2_KS;               // features of the screen: D (first 8 rows of U_k) or 8 (last 8 rows = last 8 features)
   int t2_n0;               // clusters in chunk 0 (behind the pivot's D columns)
+  // optional: the factor itself, L lower with invSigma = L L' ([3K][D][D] Float64, from niw_draw_kernel);
+  // inv_sigma is then ignored and no factorisation runs
+  const double* lfac;
 };
 
 // The centre every point of cluster k is shifted by before it meets the tensor core: the cluster mean
@@ -58,36 +61,11 @@ __device__ __forceinline__ float niw_pack_center(float m, float ml, float mr) {
 // One CTA of 256 threads per distribution.  The right-looking Cholesky applies, per column j, the same
 // operations in the same order as a one-thread loop would (every element L[i][k] receives its updates
 // for j = 0, 1, ... in turn), spread over the CTA: 3 barriers per column instead of a D-long serial chain.
-__global__ void __launch_bounds__(NIW_PACK_THREADS) niw_pack_kernel(const NiwPackArgs a) {
-  extern __shared__ double Ls[];   // [D][D+1]
+// Everything the sweep kernels read of ONE distribution t, from the Float64 factor L (invSigma = L L', lower,
+// shared memory Ls[D][D+1]), the Float32 mean a.mu[t] and a.logdet[t].  Called by the whole CTA.
+__device__ __forceinline__ void niw_pack_body(const NiwPackArgs& a, const int t, const double* Ls, const bool ok) {
   const int D = a.D, LD = D + 1;
-  const int t = blockIdx.x, tid = threadIdx.x, NT = NIW_PACK_THREADS;
-  const float* A = a.inv_sigma + (size_t)t * D * D;
-  for (int e = tid; e < D * D; e += NT) {
-    const int i = e / D, j = e - i * D;
-    Ls[i * LD + j] = 0.5 * ((double)A[(size_t)i * D + j] + (double)A[(size_t)j * D + i]);
-  }
-  __syncthreads();
-  bool ok = true;
-  for (int j = 0; j < D; ++j) {
-    const double d = Ls[j * LD + j];
-    ok = ok && (d > 0.0) && (d < CUDART_INF);
-    const double ljj = sqrt(d);
-    __syncthreads();
-    if (tid == 0) Ls[j * LD + j] = ljj;
-    for (int i = j + 1 + tid; i < D; i += NT) Ls[i * LD + j] /= ljj;
-    __syncthreads();
-    // trailing update of the lower triangle: element (i, k), j < k <= i < D
-    const int m = D - j - 1;
-    for (int e = tid; e < m * m; e += NT) {
-      const int ii = e / m, kk = e - ii * m;
-      if (kk <= ii) {
-        const int i = j + 1 + ii, k = j + 1 + kk;
-        Ls[i * LD + k] -= Ls[i * LD + j] * Ls[k * LD + j];
-      }
-    }
-    __syncthreads();   // the next column's pivot is part of the trailing block
-  }
+  const int tid = threadIdx.x, NT = NIW_PACK_THREADS;
   const float nanv = __int_as_float(0x7fc00000);
   float* rec = a.recs + (size_t)t * a.rec_f;
   for (int e = tid; e < a.rec_f; e += NT) rec[e] = 0.f;
@@ -180,6 +158,51 @@ __global__ void __launch_bounds__(NIW_PACK_THREADS) niw_pack_kernel(const NiwPac
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(NIW_PACK_THREADS) niw_pack_kernel(const NiwPackArgs a) {
+  extern __shared__ double Ls[];   // [D][D+1]
+  const int D = a.D, LD = D + 1;
+  const int t = blockIdx.x, tid = threadIdx.x, NT = NIW_PACK_THREADS;
+  bool ok = true;
+  if (a.lfac != nullptr) {
+    const double* Lf = a.lfac + (size_t)t * D * D;
+    bool fine = true;
+    for (int e = tid; e < D * D; e += NT) {
+      const int i = e / D, j = e - i * D;
+      const double v = Lf[e];
+      Ls[i * LD + j] = v;
+      if (j <= i && (!(fabs(v) < CUDART_INF) || (i == j && !(v > 0.0)))) fine = false;
+    }
+    ok = __syncthreads_and(fine ? 1 : 0) != 0;
+  } else {
+    const float* A = a.inv_sigma + (size_t)t * D * D;
+    for (int e = tid; e < D * D; e += NT) {
+      const int i = e / D, j = e - i * D;
+      Ls[i * LD + j] = 0.5 * ((double)A[(size_t)i * D + j] + (double)A[(size_t)j * D + i]);
+    }
+    __syncthreads();
+    for (int j = 0; j < D; ++j) {
+      const double d = Ls[j * LD + j];
+      ok = ok && (d > 0.0) && (d < CUDART_INF);
+      const double ljj = sqrt(d);
+      __syncthreads();
+      if (tid == 0) Ls[j * LD + j] = ljj;
+      for (int i = j + 1 + tid; i < D; i += NT) Ls[i * LD + j] /= ljj;
+      __syncthreads();
+      // trailing update of the lower triangle: element (i, k), j < k <= i < D
+      const int m = D - j - 1;
+      for (int e = tid; e < m * m; e += NT) {
+        const int ii = e / m, kk = e - ii * m;
+        if (kk <= ii) {
+          const int i = j + 1 + ii, k = j + 1 + kk;
+          Ls[i * LD + k] -= Ls[i * LD + j] * Ls[k * LD + j];
+        }
+      }
+      __syncthreads();   // the next column's pivot is part of the trailing block
+    }
+  }
+  niw_pack_body(a, t, Ls, ok);
 }
 
 // Bias tables of the second-generation label kernel.  Its tiles are centred by the pivot's mean,

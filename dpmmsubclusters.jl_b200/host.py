@@ -11,6 +11,7 @@ Only the worker calls differ: every `@spawnat ... _worker!` becomes one GpuSweep
 from __future__ import annotations
 
 import copy
+import os
 import time
 from dataclasses import dataclass, field
 
@@ -408,20 +409,59 @@ def _gpu_factory(device=0):
     return make
 
 
+def _clusters_from_device(group, st, cfg):
+    """Rebuild the reference's host objects (local_cluster list, weights) from the final device state, so that
+    the tuple fit() returns, predict() and calculate_posterior() see what the host path would have left."""
+    hyper = group.model_hyperparams.distribution_hyper_params
+    sw = group.sweep
+    K = st.K
+    counts, sum_x, sum_xx = sw.suff_stats(list(range(1, K + 1)))
+    mu, lfac, logdet, w, lr = st.params
+    group.local_clusters = []
+    for k in range(K):
+        cps = []
+        for s_ in range(3):
+            ss = P.make_suff_stats(hyper, counts[k, s_], sum_x[k, s_], sum_xx[k, s_])
+            L = np.tril(lfac[k, s_])
+            inv = L @ L.T
+            with np.errstate(all="ignore"):
+                Sig = np.linalg.inv(inv) if np.isfinite(inv).all() else np.full_like(inv, np.nan)
+            dist = P.mv_gaussian(mu[k, s_].astype(F32), Sig.astype(F32), inv.astype(F32), float(logdet[k, s_]), L.T.copy())
+            cps.append(cluster_parameters(hyper, dist, ss, P.calc_posterior(hyper, ss)))
+        sp = splittable_cluster_params(cps[0], cps[1], cps[2], lr[k].astype(np.float64), bool(st.splittable[k]),
+                                       st.hist[k].copy())
+        group.local_clusters.append(local_cluster(sp, group.model_hyperparams.total_dim, int(counts[k, 0]),
+                                                  int(counts[k, 1]), int(counts[k, 2])))
+    group.weights = np.asarray(w, F32)
+
+
 def dp_parallel(all_data, local_hyper_params, α_param, iters=100, init_clusters=1, seed=None, verbose=True,
                 save_model=False, burnout=15, gt=None, max_clusters=np.inf, outlier_weight=0, outlier_params=None,
-                smart_splits=False, *, sweep_factory=None, shard=None, comm=None, device=0):
-    """dp_parallel :121-157.  `sweep_factory`, `shard`, `comm`, `device` have no reference counterpart:
-    they select the device / inject a test double / attach the multi-GPU communicator."""
+                smart_splits=False, *, sweep_factory=None, shard=None, comm=None, device=0, device_params=None):
+    """dp_parallel :121-157.  `sweep_factory`, `shard`, `comm`, `device`, `device_params` have no reference
+    counterpart: they select the device / inject a test double / attach the multi-GPU communicator / choose
+    where the parameter step runs (default: on the device for the NIW prior; False = the Python
+    mirror of the reference's master functions below)."""
     if outlier_weight or smart_splits or save_model:
         raise NotImplementedError("outlier component, smart splits and checkpoints are out of scope (DESIGN.md 6)")
+    if (comm is not None or shard is not None) and seed is None:
+        # every rank must draw the same parameters and take the same split / merge decisions
+        raise ValueError("multi-GPU runs (comm / shard) need an explicit seed shared by all ranks")
     cfg = Settings(iterations=int(iters), initial_clusters=int(init_clusters), burnout_period=int(burnout),
                    max_num_of_clusters=max_clusters, use_verbose=bool(verbose), ground_truth=gt)
     rng = np.random.default_rng(seed)
     dp_model = init_model_from_data(all_data, local_hyper_params, α_param, cfg, seed,
                                     sweep_factory or _gpu_factory(device), shard)
+    sw = dp_model.group.sweep
     if comm is not None:
-        dp_model.group.sweep.comm_init(*comm)
+        sw.comm_init(*comm)
+    if device_params is None:
+        device_params = os.environ.get("DPMM_DEVICE_PARAMS", "1") != "0"
+    if device_params and isinstance(local_hyper_params, P.niw_hyperparams) and hasattr(sw, "sample_params"):
+        from . import host_device as HD
+        st, iter_count, nmi, ll, kh = HD.run_model_device(dp_model, cfg, rng, normalized_mutual_info)
+        _clusters_from_device(dp_model.group, st, cfg)
+        return dp_model, iter_count, nmi, ll, kh
     init_first_clusters(dp_model, cfg, rng)
     return run_model(dp_model, 1, cfg, rng)
 

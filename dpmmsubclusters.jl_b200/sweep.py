@@ -138,7 +138,7 @@ class GpuSweep:
         `out`: an earlier result of the same shape to be overwritten (saves the allocation and the
         first-touch page faults of ~0.5 MB per call in a tight loop)."""
         if indices is None:
-            m, idx_p, idx = max(self.K, 1), None, None
+            m, idx_p, idx = max(int(self.lib.dpmm_num_clusters(self.h)), 1), None, None
         else:
             idx = _i64(indices)
             m, idx_p = len(idx), _ptr(idx, C.c_int64)
@@ -161,6 +161,54 @@ class GpuSweep:
         self._ck(self.lib.dpmm_suff_stats(self.h, idx_p, m, _ptr(counts, C.c_int64), _ptr(sum_x, C.c_double),
                                           _ptr(sum_xx, C.c_double)))
         return counts, sum_x, sum_xx
+
+    # ---- device-side parameter step (NIW) ----
+    def set_hyper_niw(self, kappa, m, nu, psi, alpha):
+        m = np.ascontiguousarray(m, np.float64).reshape(-1)
+        psi = np.ascontiguousarray(psi, np.float64)
+        assert m.shape == (self.D,) and psi.shape == (self.D, self.D)
+        self._ck(self.lib.dpmm_set_hyper_niw(self.h, float(kappa), _ptr(m, C.c_double), float(nu), _ptr(psi, C.c_double),
+                                             float(alpha)))
+
+    def posterior_step(self, indices=None, splittable=None, from_table=False, fetch=True):
+        """Statistics (unless from_table) -> table -> posteriors.  Returns (counts [m,3] i64, logml [m,3] f64,
+        merge [K,K] f64 or None); `splittable` (bool [K]) requests the merge table."""
+        if indices is None:
+            m, idx_p, idx = max(int(self.lib.dpmm_num_clusters(self.h)), 1), None, None
+        else:
+            idx = _i64(indices)
+            m, idx_p = len(idx), _ptr(idx, C.c_int64)
+        if not fetch:
+            self._ck(self.lib.dpmm_posterior_step(self.h, idx_p, m, 1 if from_table else 0, None, 0, None, None, None))
+            return None
+        counts = np.zeros((m, 3), np.int64)
+        logml = np.zeros((m, 3), np.float64)
+        merge, sp, km = None, None, 0
+        if splittable is not None and len(splittable) > 1:
+            sp = np.ascontiguousarray(splittable, np.uint8)
+            km = len(sp)
+            merge = np.empty((km, km), np.float64)
+        self._ck(self.lib.dpmm_posterior_step(self.h, idx_p, m, 1 if from_table else 0, _ptr(sp, C.c_uint8), km,
+                                              _ptr(counts, C.c_int64), _ptr(logml, C.c_double), _ptr(merge, C.c_double)))
+        return counts, logml, merge
+
+    def sample_params(self, K, from_prior=False, unit_weights=False):
+        self._ck(self.lib.dpmm_sample_params(self.h, int(K), 1 if from_prior else 0, 1 if unit_weights else 0))
+        self.K = int(K)
+
+    def params_merge(self, i, j):
+        self._ck(self.lib.dpmm_params_merge(self.h, int(i), int(j)))
+
+    def get_params_niw(self, K):
+        """(mu [K,3,D] f32, lfac [K,3,D,D] f64 with invSigma = L L', logdet [K,3] f32, weights [K] f32, lr [K,2] f32)."""
+        mu = np.empty((K, 3, self.D), np.float32)
+        lf = np.empty((K, 3, self.D, self.D), np.float64)
+        ld = np.empty((K, 3), np.float32)
+        w = np.empty(K, np.float32)
+        lr = np.empty((K, 2), np.float32)
+        self._ck(self.lib.dpmm_get_params_niw(self.h, int(K), _ptr(mu, C.c_float), _ptr(lf, C.c_double), _ptr(ld, C.c_float),
+                                              _ptr(w, C.c_float), _ptr(lr, C.c_float)))
+        return mu, lf, ld, w, lr
 
     # ---- relabel ----
     def apply_split(self, indices, new_indices):

@@ -88,8 +88,8 @@ int dpmm_set_sublabels(dpmm_ctx* ctx, const int64_t* sublabels);
  *   inv_sigma float32 [3K][D][D]     mv_gaussian.invSigma  (:15; symmetric, either major order)
  *   logdet    float32 [3K]           mv_gaussian.logdetSigma (:16)
  *   weights   float32 [K]            group.weights (ds.jl:57);  lr_weights float32 [K][2] (ds.jl:33)
- * The library factors invSigma = U'U on the host in float64 (the reference carries the same factor
- * in mv_gaussian.invChol, :17) and evaluates z'invSigma z as |U z|^2. */
+ * The library factors invSigma = U'U on the device in float64 (niw_pack_kernel; the reference carries
+ * the same factor in mv_gaussian.invChol, :17) and evaluates z'invSigma z as |U z|^2. */
 int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t k, const float* mu, const float* inv_sigma,
                         const float* logdet, const float* weights, const float* lr_weights);
 /* log_p float32 [3K][D] = multinomial_dist.alpha (log-probabilities, multinomial_dist.jl:8-10). */
@@ -120,6 +120,44 @@ int dpmm_sample_sublabels(dpmm_ctx* ctx);
  *   sum_xx  double [m][3][D][D]      S (symmetric; NIW only, ignored for multinomial) */
 int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_indices, int64_t* counts,
                     double* sum_x, double* sum_xx);
+
+/* Number of label values in use = max(K of the last set_params, largest label): the row count of a
+ * dpmm_suff_stats(indices = NULL) result.  With indices == NULL, n_indices must be 0 or exactly this. */
+int dpmm_num_clusters(const dpmm_ctx* ctx);
+
+/* ---- device-side parameter step (NIW) --------------------------------------------
+ * Optional: the host may keep sampling parameters itself (dpmm_set_params_niw).  With these calls the
+ * per-iteration master work that scales with K D^3 runs next to the statistics:
+ *   calc_posterior / log_marginal_likelihood   src/priors/niw.jl:20-31, 53-62
+ *   sample_distribution                        src/priors/niw.jl:34-40
+ *   sample_cluster_params / sample_clusters!   src/shared_actions.jl:41-66, src/local_clusters_actions.jl:417-437
+ *   should_merge! (the merged log marginal)    src/shared_actions.jl:21-38
+ * The host keeps the Hastings accept / reject decisions on 3K scalars (+ the K x K merge table). */
+
+/* niw_hyperparams (niw.jl:6-11: kappa, m[D], nu, psi[D][D]) and the concentration alpha (ds.jl:9). */
+int dpmm_set_hyper_niw(dpmm_ctx* ctx, double kappa, const double* m, double nu, const double* psi, double alpha);
+/* update_suff_stats_posterior! (local_clusters_actions.jl:206-254) kept on the device: statistics of the
+ * listed clusters (NULL = all) -> all-reduce -> persistent table -> posterior hyper-parameters and log
+ * marginal likelihoods of {cluster, left, right}.  from_table != 0: skip the statistics and re-evaluate the
+ * listed table rows (after dpmm_params_merge).  splittable[k_merge] (optional): also evaluate, for every
+ * pair i < j of splittable non-empty clusters, the log marginal likelihood of the merged cluster
+ * (check_and_merge!, :385-413) into merge_logml[k_merge][k_merge] (NaN elsewhere).
+ * Outputs (host, optional): counts int64 [m][3], logml double [m][3].  Synchronises iff an output is given. */
+int dpmm_posterior_step(dpmm_ctx* ctx, const int64_t* indices, int32_t n_indices, int32_t from_table,
+                        const uint8_t* splittable, int32_t k_merge, int64_t* counts, double* logml,
+                        double* merge_logml);
+/* sample_clusters! + broadcast_cluster_params (:417-437, :518-549) on the device: draw the 3K distributions
+ * from the posterior table (from_prior != 0: from the prior), the sub-cluster weights Dirichlet(N_l + a/2,
+ * N_r + a/2) and the mixture weights Dirichlet(N_1..N_K, a) (unit_weights != 0: 1/K, as
+ * init_first_clusters!, dp-parallel-sampling.jl:77), and pack them for the sweep.  Replaces dpmm_set_params_niw. */
+int dpmm_sample_params(dpmm_ctx* ctx, int32_t k, int32_t from_prior, int32_t unit_weights);
+/* merge_clusters_to_splittable (shared_actions.jl:12-18) on the statistics table: cluster i <- {i + j, i, j},
+ * cluster j <- empty (1-based).  Follow with dpmm_posterior_step(from_table = 1) for i. */
+int dpmm_params_merge(dpmm_ctx* ctx, int64_t i, int64_t j);
+/* The parameters of the last dpmm_sample_params: mu float32 [3K][D], lfac double [3K][D][D] (L lower,
+ * invSigma = L L'), logdet float32 [3K] (log det Sigma), weights float32 [K], lr_weights float32 [K][2]. */
+int dpmm_get_params_niw(dpmm_ctx* ctx, int32_t k, float* mu, double* lfac, float* logdet, float* weights,
+                        float* lr_weights);
 
 /* ---- relabelling after split / merge / compaction ------------------------------------------- */
 

@@ -67,7 +67,7 @@ def test_gpu_and_oracle_hosts_statistically_indistinguishable(pkg):
     x, labels, _, _ = pkg.generate_gaussian_data(3000, 2, 4, 100.0, np.random.default_rng(11))
     nmi_g, nmi_o, k_g, k_o, same = [], [], [], [], 0
     for seed in range(10):
-        g = H.fit(x, 10.0, iters=40, seed=seed, gt=labels, burnout=5)
+        g = H.fit(x, 10.0, iters=40, seed=seed, gt=labels, burnout=5, device_params=False)
         o = H.fit(x, 10.0, iters=40, seed=seed, gt=labels, burnout=5, sweep_factory=oracle_factory)
         nmi_g.append(g[4][-1]); nmi_o.append(o[4][-1]); k_g.append(len(g[1])); k_o.append(len(o[1]))
         same += int(np.array_equal(g[0], o[0]))
