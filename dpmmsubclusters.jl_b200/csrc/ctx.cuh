@@ -45,6 +45,7 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, UidBlob, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -166,6 +167,13 @@ struct dpmm_ctx {
   NcclApi nccl;
   void* comm = nullptr;
   int world = 1, rank = 0;
+  // one-shot all-reduce of the packed statistics over peer memory (NVLink): every rank maps every peer's
+  // exchange region [flags | buffer 0 | buffer 1] through CUDA IPC; see kernels_ipc.cuh
+  bool ipc_ok = false;
+  uint8_t* ipc_local = nullptr;
+  uint8_t* ipc_peer[16] = {nullptr};
+  size_t ipc_cap = 0;        // doubles per buffer
+  uint32_t ipc_epoch = 0;
 };
 
 inline thread_local std::string g_err;

@@ -16,6 +16,7 @@
 #include "kernels_gauss.cuh"
 #include "kernels_gauss_tc.cuh"
 #include "kernels_gauss_tc2.cuh"
+#include "kernels_ipc.cuh"
 #include "kernels_mnm.cuh"
 #include "kernels_mnm_tc.cuh"
 #include "kernels_pack.cuh"
@@ -318,6 +319,9 @@ extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
   if (env_int("DPMM_VERBOSE", 0))
     fprintf(stderr, "[dpmm] fused sub-label+statistics launches %lld, statistics served from them %lld, exact recomputations %lld\n",
             (long long)ctx->n_fused, (long long)ctx->n_cached, (long long)ctx->n_recompute);
+  for (int p = 0; p < IPC_MAX_WORLD; ++p)
+    if (ctx->ipc_peer[p]) cudaIpcCloseMemHandle(ctx->ipc_peer[p]);
+  if (ctx->ipc_local) cudaFree(ctx->ipc_local);
   if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
   for (auto& t : ctx->tev) {
     cudaEventDestroy(t.a);
@@ -1136,19 +1140,38 @@ static int stats_compute(dpmm_ctx* ctx, const int64_t* indices, int32_t n_indice
     mnm_stats_kernel<<<ctx->sm_count * occ, 256, 0, ctx->stream>>>(sa);
     CK(cudaGetLastError());
   }
+  // with a communicator and mapped peer memory the packed statistics go straight into this rank's exchange
+  // buffer and one kernel reduces over NVLink; otherwise they go to outbuf (and through ncclAllReduce)
+  const size_t nred = (size_t)m * 3 * rec + 1;
+  const bool use_ipc = ctx->comm != nullptr && ctx->ipc_ok && nred <= ctx->ipc_cap;
+  const uint32_t epoch = use_ipc ? ++ctx->ipc_epoch : 0;
+  double* fin = use_ipc ? reinterpret_cast<double*>(ctx->ipc_local + IPC_FLAG_BYTES) + (size_t)(epoch & 1) * ctx->ipc_cap : ctx->outbuf;
   {
     KernelTimer kt(ctx, TK_STATS_AUX);
     const int T = 256;
     dim3 grid((unsigned)std::min((rec + T - 1) / T, 64), (unsigned)m);
-    CK(cudaMemsetAsync(ctx->outbuf + (size_t)m * 3 * rec, 0, 8, ctx->stream));
+    CK(cudaMemsetAsync(fin + (size_t)m * 3 * rec, 0, 8, ctx->stream));
     stats_finalize_kernel<<<grid, T, 0, ctx->stream>>>(ctx->acc, ctx->seg_off, ctx->lr_cursor, all ? nullptr : ctx->idx_list, m, D, rec,
-                                                       ctx->prior == DPMM_PRIOR_NIW ? 1 : 0, ctx->outbuf,
+                                                       ctx->prior == DPMM_PRIOR_NIW ? 1 : 0, fin,
                                                        (stats_tc || cached) ? ctx->centers : nullptr,
                                                        cached ? ctx->lcount : nullptr,
-                                                       cached ? ctx->outbuf + (size_t)m * 3 * rec : nullptr);
+                                                       cached ? fin + (size_t)m * 3 * rec : nullptr);
     CK(cudaGetLastError());
   }
-  if (ctx->comm != nullptr) {
+  if (use_ipc) {
+    IpcReduceArgs ia{};
+    ia.world = ctx->world; ia.rank = ctx->rank; ia.epoch = epoch; ia.n = nred; ia.out = ctx->outbuf;
+    ia.my_flags = reinterpret_cast<const uint32_t*>(ctx->ipc_local);
+    for (int r = 0; r < ctx->world; ++r) {
+      uint8_t* base = r == ctx->rank ? ctx->ipc_local : ctx->ipc_peer[r];
+      ia.src[r] = reinterpret_cast<const double*>(base + IPC_FLAG_BYTES) + (size_t)(epoch & 1) * ctx->ipc_cap;
+      ia.peer_flags[r] = reinterpret_cast<uint32_t*>(base);
+    }
+    KernelTimer kt(ctx, TK_ALLREDUCE);
+    const unsigned grid = (unsigned)std::min<size_t>((nred / 2 + 255) / 256, (size_t)ctx->sm_count * 4);
+    ipc_allreduce_kernel<<<grid, 256, 0, ctx->stream>>>(ia);
+    CK(cudaGetLastError());
+  } else if (ctx->comm != nullptr) {
     KernelTimer kt(ctx, TK_ALLREDUCE);
     // aggregate_suff_stats across workers (niw.jl:64-66; local_clusters_actions.jl:194-196, 246-248)
     // (the risk slot always travels, so the element count cannot differ between ranks)
@@ -1534,6 +1557,7 @@ static int load_nccl(dpmm_ctx* ctx, NcclApi& api) {
   api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
   api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
   api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+  api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
   api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
   api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
   if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy || !api.GetErrorString)
@@ -1564,5 +1588,46 @@ extern "C" int dpmm_comm_init(dpmm_ctx* ctx, const void* unique_id128, int32_t r
   if (r != 0) return fail(ctx, DPMM_ENCCL, std::string("ncclCommInitRank: ") + ctx->nccl.GetErrorString(r));
   ctx->world = world_size;
   ctx->rank = rank;
+  // ---- peer-memory exchange regions (optional: any failure leaves the NCCL all-reduce in charge) ----
+  if (world_size > 1 && world_size <= IPC_MAX_WORLD && ctx->nccl.AllGather && env_int("DPMM_ALLREDUCE_IPC", 1) != 0) {
+    const size_t cap = ((size_t)32 << 20) / 8;   // 32 MB per buffer
+    const size_t bytes = IPC_FLAG_BYTES + 2 * cap * 8;
+    cudaIpcMemHandle_t mine;
+    char* hbuf = nullptr;
+    bool ok = cudaMalloc((void**)&ctx->ipc_local, bytes) == cudaSuccess && cudaMemset(ctx->ipc_local, 0, bytes) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine, ctx->ipc_local) == cudaSuccess &&
+              cudaMalloc((void**)&hbuf, (size_t)(world_size + 1) * sizeof(mine)) == cudaSuccess;
+    std::vector<cudaIpcMemHandle_t> all(world_size);
+    if (ok) {
+      ok = cudaMemcpy(hbuf + (size_t)world_size * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice) == cudaSuccess &&
+           ctx->nccl.AllGather(hbuf + (size_t)world_size * sizeof(mine), hbuf, sizeof(mine), /*ncclChar*/ 0, ctx->comm, ctx->stream) == 0 &&
+           cudaStreamSynchronize(ctx->stream) == cudaSuccess &&
+           cudaMemcpy(all.data(), hbuf, (size_t)world_size * sizeof(mine), cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    int nopen = 0;
+    for (int p = 0; ok && p < world_size; ++p) {
+      if (p == rank) continue;
+      ok = cudaIpcOpenMemHandle((void**)&ctx->ipc_peer[p], all[p], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      if (ok) ++nopen;
+    }
+    if (hbuf) cudaFree(hbuf);
+    // every rank must take the same path: agree through one more collective (sum of the ok flags)
+    double* agree = nullptr;
+    int all_ok = 0;
+    if (cudaMalloc((void**)&agree, 8) == cudaSuccess) {
+      const double v = ok ? 1.0 : 0.0;
+      double got = 0.0;
+      if (cudaMemcpy(agree, &v, 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+          ctx->nccl.AllReduce(agree, agree, 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->comm, ctx->stream) == 0 &&
+          cudaStreamSynchronize(ctx->stream) == cudaSuccess && cudaMemcpy(&got, agree, 8, cudaMemcpyDeviceToHost) == cudaSuccess)
+        all_ok = (int)llround(got) == world_size;
+      cudaFree(agree);
+    }
+    cudaGetLastError();   // a failed optional step must not poison later calls
+    ctx->ipc_ok = all_ok != 0;
+    ctx->ipc_cap = cap;
+    if (env_int("DPMM_VERBOSE", 0))
+      fprintf(stderr, "[dpmm] rank %d: peer-memory all-reduce %s (%d peers mapped)\n", rank, ctx->ipc_ok ? "enabled" : "unavailable, using NCCL", nopen);
+  }
   return 0;
 }

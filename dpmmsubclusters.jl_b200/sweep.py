@@ -30,13 +30,14 @@ class GpuSweep:
 
     def __init__(self, x, prior_kind, seed=0, global_offset=0, device=0):
         self.lib = L.load()
-        x = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+        x = np.asarray(x, dtype=np.float32)
         if x.ndim != 2:
             raise ValueError("x must be D x N")
         self.D, self.n = int(x.shape[0]), int(x.shape[1])
         self.prior_kind = int(prior_kind)
         self.K = 0
-        # D x N column-major (Julia) == N x D row-major: every point is D contiguous floats
+        # D x N column-major (Julia, numpy order="F") == N x D row-major: every point is D contiguous floats.
+        # A column-major array goes up as it is; a row-major (numpy default) one is transposed once.
         xt = np.ascontiguousarray(x.T)
         h = C.c_void_p()
         rc = self.lib.dpmm_create(C.byref(h), _ptr(xt, C.c_float), self.n, self.D, self.prior_kind, int(device),
