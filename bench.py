@@ -440,8 +440,11 @@ def main():
     if niw:
         hy = case["hyper"]
         g.set_hyper_niw(hy.κ, hy.m, hy.ν, hy.ψ, case["alpha"])
-        for _ in range(3):
+        g.posterior_step(None)         # the statistics / posterior tables of the current (converged) labels
+        for _ in range(5):
             res = iteration_e2e()
+        assert (res[0][:, 0] > 0).sum() == case["K"], "the e2e state lost clusters"
+
         barrier()
         align()
         t0 = time.perf_counter()

@@ -47,6 +47,7 @@ SIGNATURES = {
     "dpmm_sample_params": (C.c_int, [_p, _i32, _i32, _i32]),
     "dpmm_params_merge": (C.c_int, [_p, _i64, _i64]),
     "dpmm_get_params_niw": (C.c_int, [_p, _i32, _f32p, _f64p, _f32p, _f32p, _f32p]),
+    "dpmm_predict_niw": (C.c_int, [_p, _i32, _f32p, _f32p, _f32p, _f32p, _i64p, _f32p]),
     "dpmm_apply_split": (C.c_int, [_p, _i64p, _i64p, _i32]),
     "dpmm_apply_merge": (C.c_int, [_p, _i64p, _i64p, _i32]),
     "dpmm_remove_empty": (C.c_int, [_p, _i64p, _i32]),

@@ -131,9 +131,14 @@ struct dpmm_ctx {
   int32_t* item_ctr = nullptr;  // [0]=n_items [1]=next_item
   int chunk = 1024;
 
-  // pinned staging
+  // pinned staging: hstage for results coming back (the call synchronises anyway); two alternating upload
+  // buffers, each guarded by an event recorded after its last copy, so that an upload never waits for the stream
   void* hstage = nullptr;
   size_t hstage_bytes = 0;
+  void* hup[2] = {nullptr, nullptr};
+  size_t hup_bytes[2] = {0, 0};
+  cudaEvent_t hup_ev[2] = {nullptr, nullptr};
+  int hup_i = 0;
 
   bool hist_valid = false, sorted = false, partitioned = false;
   int64_t n_fused = 0, n_cached = 0, n_recompute = 0;   // DPMM_VERBOSE counters
@@ -233,6 +238,28 @@ inline int ensure_stage(dpmm_ctx* ctx, size_t bytes) {
   size_t want = std::max(bytes, (size_t)1 << 20);
   CK(cudaMallocHost(&ctx->hstage, want));
   ctx->hstage_bytes = want;
+  return 0;
+}
+
+// Next upload staging buffer (>= bytes): waits only for the copies issued from THIS buffer two uploads ago.
+inline int upload_acquire(dpmm_ctx* ctx, size_t bytes, void** out) {
+  const int i = ctx->hup_i;
+  ctx->hup_i ^= 1;
+  if (ctx->hup_ev[i] == nullptr) CK(cudaEventCreateWithFlags(&ctx->hup_ev[i], cudaEventDisableTiming));
+  CK(cudaEventSynchronize(ctx->hup_ev[i]));
+  if (ctx->hup_bytes[i] < bytes) {
+    if (ctx->hup[i]) cudaFreeHost(ctx->hup[i]);
+    ctx->hup[i] = nullptr;
+    ctx->hup_bytes[i] = 0;
+    const size_t want = std::max(bytes, (size_t)1 << 20);
+    CK(cudaMallocHost(&ctx->hup[i], want));
+    ctx->hup_bytes[i] = want;
+  }
+  *out = ctx->hup[i];
+  return i;
+}
+inline int upload_release(dpmm_ctx* ctx, int i) {
+  CK(cudaEventRecord(ctx->hup_ev[i], ctx->stream));
   return 0;
 }
 

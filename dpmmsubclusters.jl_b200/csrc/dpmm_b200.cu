@@ -337,6 +337,10 @@ extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (ctx->hstage) cudaFreeHost(ctx->hstage);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->hup[i]) cudaFreeHost(ctx->hup[i]);
+    if (ctx->hup_ev[i]) cudaEventDestroy(ctx->hup_ev[i]);
+  }
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -375,17 +379,18 @@ static int run_relabel(dpmm_ctx* ctx, const std::vector<int32_t>& ll, const std:
   int rc = ensure_k(ctx, K);
   if (rc) return rc;
   const size_t b4 = (size_t)K * 4;
-  rc = ensure_stage(ctx, 2 * b4 + K);
-  if (rc) return rc;
-  // the staging buffer may still be in flight from a previous async copy
-  CK(cudaStreamSynchronize(ctx->stream));
-  char* h = (char*)ctx->hstage;
+  void* hs = nullptr;
+  const int slot = upload_acquire(ctx, 2 * b4 + K, &hs);
+  if (slot < 0) return slot;
+  char* h = (char*)hs;
   memcpy(h, ll.data(), b4);
   memcpy(h + b4, lr.data(), b4);
   memcpy(h + 2 * b4, rule.data(), K);
   CK(cudaMemcpyAsync(ctx->lut_l, h, b4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->lut_r, h + b4, b4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->rule, h + 2 * b4, K, cudaMemcpyHostToDevice, ctx->stream));
+  rc = upload_release(ctx, slot);
+  if (rc) return rc;
   if (uses_rng) ctx->call += 1;
   {
     KernelTimer kt(ctx, TK_RELABEL);
@@ -717,10 +722,10 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
   // raw parameters -> pinned staging -> device; the factorisation and packing run on the device
   const size_t raw_floats = nrec * D + nrec * D * D + nrec;
   const size_t bytes = (raw_floats + K + 2 * K) * sizeof(float);
-  rc = ensure_stage(ctx, bytes);
-  if (rc) return rc;
-  CK(cudaStreamSynchronize(ctx->stream));  // staging buffer reuse
-  float* h_mu = (float*)ctx->hstage;
+  void* hs = nullptr;
+  const int slot = upload_acquire(ctx, bytes, &hs);   // alternating pinned buffers: no stream synchronisation
+  if (slot < 0) return slot;
+  float* h_mu = (float*)hs;
   float* h_inv = h_mu + nrec * D;
   float* h_ld = h_inv + nrec * D * D;
   float* h_logw = h_ld + nrec;
@@ -732,6 +737,8 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
   CK(cudaMemcpyAsync(ctx->raw_params, h_mu, raw_floats * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->logw, h_logw, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->loglr, h_loglr, (size_t)2 * K * 4, cudaMemcpyHostToDevice, ctx->stream));
+  rc = upload_release(ctx, slot);
+  if (rc) return rc;
   rc = niw_pack_launch(ctx, K, nullptr);
   if (rc) return rc;
   return 0;
@@ -753,10 +760,10 @@ extern "C" int dpmm_set_params_multinomial(dpmm_ctx* ctx, int32_t K, const float
   const int NP = (D + 31) / 32;
   const size_t wfl = mtc ? (size_t)3 * NP * MTC_N * 32 : 0;
   const size_t bytes = (nrec * D + (size_t)D * KP + K + 2 * K + wfl) * sizeof(float);
-  rc = ensure_stage(ctx, bytes);
-  if (rc) return rc;
-  CK(cudaStreamSynchronize(ctx->stream));
-  float* h_recs = (float*)ctx->hstage;
+  void* hs = nullptr;
+  const int slot = upload_acquire(ctx, bytes, &hs);
+  if (slot < 0) return slot;
+  float* h_recs = (float*)hs;
   float* h_t = h_recs + nrec * D;
   float* h_logw = h_t + (size_t)D * KP;
   float* h_loglr = h_logw + K;
@@ -798,6 +805,8 @@ extern "C" int dpmm_set_params_multinomial(dpmm_ctx* ctx, int32_t K, const float
   CK(cudaMemcpyAsync(ctx->logp_t, h_t, (size_t)D * KP * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->logw, h_logw, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->loglr, h_loglr, (size_t)2 * K * 4, cudaMemcpyHostToDevice, ctx->stream));
+  rc = upload_release(ctx, slot);
+  if (rc) return rc;
   ctx->K = K;
   ctx->KP = KP;
   ctx->params_set = true;
@@ -1418,6 +1427,62 @@ extern "C" int dpmm_get_params_niw(dpmm_ctx* ctx, int32_t K, float* mu, double* 
   if (lfac) CK(cudaMemcpy(lfac, ctx->lfac, nrec * D * D * 8, cudaMemcpyDeviceToHost));
   if (weights) CK(cudaMemcpy(weights, ctx->w_out, (size_t)K * 4, cudaMemcpyDeviceToHost));
   if (lr_weights) CK(cudaMemcpy(lr_weights, ctx->lr_out, (size_t)2 * K * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int dpmm_predict_niw(dpmm_ctx* ctx, int32_t K, const float* u, const float* mu, const float* tconst,
+                                const float* df, int64_t* labels, float* probs) {
+  NEED(ctx && u && mu && tconst && df && labels, DPMM_EINVAL, "NULL argument");
+  NEED(ctx->prior == DPMM_PRIOR_NIW, DPMM_ESTATE, "context was created with the multinomial prior");
+  NEED(K >= 1 && K <= DPMM_MAX_K, DPMM_ELIMIT, "K out of range");
+  CK(cudaSetDevice(ctx->device));
+  const int D = ctx->D;
+  const size_t nf = (size_t)K * D * D + (size_t)K * D + 2 * (size_t)K;
+  float* dpar = nullptr;
+  int32_t* dlab = nullptr;
+  float* dprob = nullptr;
+  CK(cudaMalloc((void**)&dpar, nf * 4));
+  auto cleanup = [&]() {
+    if (dpar) cudaFree(dpar);
+    if (dlab) cudaFree(dlab);
+    if (dprob) cudaFree(dprob);
+  };
+#define CKP(call)                                                                                        \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess) {                                                                            \
+      cleanup();                                                                                         \
+      return fail(ctx, DPMM_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                \
+    }                                                                                                    \
+  } while (0)
+  CKP(cudaMalloc((void**)&dlab, (size_t)ctx->n * 4));
+  if (probs) CKP(cudaMalloc((void**)&dprob, (size_t)ctx->n * K * 4));
+  float* d_u = dpar;
+  float* d_mu = d_u + (size_t)K * D * D;
+  float* d_tc = d_mu + (size_t)K * D;
+  float* d_df = d_tc + K;
+  CKP(cudaMemcpyAsync(d_u, u, (size_t)K * D * D * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaMemcpyAsync(d_mu, mu, (size_t)K * D * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaMemcpyAsync(d_tc, tconst, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaMemcpyAsync(d_df, df, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
+  NiwPredictArgs pa{};
+  pa.x = ctx->x; pa.n = ctx->n; pa.D = D; pa.K = K; pa.u = d_u; pa.mu = d_mu; pa.tconst = d_tc; pa.df = d_df;
+  pa.labels = dlab; pa.probs = dprob;
+  const size_t sm = (size_t)8 * (D + K) * 4;
+  if (sm > 48 * 1024) CKP(cudaFuncSetAttribute(niw_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  {
+    KernelTimer kt(ctx, TK_LABEL);
+    const unsigned grid = (unsigned)std::min<int64_t>((ctx->n + 7) / 8, (int64_t)ctx->sm_count * 8);
+    niw_predict_kernel<<<grid, 256, sm, ctx->stream>>>(pa);
+    CKP(cudaGetLastError());
+  }
+  std::vector<int32_t> h((size_t)ctx->n);
+  CKP(cudaMemcpyAsync(h.data(), dlab, (size_t)ctx->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (probs) CKP(cudaMemcpyAsync(probs, dprob, (size_t)ctx->n * K * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CKP(cudaStreamSynchronize(ctx->stream));
+#undef CKP
+  for (int64_t i = 0; i < ctx->n; ++i) labels[i] = (int64_t)h[i] + 1;
+  cleanup();
   return 0;
 }
 

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(T2_THREADS(D), 1) gauss_label_tc2_kernel(const
   if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
   for (int j = tid; j <= nkeys; j += T2_THREADS(D)) B[j] = __ldg(a.seg_off + j);
   {   // screen images: already in the shared-memory layout
-    const int nf4 = nch * (KS / 8 + 1) * 256;
+    const int nf4 = nch * (KS / 8) * 256;
     const float4* src = reinterpret_cast<const float4*>(a.wscr);
     float4* dst = reinterpret_cast<float4*>(scrsm);
     for (int e = tid; e < nf4; e += T2_THREADS(D)) dst[e] = __ldg(src + e);

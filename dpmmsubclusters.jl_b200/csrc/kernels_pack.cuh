@@ -4,8 +4,10 @@
 //   invSigma (Float32, symmetrised) -> Float64 Cholesky  invSigma = L L'  -> U = L' rounded to Float32,
 //   stored by columns (FMA path records) and, for the cluster distributions of the tensor-core path,
 //   by rows (K-major B operand) with b = U mu and |U|_F;  c = (D^2 * Float32(log 2pi) + logdetSigma)/2.
-// The reference carries the same factor (mv_gaussian.invChol, niw.jl:38-39).  A non positive definite
-// or NaN input gives NaN factors, i.e. NaN log-likelihoods, exactly like the reference's arithmetic.
+// The reference carries the same factor (mv_gaussian.invChol, niw.jl:38-39) but evaluates z' invSigma z
+// directly (mv_gaussian.jl:21-24).  A Float32-rounded invSigma that lost positive definiteness by rounding
+// alone is factored with a tiny diagonal jitter (see niw_pack_kernel); an indefinite or NaN input gives NaN
+// factors, i.e. NaN log-likelihoods.
 #pragma once
 #include "common.cuh"
 #include "kernels_gauss.cuh"   // gauss_col_off
@@ -176,30 +178,43 @@ __global__ void __launch_bounds__(NIW_PACK_THREADS) niw_pack_kernel(const NiwPac
     }
     ok = __syncthreads_and(fine ? 1 : 0) != 0;
   } else {
+    // invSigma arrives rounded to Float32 (mv_gaussian.jl:15).  For a badly conditioned cluster (condition number
+    // above ~1e7) the rounded matrix can lose positive definiteness by a hair although the reference's direct
+    // z' invSigma z stays finite and meaningful; the factorisation is then retried with a relative diagonal
+    // jitter of 1e-7 .. 1e-4 (far inside the 1e-4 log-likelihood tolerance).  A genuinely indefinite matrix still
+    // fails and gives NaN log-likelihoods.
     const float* A = a.inv_sigma + (size_t)t * D * D;
-    for (int e = tid; e < D * D; e += NT) {
-      const int i = e / D, j = e - i * D;
-      Ls[i * LD + j] = 0.5 * ((double)A[(size_t)i * D + j] + (double)A[(size_t)j * D + i]);
-    }
-    __syncthreads();
-    for (int j = 0; j < D; ++j) {
-      const double d = Ls[j * LD + j];
-      ok = ok && (d > 0.0) && (d < CUDART_INF);
-      const double ljj = sqrt(d);
+    const double jit[5] = {0.0, 1e-7, 1e-6, 1e-5, 1e-4};
+    for (int attempt = 0; attempt < 5; ++attempt) {
       __syncthreads();
-      if (tid == 0) Ls[j * LD + j] = ljj;
-      for (int i = j + 1 + tid; i < D; i += NT) Ls[i * LD + j] /= ljj;
-      __syncthreads();
-      // trailing update of the lower triangle: element (i, k), j < k <= i < D
-      const int m = D - j - 1;
-      for (int e = tid; e < m * m; e += NT) {
-        const int ii = e / m, kk = e - ii * m;
-        if (kk <= ii) {
-          const int i = j + 1 + ii, k = j + 1 + kk;
-          Ls[i * LD + k] -= Ls[i * LD + j] * Ls[k * LD + j];
-        }
+      for (int e = tid; e < D * D; e += NT) {
+        const int i = e / D, j = e - i * D;
+        double v = 0.5 * ((double)A[(size_t)i * D + j] + (double)A[(size_t)j * D + i]);
+        if (i == j) v += jit[attempt] * fabs(v);
+        Ls[i * LD + j] = v;
       }
-      __syncthreads();   // the next column's pivot is part of the trailing block
+      __syncthreads();
+      ok = true;
+      for (int j = 0; j < D; ++j) {
+        const double d = Ls[j * LD + j];
+        ok = ok && (d > 0.0) && (d < CUDART_INF);
+        const double ljj = sqrt(d);
+        __syncthreads();
+        if (tid == 0) Ls[j * LD + j] = ljj;
+        for (int i = j + 1 + tid; i < D; i += NT) Ls[i * LD + j] /= ljj;
+        __syncthreads();
+        // trailing update of the lower triangle: element (i, k), j < k <= i < D
+        const int m = D - j - 1;
+        for (int e = tid; e < m * m; e += NT) {
+          const int ii = e / m, kk = e - ii * m;
+          if (kk <= ii) {
+            const int i = j + 1 + ii, k = j + 1 + kk;
+            Ls[i * LD + k] -= Ls[i * LD + j] * Ls[k * LD + j];
+          }
+        }
+        __syncthreads();   // the next column's pivot is part of the trailing block
+      }
+      if (ok) break;   // (uniform over the CTA: every thread read the same pivots)
     }
   }
   niw_pack_body(a, t, Ls, ok);

@@ -45,9 +45,11 @@ struct ParamRng {
   }
   __device__ double normal() {
     const Philox4 r = next();
-    const double u1 = ((double)(r.x >> 5) * 67108864.0 + (double)(r.y >> 6) + 0.5) * (1.0 / 9007199254740992.0);
-    const double u2 = ((double)(r.z >> 5) * 67108864.0 + (double)(r.w >> 6) + 0.5) * (1.0 / 9007199254740992.0);
-    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    // Box-Muller in Float32 on 32-bit uniforms (|z| <= 6.7): the variates feed Float32 parameters anyway, and a
+    // CTA draws ~D^2/2 of them on its critical path
+    const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    return (double)(sqrtf(-2.0f * __logf(u1)) * cospif(2.0f * u2));
   }
   // Gamma(a, 1), Marsaglia & Tsang (2000); a < 1 through Gamma(a + 1) U^(1/a)
   __device__ double gamma(double a) {
@@ -138,14 +140,26 @@ __device__ inline void niw_posterior_to_smem(const double* hyper, int D, int LD,
   __syncthreads();
 }
 
-// log marginal likelihood (niw.jl:53-62) from the Cholesky factor in A; thread 0 returns it
-__device__ inline double niw_logml(const double* hyper, int D, int LD, const double* A, double N, double kp, double nup,
-                                   double& logdet) {
+// log marginal likelihood (niw.jl:53-62) from the Cholesky factor in A.  Called by EVERY thread of the CTA (the D
+// logarithms and the D log-gamma values are evaluated by D threads, not by one: they are the kernel's critical
+// path); thread 0 holds the result.  log_multivariate_gamma keeps the reference's Float32 accumulation order.
+__device__ inline double niw_logml_cta(const double* hyper, int D, int LD, const double* A, double N, double kp, double nup,
+                                       double* scratch, double& logdet) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  if (tid < D) scratch[tid] = log(A[tid * LD + tid]);
+  __syncthreads();
   logdet = 0.0;
-  for (int i = 0; i < D; ++i) logdet += 2.0 * log(A[i * LD + i]);
-  if (!(N > 0.0)) return 0.0;   // posterior == prior: every term cancels (and the reference never uses it)
+  if (tid == 0)
+    for (int i = 0; i < D; ++i) logdet += 2.0 * scratch[i];
+  __syncthreads();
+  if (tid < D) scratch[tid] = lgamma(nup / 2.0 + (1.0 - (tid + 1)) / 2.0);
+  __syncthreads();
+  if (tid != 0 || !(N > 0.0)) return 0.0;   // N = 0: posterior == prior, every term cancels
+  float lmv = (float)((double)D * (D - 1) / 4.0 * 1.1447298858494002);   // log(pi); utils.jl:66-72
+  for (int j = 0; j < D; ++j) lmv = (float)((double)lmv + scratch[j]);
   const double kappa = hyper[0], nu = hyper[1], logdet0 = hyper[2], lmv0 = hyper[3];
-  return -N * D * 0.5 * 1.1447298858494002 + niw_lmvgamma(nup / 2.0, D) - lmv0 + (nu / 2.0) * (D * log(nu) + logdet0) -
+  return -N * D * 0.5 * 1.1447298858494002 + (double)lmv - lmv0 + (nu / 2.0) * (D * log(nu) + logdet0) -
          (nup / 2.0) * (D * log(nup) + logdet) + (D / 2.0) * log(kappa / kp);
 }
 
@@ -173,9 +187,9 @@ __global__ void __launch_bounds__(256) niw_post_kernel(const NiwPostArgs a) {
   double* P = a.post + ((size_t)k * 3 + s) * NIW_POST_DOUBLES(D);
   for (int e = threadIdx.x; e < D * D; e += blockDim.x) P[8 + D + e] = A[(e / D) * LD + (e % D)];
   for (int i = threadIdx.x; i < D; i += blockDim.x) P[8 + i] = mp[i];
+  double logdet;
+  double lml = niw_logml_cta(a.hyper, D, LD, A, N, kp, nup, sxs, logdet);
   if (threadIdx.x == 0) {
-    double logdet;
-    double lml = niw_logml(a.hyper, D, LD, A, N, kp, nup, logdet);
     if (!ok) lml = __longlong_as_double(0x7ff8000000000000LL);
     P[0] = kp; P[1] = nup; P[2] = N; P[3] = lml; P[4] = logdet; P[5] = ok ? 1.0 : 0.0;
     a.out[((size_t)ai * 3 + s) * 2] = N;
@@ -213,11 +227,9 @@ __global__ void __launch_bounds__(256) niw_merge_kernel(const NiwMergeArgs a) {
   double N, kp, nup;
   niw_posterior_to_smem(a.hyper, D, LD, src, 2, false, A, mp, sxs, N, kp, nup);
   const bool ok = cta_cholesky(A, D, LD);
-  if (threadIdx.x == 0) {
-    double logdet;
-    const double lml = niw_logml(a.hyper, D, LD, A, N, kp, nup, logdet);
-    *o = ok ? lml : __longlong_as_double(0x7ff8000000000000LL);
-  }
+  double logdet;
+  const double lml = niw_logml_cta(a.hyper, D, LD, A, N, kp, nup, sxs, logdet);
+  if (threadIdx.x == 0) *o = ok ? lml : __longlong_as_double(0x7ff8000000000000LL);
 }
 
 struct NiwDrawArgs {
@@ -413,5 +425,66 @@ __global__ void ptab_merge_kernel(double* ptab, int rec, int i, int j) {
     pj[e] = 0.0;
     pj[rec + e] = 0.0;
     pj[2 * rec + e] = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// predict / predict_points (src/dp-parallel-sampling.jl:509-537, src/local_clusters_actions.jl:23-40) with the
+// NIW posterior predictive (multivariate Student-t, src/priors/niw.jl:68-76) on the device:
+//   parr[i, k] = C_k - (df_k + D)/2 * log1p(q_ik / df_k) + log w_k,   q = |U_k (x_i - m_k)|^2,
+// U_k the upper factor of the inverse scale matrix (((kappa+1)/(kappa df)) nu psi)^-1, prepared by the host from
+// the K posterior hyper-parameters (K D^3 work); labels = first argmax over k; optional probabilities
+// (NaN -> -Inf, softmax over k) as the reference returns them.  One warp per point, lanes <-> clusters.
+// ------------------------------------------------------------------------------------------------
+struct NiwPredictArgs {
+  const float* x;       // [n][D]
+  int64_t n;
+  int D, K;
+  const float* u;       // [K][D][D] rows of U_k (zero below the diagonal)
+  const float* mu;      // [K][D]
+  const float* tconst;  // [K]  C_k + log w_k
+  const float* df;      // [K]
+  int32_t* labels;      // [n] out, 0-based
+  float* probs;         // [n][K] out (point-major) or nullptr
+};
+
+__global__ void __launch_bounds__(256) niw_predict_kernel(const NiwPredictArgs a) {
+  extern __shared__ float pr_sm[];   // per warp: x[D] | r[K]
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, D = a.D, K = a.K;
+  float* xs = pr_sm + (size_t)wl * (D + K);
+  float* rs = xs + D;
+  for (int64_t i = (int64_t)blockIdx.x * 8 + wl; i < a.n; i += (int64_t)gridDim.x * 8) {
+    for (int j = lane; j < D; j += 32) xs[j] = a.x[(size_t)i * D + j];
+    __syncwarp();
+    for (int k = lane; k < K; k += 32) {
+      const float* U = a.u + (size_t)k * D * D;
+      const float* m = a.mu + (size_t)k * D;
+      float q = 0.f;
+      for (int r = 0; r < D; ++r) {
+        float y = 0.f;
+        for (int j = r; j < D; ++j) y = fmaf(__ldg(U + r * D + j), xs[j] - __ldg(m + j), y);
+        q = fmaf(y, y, q);
+      }
+      const float df = __ldg(a.df + k);
+      rs[k] = __ldg(a.tconst + k) - 0.5f * (df + (float)D) * log1pf(q / df);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      a.labels[i] = dpmm_draw_argmax(rs, 1, K);
+      if (a.probs != nullptr) {
+        float mx = -CUDART_INF_F;
+        for (int k = 0; k < K; ++k) {
+          if (rs[k] != rs[k]) rs[k] = -CUDART_INF_F;
+          mx = fmaxf(mx, rs[k]);
+        }
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) {
+          rs[k] = expf(rs[k] - mx);
+          s += rs[k];
+        }
+        for (int k = 0; k < K; ++k) a.probs[(size_t)i * K + k] = rs[k] / s;
+      }
+    }
+    __syncwarp();
   }
 }

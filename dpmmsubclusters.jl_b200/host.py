@@ -486,15 +486,39 @@ def fit(all_data, *args, iters=100, init_clusters=1, seed=None, verbose=False, s
             g.weights, iter_count, nmi, ll, kh, g.sweep.get_sublabels(), dp_model)
 
 
-def predict(dp_model, data):
-    """predict / predict_points :23-40, :532-537 (host-only; posterior predictive, hard labels + probs)."""
+def predict(dp_model, data, device=0, on_device=None):
+    """predict / predict_points :23-40, :532-537: posterior-predictive hard labels + probabilities.
+    NIW models run on the GPU (dpmm_predict_niw: Student-t densities, argmax and softmax per point; the host
+    prepares the K factors); on_device=False, or a multinomial model, takes the NumPy formulas below."""
     data = np.asarray(data, F32)
     cl = dp_model.group.local_clusters
+    posts = [c.cluster_params.cluster_params.posterior_hyperparams for c in cl]
+    w = np.asarray(dp_model.group.weights, F32)
+    if on_device is None:
+        on_device = os.environ.get("DPMM_DEVICE_PREDICT", "1") != "0"
+    if on_device and posts and isinstance(posts[0], P.niw_hyperparams) and isinstance(dp_model.group.sweep, GpuSweep):
+        D, K = data.shape[0], len(posts)
+        u = np.zeros((K, D, D)); mu = np.zeros((K, D)); tc = np.zeros(K); dfs = np.zeros(K)
+        with np.errstate(divide="ignore"):
+            lw = np.log(w.astype(np.float64))
+        for k, p in enumerate(posts):                    # niw.jl:68-76
+            df = p.ν - D + 1
+            Sig = ((p.κ + 1) / (p.κ * df)) * p.ν * p.ψ
+            u[k] = np.linalg.cholesky(np.linalg.inv(Sig)).T          # Sig^-1 = U'U
+            mu[k] = p.m
+            dfs[k] = df
+            tc[k] = (gammaln((df + D) / 2) - gammaln(df / 2) - 0.5 * D * np.log(df * np.pi)
+                     - 0.5 * np.linalg.slogdet(Sig)[1] + lw[k])
+        g = GpuSweep(data, NIW, device=device)
+        try:
+            return g.predict_niw(u, mu, tc, dfs)
+        finally:
+            g.close()
     parr = np.zeros((data.shape[1], len(cl)), F32)
     for k, c in enumerate(cl):
         parr[:, k] = P.posterior_predictive(data, c.cluster_params.cluster_params.posterior_hyperparams)
     with np.errstate(divide="ignore"):
-        parr += np.log(np.asarray(dp_model.group.weights, F32))[None, :]
+        parr += np.log(w)[None, :]
     lbls = np.argmax(parr, axis=1) + 1
     parr = np.where(np.isnan(parr), -np.inf, parr)
     parr = np.exp(parr - parr.max(axis=1, keepdims=True))

@@ -211,6 +211,18 @@ class GpuSweep:
                                               _ptr(w, C.c_float), _ptr(lr, C.c_float)))
         return mu, lf, ld, w, lr
 
+    def predict_niw(self, u, mu, tconst, df, want_probs=True):
+        """Posterior-predictive labels (and probabilities) of this context's points; see dpmm_predict_niw."""
+        u = np.ascontiguousarray(u, np.float32); mu = np.ascontiguousarray(mu, np.float32)
+        tconst = np.ascontiguousarray(tconst, np.float32); df = np.ascontiguousarray(df, np.float32)
+        K = u.shape[0]
+        assert u.shape == (K, self.D, self.D) and mu.shape == (K, self.D) and tconst.shape == (K,) and df.shape == (K,)
+        labels = np.empty(self.n, np.int64)
+        probs = np.empty((self.n, K), np.float32) if want_probs else None
+        self._ck(self.lib.dpmm_predict_niw(self.h, K, _ptr(u, C.c_float), _ptr(mu, C.c_float), _ptr(tconst, C.c_float),
+                                           _ptr(df, C.c_float), _ptr(labels, C.c_int64), _ptr(probs, C.c_float)))
+        return labels, probs
+
     # ---- relabel ----
     def apply_split(self, indices, new_indices):
         a, b = _i64(indices), _i64(new_indices)

@@ -159,6 +159,15 @@ int dpmm_params_merge(dpmm_ctx* ctx, int64_t i, int64_t j);
 int dpmm_get_params_niw(dpmm_ctx* ctx, int32_t k, float* mu, double* lfac, float* logdet, float* weights,
                         float* lr_weights);
 
+/* predict / predict_points (src/dp-parallel-sampling.jl:509-537, src/local_clusters_actions.jl:23-40) for the
+ * points of THIS context under K NIW posterior predictives (multivariate Student-t, niw.jl:68-76):
+ *   parr[i,k] = tconst[k] - (df[k] + D)/2 * log1p(|U_k (x_i - mu_k)|^2 / df[k])
+ * u float32 [K][D][D] = rows of the upper factor of the inverse scale matrix, tconst = the density's constant
+ * plus log weight (the host prepares both from the K posterior hyper-parameters).  labels: int64 [n] (1-based
+ * first argmax); probs: float32 [n][K] softmax over k, or NULL. */
+int dpmm_predict_niw(dpmm_ctx* ctx, int32_t k, const float* u, const float* mu, const float* tconst,
+                     const float* df, int64_t* labels, float* probs);
+
 /* ---- relabelling after split / merge / compaction ------------------------------------------- */
 
 /* split_cluster_local_worker! (local_clusters_actions.jl:265-278). */

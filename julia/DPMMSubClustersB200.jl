@@ -127,6 +127,77 @@ apply_merge!(c::Ctx, idx::Vector{Int64}, new_idx::Vector{Int64}) = check(ccall((
 remove_empty!(c::Ctx, pts_count::Vector{Int64}) = check(ccall((:dpmm_remove_empty, lib), Cint,
     (Ptr{Cvoid}, Ptr{Int64}, Int32), c.ptr, pts_count, length(pts_count)), c.ptr)
 
+# ---- device-side parameter step (NIW; include/dpmm_b200.h "device-side parameter step") ------------------
+# With these the master keeps only the Hastings decisions: posterior hyper-parameters, log marginal
+# likelihoods, the 3K posterior draws and the Dirichlet weights are produced next to the statistics.
+
+"""
+    set_hyper!(c, h::niw_hyperparams, α)   (niw.jl:6-11, ds.jl:9)
+"""
+function set_hyper!(c::Ctx, κ::Real, m::Vector{Float64}, ν::Real, ψ::Matrix{Float64}, α::Real)
+    GC.@preserve m ψ check(ccall((:dpmm_set_hyper_niw, lib), Cint,
+        (Ptr{Cvoid}, Cdouble, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Cdouble), c.ptr, κ, m, ν, ψ, α), c.ptr)
+end
+
+"""
+    posterior_step(c, indices; splittable=nothing, from_table=false) -> (counts[3,m], logml[3,m], merge[K,K] or nothing)
+
+update_suff_stats_posterior! (local_clusters_actions.jl:206-254) kept on the device.  `indices === nothing`
+means every cluster.  `merge[j, i]` (column-major view of the C row-major table) holds the log marginal
+likelihood of clusters i < j merged (should_merge!, shared_actions.jl:21-38).
+"""
+function posterior_step(c::Ctx, indices::Union{Nothing,Vector{Int64}}; splittable::Union{Nothing,Vector{UInt8}} = nothing,
+                        from_table::Bool = false)
+    m = indices === nothing ? Int(ccall((:dpmm_num_clusters, lib), Cint, (Ptr{Cvoid},), c.ptr)) : length(indices)
+    counts = Array{Int64}(undef, 3, m); logml = Array{Float64}(undef, 3, m)
+    km = splittable === nothing ? 0 : length(splittable)
+    merge = km > 1 ? Array{Float64}(undef, km, km) : nothing
+    GC.@preserve indices splittable counts logml merge check(ccall((:dpmm_posterior_step, lib), Cint,
+        (Ptr{Cvoid}, Ptr{Int64}, Int32, Int32, Ptr{UInt8}, Int32, Ptr{Int64}, Ptr{Cdouble}, Ptr{Cdouble}),
+        c.ptr, indices === nothing ? C_NULL : pointer(indices), m, from_table,
+        km > 1 ? pointer(splittable) : C_NULL, km > 1 ? km : 0, counts, logml,
+        merge === nothing ? C_NULL : pointer(merge)), c.ptr)
+    counts, logml, merge
+end
+
+"sample_clusters! + broadcast_cluster_params on the device (local_clusters_actions.jl:417-437, 518-549)."
+sample_params!(c::Ctx, K::Integer; from_prior::Bool = false, unit_weights::Bool = false) =
+    check(ccall((:dpmm_sample_params, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Int32), c.ptr, K, from_prior, unit_weights), c.ptr)
+"merge_clusters_to_splittable on the statistics table (shared_actions.jl:12-18); i, j 1-based."
+params_merge!(c::Ctx, i::Integer, j::Integer) =
+    check(ccall((:dpmm_params_merge, lib), Cint, (Ptr{Cvoid}, Int64, Int64), c.ptr, i, j), c.ptr)
+
+"(mu[D,3,K], L[D,D,3,K] with invΣ = L*L' (stored row-major: read it transposed), logdetΣ[3,K], weights[K], lr[2,K])"
+function get_params(c::Ctx, K::Integer)
+    D = c.d
+    mu = Array{Float32}(undef, D, 3, K); lf = Array{Float64}(undef, D, D, 3, K); ld = Array{Float32}(undef, 3, K)
+    w = Vector{Float32}(undef, K); lr = Array{Float32}(undef, 2, K)
+    GC.@preserve mu lf ld w lr check(ccall((:dpmm_get_params_niw, lib), Cint,
+        (Ptr{Cvoid}, Int32, Ptr{Cfloat}, Ptr{Cdouble}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}), c.ptr, K, mu, lf, ld, w, lr), c.ptr)
+    mu, lf, ld, w, lr
+end
+
+# ---- host-type shim ------------------------------------------------------------------------------------
+# local_group.points / labels / labels_subcluster are typed AbstractArray (ds.jl:53-55).  These wrappers over the
+# context implement what fit / run_model / save_model / calculate_posterior touch -- size and Array(...) --
+# so those functions run unmodified (size(points, 2) at dp-parallel-sampling.jl:459; Array(group.labels) at
+# :218, :276, :371 and ds.jl:85-87).
+struct DevicePoints <: AbstractArray{Float32,2}
+    c::Ctx
+end
+Base.size(p::DevicePoints) = (p.c.d, p.c.n)
+Base.getindex(::DevicePoints, ::Int...) = error("the points live on the GPU; they are not read back element-wise")
+
+struct DeviceLabels <: AbstractArray{Int64,1}
+    c::Ctx
+    sub::Bool
+end
+Base.size(l::DeviceLabels) = (l.c.n,)
+Base.Array(l::DeviceLabels) = l.sub ? sublabels(l.c) : labels(l.c)
+Base.collect(l::DeviceLabels) = Array(l)
+Base.getindex(l::DeviceLabels, i::Int) = Array(l)[i]   # (debugging only: one device->host copy per call)
+# e.g.  local_group(model_hyperparams, DevicePoints(ctx), DeviceLabels(ctx, false), DeviceLabels(ctx, true), [], Float32[])
+
 # multi-GPU: one Julia process per GPU; rank 0 creates the id and ships it (e.g. over Distributed)
 function nccl_unique_id()
     id = Vector{UInt8}(undef, 128)

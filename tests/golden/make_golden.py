@@ -80,9 +80,27 @@ def make_niw():
                     off, val = _find_f64(blob, S[i, j])
                     sum_xx[k, s, i, j] = val
                     offsets.append(off)
+    # The checkpoint also stores every cluster's POSTERIOR hyper-parameters (cluster_parameters.posterior_hyperparams,
+    # ds.jl:13-18) next to the statistics: m' and psi' of calc_posterior (niw.jl:20-31) under the example's prior
+    # niw_hyperparams(1.0, [0,0], 5.0, I) (examples/save_load_model/params_2d.jl).  Located by value like the
+    # statistics; the STORED bytes are the golden answer for calc_posterior.
+    post_m = np.zeros((K, 3, D))
+    post_psi = np.zeros((K, 3, D, D))
+    kappa0, nu0 = 1.0, 5.0
+    for k in range(K):
+        for s in range(3):
+            N = float(counts[k, s])
+            kp, nup = kappa0 + N, nu0 + N
+            m = sum_x[k, s] / kp
+            psi = (nu0 * np.eye(D) - kp * np.outer(m, m) + sum_xx[k, s]) / nup
+            for d in range(D):
+                post_m[k, s, d] = _find_f64(blob, m[d], rtol=1e-11)[1]
+            for i in range(D):
+                for j in range(D):
+                    post_psi[k, s, i, j] = _find_f64(blob, psi[i, j], rtol=1e-11)[1]
     np.savez_compressed(f"{OUT}/niw_2d1k_checkpoint50.npz", x=pts, labels=labels, sublabels=sub,
-                        counts=counts, sum_x=sum_x, sum_xx=sum_xx,
-                        found_offsets=np.asarray(offsets, np.int64))
+                        counts=counts, sum_x=sum_x, sum_xx=sum_xx, post_m=post_m, post_psi=post_psi,
+                        prior=np.array([kappa0, nu0]), found_offsets=np.asarray(offsets, np.int64))
     print("niw: counts\n", counts)
 
 
@@ -106,8 +124,19 @@ def make_mnm():
             off = _find_f32_vector(blob, sx)
             offsets.append(off)
             sum_x[k, s] = np.frombuffer(blob, dtype="<f4", count=D, offset=off)
+    # posterior alpha' = alpha + sum x (multinomial_prior.jl:16-21) under multinomial_hyper(ones(Float32,100))
+    # (test/save_load_test/multinomial_params.jl): stored as Float32 vectors, found byte-exact
+    post_alpha = np.zeros((K, 3, D), np.float32)
+    for k in range(K):
+        for s in range(3):
+            off = _find_f32_vector(blob, np.ones(D, np.float32) + sum_x[k, s])
+            post_alpha[k, s] = np.frombuffer(blob, dtype="<f4", count=D, offset=off)
+    # generate_mnmm_data invariants of the reference's own data file (data_generators.jl:59-72): integral counts,
+    # every point is `trials` draws
+    assert np.array_equal(m, np.round(m)) and m.min() >= 0
     np.savez_compressed(f"{OUT}/mnm_1k_checkpoint20.npz", x=pts, labels=labels, sublabels=sub,
-                        counts=counts, sum_x=sum_x, found_offsets=np.asarray(offsets, np.int64))
+                        counts=counts, sum_x=sum_x, post_alpha=post_alpha, row_sums=m.sum(axis=1).astype(np.float32),
+                        found_offsets=np.asarray(offsets, np.int64))
     print("mnm: counts\n", counts, "\noffsets", offsets)
 
 

@@ -68,6 +68,29 @@ def test_posterior_logml_and_merge_table_match_the_prior_plugin(pkg, D, K, n):
     g.close()
 
 
+def test_device_posterior_on_the_reference_checkpoint(pkg, golden_dir):
+    """The device posterior step on the labels / sub-labels of the reference's checkpoint__50.jld2: the log marginal
+    likelihoods must equal those of the posteriors the reference itself stored in that file (post_m / post_psi,
+    tests/golden/make_golden.py), evaluated with niw.jl:53-62."""
+    import os
+    from dpmmsubclusters_jl_b200 import priors as P
+    gd = np.load(os.path.join(golden_dir, "niw_2d1k_checkpoint50.npz"))
+    hyper = P.niw_hyperparams(gd["prior"][0], np.zeros(2), gd["prior"][1], np.eye(2))
+    g = pkg.GpuSweep(gd["x"].astype(np.float32), pkg.NIW)
+    g.set_labels(gd["labels"]); g.set_sublabels(gd["sublabels"])
+    g.set_hyper_niw(hyper.κ, hyper.m, hyper.ν, hyper.ψ, 100000.0)
+    counts, logml, _ = g.posterior_step(None)
+    np.testing.assert_array_equal(counts, gd["counts"])
+    for k in range(5):
+        for s in range(3):
+            N = float(gd["counts"][k, s])
+            stored = P.niw_hyperparams(1.0 + N, gd["post_m"][k, s], 5.0 + N, gd["post_psi"][k, s])
+            ss = P.make_suff_stats(hyper, N, gd["sum_x"][k, s], gd["sum_xx"][k, s])
+            want = P.log_marginal_likelihood(hyper, stored, ss)
+            assert abs(logml[k, s] - want) <= 2e-6 * abs(want) + 1e-4, (k, s, logml[k, s], want)
+    g.close()
+
+
 @pytest.mark.parametrize("D", [3, 32])
 def test_device_draws_have_the_right_moments_and_feed_the_sweep(pkg, D):
     """Sigma ~ IW(nu', nu' psi')  =>  E[invSigma] = psi'^-1;  mu | Sigma ~ N(m', Sigma / kappa');
@@ -128,3 +151,25 @@ def test_fit_device_and_host_parameter_paths_agree_over_seeds(pkg):
         print(f"N={N} D={D}: device NMI {np.round(res[True][0], 3)} K {res[True][1]}; host NMI {np.round(res[False][0], 3)} K {res[False][1]}")
         assert abs(res[True][0].mean() - res[False][0].mean()) < 0.05
         assert abs(res[True][1].mean() - res[False][1].mean()) <= 1.5
+
+
+def test_predict_on_device_matches_the_numpy_posterior_predictive(pkg):
+    """predict() runs the Student-t posterior predictive on the GPU (dpmm_predict_niw); labels and
+    probabilities against the NumPy formulas of priors.posterior_predictive (niw.jl:68-76) on new points."""
+    from dpmmsubclusters_jl_b200 import host as H
+    for D, K, N in [(2, 6, 20000), (32, 8, 30000)]:
+        x, labels, _, _ = pkg.generate_gaussian_data(N, D, K, 100.0, np.random.default_rng(3))
+        out = H.fit(x, 10.0, iters=40, seed=2, burnout=5)
+        model = out[-1]
+        xnew, _, _, _ = pkg.generate_gaussian_data(5000, D, K, 100.0, np.random.default_rng(4))
+        xnew = np.concatenate([xnew, x[:, :3000]], axis=1)
+        lg, pg = H.predict(model, xnew, on_device=True)
+        lh, ph = H.predict(model, xnew, on_device=False)
+        agree = (lg == lh).mean()
+        assert agree > 0.999, agree
+        np.testing.assert_allclose(pg, ph, atol=2e-3)
+        np.testing.assert_allclose(pg.sum(1), 1.0, atol=1e-5)
+        # on the training points the posterior-predictive argmax mostly agrees with the sampled labels
+        lt, _ = H.predict(model, x, on_device=True)
+        print(f"D={D}: device vs NumPy predict agree on {agree:.5f}; predict == fit labels on {(lt == out[0]).mean():.4f}")
+        assert (lt == out[0]).mean() > 0.95

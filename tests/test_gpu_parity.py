@@ -343,6 +343,30 @@ def test_edge_cases(pkg):
     g.close()
 
 
+def test_ill_conditioned_inverse_covariance_stays_finite_and_matches_the_oracle(pkg):
+    """a Float32-rounded invSigma of a nearly collinear cluster (condition number ~1e8) is not exactly
+    positive definite any more; the reference's direct z' invSigma z (which the oracle follows) stays finite, and
+    so must the factored form (tiny diagonal jitter in niw_pack_kernel), within the 1e-4 tolerance."""
+    rng = np.random.default_rng(8)
+    D, K, n = 8, 3, 4000
+    case = make_niw_case(D, K, n, seed=9)
+    v = rng.standard_normal(D); v /= np.linalg.norm(v)
+    for k in range(K):
+        Sig = np.linalg.inv(case["inv_sigma"][k, 0].astype(np.float64))
+        Sig = Sig + 3e7 * np.outer(v, v)                 # one very long axis: cond(Sigma) ~ 1e8
+        case["inv_sigma"][k, 0] = np.linalg.inv(Sig)     # Float64 inverse rounded to Float32
+        case["logdet"][k, 0] = np.linalg.slogdet(Sig)[1]
+    g = pkg.GpuSweep(case["x"], pkg.NIW); o = O.OracleSweep(case["x"], O.NIW)
+    for s_ in (g, o):
+        set_params(s_, case)
+    got, want = g.debug_loglik(0), o.debug_loglik(0)
+    assert np.isfinite(got).all() and np.isfinite(want).all()
+    # the quadratic form itself is ill conditioned in Float32 on both sides: compare on the scale of the row
+    err = np.abs(got.astype(np.float64) - want) / np.maximum(np.abs(want), 1.0)
+    assert err.max() <= 2e-3, err.max()
+    g.close()
+
+
 def test_error_behaviour(pkg):
     E = pkg._lib
     x = np.zeros((2, 16), np.float32)

@@ -50,6 +50,30 @@ def test_niw_posterior_and_marginal_closed_forms():
     assert abs(lhs - rhs) < 1e-3 * max(1, abs(lhs))      # log_multivariate_gamma accumulates in Float32 (utils.jl:66-72)
 
 
+def test_calc_posterior_matches_the_posteriors_stored_in_the_reference_checkpoints(golden_dir):
+    """The reference's own checkpoints hold every cluster's posterior hyper-parameters next to its statistics
+    (tests/golden/make_golden.py): m' and psi' of niw.jl:20-31 for checkpoint__50.jld2, alpha' of
+    multinomial_prior.jl:16-21 for checkpoint_20.jld2.  calc_posterior must reproduce the stored bytes."""
+    import os
+    gd = np.load(os.path.join(golden_dir, "niw_2d1k_checkpoint50.npz"))
+    hyper = P.niw_hyperparams(gd["prior"][0], np.zeros(2), gd["prior"][1], np.eye(2))
+    for k in range(5):
+        for s in range(3):
+            ss = P.make_suff_stats(hyper, gd["counts"][k, s], gd["sum_x"][k, s], gd["sum_xx"][k, s])
+            post = P.calc_posterior(hyper, ss)
+            np.testing.assert_allclose(post.m, gd["post_m"][k, s], rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(post.ψ, gd["post_psi"][k, s], rtol=1e-11, atol=1e-13)
+            assert post.κ == 1.0 + gd["counts"][k, s] and post.ν == 5.0 + gd["counts"][k, s]
+    gm = np.load(os.path.join(golden_dir, "mnm_1k_checkpoint20.npz"))
+    mh = P.multinomial_hyper(np.ones(100, np.float32))
+    for k in range(2):
+        for s in range(3):
+            ss = P.make_suff_stats(mh, gm["counts"][k, s], gm["sum_x"][k, s])
+            assert P.calc_posterior(mh, ss).α.astype(np.float32).tobytes() == gm["post_alpha"][k, s].tobytes()
+    # generate_mnmm_data(N, D, K, trials) invariants of the reference's own data file: every point is 50 draws
+    assert (gm["row_sums"] == 50).all() and np.array_equal(gm["x"], np.round(gm["x"])) and gm["x"].min() >= 0
+
+
 def test_sample_distribution_moments():
     rng = np.random.default_rng(1)
     D = 3
