@@ -57,7 +57,8 @@ struct dpmm_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   int64_t n = 0;
-  int D = 0;
+  int D = 0;        // feature dimension the kernels run at (D_user zero-padded to an instantiated width)
+  int D_user = 0;   // feature dimension at the boundary
   int prior = 0;
   uint64_t seed = 0;
   int64_t goff = 0;
@@ -70,6 +71,8 @@ struct dpmm_ctx {
   uint8_t* sub = nullptr;
   int32_t* perm = nullptr;
   int32_t* perm2 = nullptr;
+  int64_t* wide = nullptr;         // [n] scratch of the boundary conversions (1-based Int64 <-> device types)
+  int32_t* wide_status = nullptr;
   double* u_label = nullptr;
   double* u_sub = nullptr;
   uint8_t* r_bits = nullptr;
@@ -100,6 +103,13 @@ struct dpmm_ctx {
   bool t2_ok = false;       // shape supported
   bool t2_params = false;   // t2_* describe the current parameters
   int t2_KS = 0, t2_nch = 0;
+  // adaptive path choice: counters of the last tensor-core label call (points, exact evaluations, overflow points)
+  // land in pinned memory behind an event; a call that finds more exact work than the FMA kernel would do for all K
+  // clusters sends the next calls to the FMA kernel for a while (early iterations, heavily overlapping clusters)
+  int32_t* t2_hstat = nullptr;       // pinned [4]
+  cudaEvent_t t2_hstat_ev = nullptr;
+  bool t2_hstat_pending = false;
+  int t2_cooldown = 0;
   // fused sub-label + statistics tensor-core path (NIW, D == 32): U rows / bias / centre per cluster, left counts
   float* ss_w = nullptr;
   float* ss_b = nullptr;

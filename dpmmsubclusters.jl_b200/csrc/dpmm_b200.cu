@@ -204,10 +204,14 @@ extern "C" int dpmm_create(dpmm_ctx** out, const float* x, int64_t n_local, int3
   NEED(x != nullptr && n_local > 0 && d > 0, DPMM_EINVAL, "x must be non-NULL with n_local > 0 and d > 0");
   NEED(n_local < ((int64_t)1 << 31) - 4096, DPMM_ELIMIT, "n_local must fit in int32 (shard the points over more GPUs)");
   NEED(prior_kind == DPMM_PRIOR_NIW || prior_kind == DPMM_PRIOR_MULTINOMIAL, DPMM_EINVAL, "unknown prior kind");
-  if (prior_kind == DPMM_PRIOR_NIW)
-    NEED(niw_dim_supported(d), DPMM_ELIMIT,
-         "NIW: D must be one of 1-8, 12, 16, 24, 32, 48, 64 (zero-pad the features otherwise)");
-  else
+  int dpad = d;
+  if (prior_kind == DPMM_PRIOR_NIW) {
+    // kernels are instantiated for D in {1-8, 12, 16, 24, 32, 48, 64}; any other D <= 64 runs zero-padded to the
+    // next width (padded features are 0 with mean 0 and unit precision: no likelihood or statistic changes, and the
+    // D^2 constant keeps the caller's D)
+    NEED(d <= 64, DPMM_ELIMIT, "NIW: D must be <= 64");
+    while (!niw_dim_supported(dpad)) ++dpad;
+  } else
     NEED(d <= 1024, DPMM_ELIMIT, "multinomial: D must be <= 1024");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -216,7 +220,8 @@ extern "C" int dpmm_create(dpmm_ctx** out, const float* x, int64_t n_local, int3
   ctx = new dpmm_ctx();
   ctx->device = device;
   ctx->n = n_local;
-  ctx->D = d;
+  ctx->D = dpad;
+  ctx->D_user = d;
   ctx->prior = prior_kind;
   ctx->seed = seed;
   ctx->goff = global_offset;
@@ -244,17 +249,30 @@ extern "C" int dpmm_create(dpmm_ctx** out, const float* x, int64_t n_local, int3
   ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
   ctx->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
   CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  CKC(cudaMalloc((void**)&ctx->x, (size_t)n_local * d * sizeof(float)));
+  CKC(cudaMalloc((void**)&ctx->x, (size_t)n_local * dpad * sizeof(float)));
   CKC(cudaMalloc((void**)&ctx->labels, (size_t)n_local * sizeof(int32_t)));
   CKC(cudaMalloc((void**)&ctx->sub, (size_t)n_local));
   CKC(cudaMalloc((void**)&ctx->perm, (size_t)n_local * sizeof(int32_t)));
   CKC(cudaMalloc((void**)&ctx->perm2, (size_t)n_local * sizeof(int32_t)));
   CKC(cudaMalloc((void**)&ctx->item_ctr, 2 * sizeof(int32_t)));
-  CKC(cudaMemcpyAsync(ctx->x, x, (size_t)n_local * d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  if (dpad == d) {
+    CKC(cudaMemcpyAsync(ctx->x, x, (size_t)n_local * d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    float* raw = nullptr;
+    CKC(cudaMalloc((void**)&raw, (size_t)n_local * d * sizeof(float)));
+    cudaError_t e1 = cudaMemcpyAsync(raw, x, (size_t)n_local * d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e1 == cudaSuccess) {
+      pad_points_kernel<<<(unsigned)prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(raw, n_local, d, dpad, ctx->x);
+      e1 = cudaGetLastError();
+    }
+    if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(raw);
+    CKC(e1);
+  }
   CKC(cudaMemsetAsync(ctx->labels, 0, (size_t)n_local * sizeof(int32_t), ctx->stream));
   CKC(cudaMemsetAsync(ctx->sub, 0, (size_t)n_local, ctx->stream));
   CKC(cudaStreamSynchronize(ctx->stream));
-  if (prior_kind == DPMM_PRIOR_NIW && d == TC_D && n_local >= TC_TILE) {
+  if (prior_kind == DPMM_PRIOR_NIW && dpad == TC_D && n_local >= TC_TILE) {
     // TMA descriptor of X as a [n][32] float tensor, 128-point boxes, 128B swizzle (K2 operand A)
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -274,18 +292,25 @@ extern "C" int dpmm_create(dpmm_ctx** out, const float* x, int64_t n_local, int3
     }
     if (ctx->tc_ok) CKC(cudaMalloc((void**)&ctx->tc_stats, 2 * sizeof(int32_t)));
   }
-  if (prior_kind == DPMM_PRIOR_NIW && (d == 32 || d == 64) && n_local >= T2_TILE) {
+  if (prior_kind == DPMM_PRIOR_NIW && (dpad == 32 || dpad == 64) && n_local >= T2_TILE) {
     ctx->t2_ok = true;
     CKC(cudaMalloc((void**)&ctx->t2_ctr, 2 * sizeof(int32_t)));
     if (ctx->tc_stats == nullptr) CKC(cudaMalloc((void**)&ctx->tc_stats, 2 * sizeof(int32_t)));
   }
   if (prior_kind == DPMM_PRIOR_MULTINOMIAL && d % 4 == 0 && d <= MTC_MAX_D && n_local >= MTC_TILE) {
     // the tensor-core likelihood is exact only for TF32-exact counts: integral, |x| < 2^11
-    bool exact = true;
-    const size_t tot = (size_t)n_local * d;
-    for (size_t e = 0; e < tot && exact; ++e) {
-      const float v = x[e];
-      exact = (v == (float)(int)v) && v > -2048.f && v < 2048.f;
+    bool exact = false;
+    {   // (on the device: the points are there already)
+      int32_t* flag = nullptr;
+      int32_t hflag = 1;
+      if (cudaMalloc((void**)&flag, 4) == cudaSuccess) {
+        cudaMemsetAsync(flag, 0, 4, ctx->stream);
+        tf32_exact_scan_kernel<<<(unsigned)ctx->sm_count * 16, 256, 0, ctx->stream>>>(ctx->x, (int64_t)n_local * d, flag);
+        if (cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+            cudaStreamSynchronize(ctx->stream) == cudaSuccess)
+          exact = hflag == 0;
+        cudaFree(flag);
+      }
     }
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -333,10 +358,12 @@ extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
                   ctx->scat_cursor, ctx->lr_cursor, ctx->lut_l, ctx->lut_r, ctx->rule, ctx->wanted,
                   ctx->idx_list, ctx->acc, ctx->centers, ctx->outbuf, ctx->items, ctx->item_ctr, ctx->hyper_d, ctx->ptab,
                   ctx->ptab_alt, ctx->post, ctx->post_alt, ctx->lfac, ctx->pm_out, ctx->splittable_d, ctx->newof_d,
-                  ctx->w_out, ctx->lr_out};
+                  ctx->w_out, ctx->lr_out, ctx->wide, ctx->wide_status};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (ctx->hstage) cudaFreeHost(ctx->hstage);
+  if (ctx->t2_hstat) cudaFreeHost(ctx->t2_hstat);
+  if (ctx->t2_hstat_ev) cudaEventDestroy(ctx->t2_hstat_ev);
   for (int i = 0; i < 2; ++i) {
     if (ctx->hup[i]) cudaFreeHost(ctx->hup[i]);
     if (ctx->hup_ev[i]) cudaEventDestroy(ctx->hup_ev[i]);
@@ -559,49 +586,77 @@ extern "C" int dpmm_remove_empty(dpmm_ctx* ctx, const int64_t* pts_count, int32_
 // ------------------------------------------------------------------------------------------------
 // label gather / restore
 // ------------------------------------------------------------------------------------------------
+// scratch of n int64 on the device for the boundary conversions (allocated on first use)
+static int ensure_wide(dpmm_ctx* ctx) {
+  if (ctx->wide == nullptr) {
+    CK(cudaMalloc((void**)&ctx->wide, (size_t)ctx->n * 8));
+    CK(cudaMalloc((void**)&ctx->wide_status, 2 * sizeof(int32_t)));
+  }
+  return 0;
+}
+static unsigned stream_grid(const dpmm_ctx* ctx, int64_t n) {
+  return (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+}
+
 extern "C" int dpmm_get_labels(dpmm_ctx* ctx, int64_t* out) {
   NEED(ctx && out, DPMM_EINVAL, "NULL argument");
   CK(cudaSetDevice(ctx->device));
-  int rc = ensure_stage(ctx, (size_t)ctx->n * 4);
+  int rc = ensure_wide(ctx);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(ctx->hstage, ctx->labels, (size_t)ctx->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  widen_labels_kernel<int32_t><<<stream_grid(ctx, ctx->n), 256, 0, ctx->stream>>>(ctx->labels, ctx->n, ctx->wide);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, ctx->wide, (size_t)ctx->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  const int32_t* h = (const int32_t*)ctx->hstage;
-  for (int64_t i = 0; i < ctx->n; ++i) out[i] = (int64_t)h[i] + 1;
   return 0;
 }
 
 extern "C" int dpmm_get_sublabels(dpmm_ctx* ctx, int64_t* out) {
   NEED(ctx && out, DPMM_EINVAL, "NULL argument");
   CK(cudaSetDevice(ctx->device));
-  int rc = ensure_stage(ctx, (size_t)ctx->n);
+  int rc = ensure_wide(ctx);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(ctx->hstage, ctx->sub, (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  widen_labels_kernel<uint8_t><<<stream_grid(ctx, ctx->n), 256, 0, ctx->stream>>>(ctx->sub, ctx->n, ctx->wide);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, ctx->wide, (size_t)ctx->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  const uint8_t* h = (const uint8_t*)ctx->hstage;
-  for (int64_t i = 0; i < ctx->n; ++i) out[i] = (int64_t)h[i] + 1;
+  return 0;
+}
+
+// upload `src` (n int64), narrow into dst on the device; returns the largest label in *mx; EINVAL on a bad value.
+// The current labels are replaced only when every value is valid (narrowing goes through a scratch copy).
+template <typename T>
+static int set_labels_common(dpmm_ctx* ctx, const int64_t* src, int64_t hi, T* dst, int* mx, const char* what) {
+  int rc = ensure_wide(ctx);
+  if (rc) return rc;
+  T* tmp = nullptr;
+  CK(cudaMalloc((void**)&tmp, (size_t)ctx->n * sizeof(T)));
+  cudaError_t e = cudaMemsetAsync(ctx->wide_status, 0, 8, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->wide, src, (size_t)ctx->n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  int32_t st[2] = {0, 1};
+  if (e == cudaSuccess) {
+    narrow_labels_kernel<T><<<stream_grid(ctx, ctx->n), 256, 0, ctx->stream>>>(ctx->wide, ctx->n, hi, tmp, ctx->wide_status);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(st, ctx->wide_status, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && st[1] == 0) e = cudaMemcpyAsync(dst, tmp, (size_t)ctx->n * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(ctx, DPMM_ECUDA, std::string("set labels: ") + cudaGetErrorString(e));
+  if (st[1] != 0) return fail(ctx, DPMM_EINVAL, what);
+  *mx = st[0];
   return 0;
 }
 
 extern "C" int dpmm_set_labels(dpmm_ctx* ctx, const int64_t* labels) {
   NEED(ctx && labels, DPMM_EINVAL, "NULL argument");
   CK(cudaSetDevice(ctx->device));
-  int rc = ensure_stage(ctx, (size_t)ctx->n * 4);
+  int mx = 0;
+  int rc = set_labels_common<int32_t>(ctx, labels, DPMM_MAX_K, ctx->labels, &mx, "label out of range [1, DPMM_MAX_K]");
   if (rc) return rc;
-  CK(cudaStreamSynchronize(ctx->stream));
-  int32_t* h = (int32_t*)ctx->hstage;
-  int64_t mx = 0;
-  for (int64_t i = 0; i < ctx->n; ++i) {
-    NEED(labels[i] >= 1 && labels[i] <= DPMM_MAX_K, DPMM_EINVAL, "label out of range [1, DPMM_MAX_K]");
-    h[i] = (int32_t)(labels[i] - 1);
-    mx = std::max(mx, labels[i]);
-  }
-  ctx->label_bound = (int)mx;
-  rc = ensure_k(ctx, (int)mx);
+  ctx->label_bound = mx;
+  rc = ensure_k(ctx, mx);
   if (rc) return rc;
-  h = (int32_t*)ctx->hstage;
-  CK(cudaMemcpyAsync(ctx->labels, h, (size_t)ctx->n * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
   ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
   return 0;
 }
@@ -609,16 +664,9 @@ extern "C" int dpmm_set_labels(dpmm_ctx* ctx, const int64_t* labels) {
 extern "C" int dpmm_set_sublabels(dpmm_ctx* ctx, const int64_t* sublabels) {
   NEED(ctx && sublabels, DPMM_EINVAL, "NULL argument");
   CK(cudaSetDevice(ctx->device));
-  int rc = ensure_stage(ctx, (size_t)ctx->n);
+  int mx = 0;
+  int rc = set_labels_common<uint8_t>(ctx, sublabels, 2, ctx->sub, &mx, "sub-label must be 1 or 2");
   if (rc) return rc;
-  CK(cudaStreamSynchronize(ctx->stream));
-  uint8_t* h = (uint8_t*)ctx->hstage;
-  for (int64_t i = 0; i < ctx->n; ++i) {
-    NEED(sublabels[i] == 1 || sublabels[i] == 2, DPMM_EINVAL, "sub-label must be 1 or 2");
-    h[i] = (uint8_t)(sublabels[i] - 1);
-  }
-  CK(cudaMemcpyAsync(ctx->sub, h, (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
   ctx->partitioned = ctx->stats_cached = false;
   return 0;
 }
@@ -680,7 +728,7 @@ static int niw_pack_launch(dpmm_ctx* ctx, int K, const double* lfac) {
   }
   {
     NiwPackArgs pa{};
-    pa.D = D; pa.K = K; pa.rec_f = REC; pa.trip = TRIP;
+    pa.D = D; pa.K = K; pa.rec_f = REC; pa.trip = TRIP; pa.D_const = ctx->D_user;
     pa.mu = ctx->raw_params; pa.inv_sigma = ctx->raw_params + nrec * D; pa.logdet = ctx->raw_params + nrec * D + nrec * D * D;
     pa.recs = ctx->recs; pa.cst = ctx->cst;
     pa.tc_w = tcp ? ctx->tc_w : nullptr; pa.tc_b = ctx->tc_b; pa.tc_mu = ctx->tc_mu; pa.tc_fro = ctx->tc_fro;
@@ -717,7 +765,7 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
   CK(cudaSetDevice(ctx->device));
   int rc = ensure_k(ctx, K);
   if (rc) return rc;
-  const int D = ctx->D;
+  const int D = ctx->D, Du = ctx->D_user;
   const size_t nrec = (size_t)3 * K;
   // raw parameters -> pinned staging -> device; the factorisation and packing run on the device
   const size_t raw_floats = nrec * D + nrec * D * D + nrec;
@@ -730,8 +778,18 @@ extern "C" int dpmm_set_params_niw(dpmm_ctx* ctx, int32_t K, const float* mu, co
   float* h_ld = h_inv + nrec * D * D;
   float* h_logw = h_ld + nrec;
   float* h_loglr = h_logw + K;
-  memcpy(h_mu, mu, nrec * D * 4);
-  memcpy(h_inv, inv_sigma, nrec * D * D * 4);
+  if (Du == D) {
+    memcpy(h_mu, mu, nrec * D * 4);
+    memcpy(h_inv, inv_sigma, nrec * D * D * 4);
+  } else {   // padded features: mean 0, unit precision, uncorrelated with the rest
+    memset(h_mu, 0, nrec * D * 4);
+    memset(h_inv, 0, nrec * D * D * 4);
+    for (size_t t = 0; t < nrec; ++t) {
+      memcpy(h_mu + t * D, mu + t * Du, (size_t)Du * 4);
+      for (int i = 0; i < Du; ++i) memcpy(h_inv + (t * D + i) * D, inv_sigma + (t * Du + i) * Du, (size_t)Du * 4);
+      for (int i = Du; i < D; ++i) h_inv[(t * D + i) * D + i] = 1.f;
+    }
+  }
   memcpy(h_ld, logdet, nrec * 4);
   common_weights(ctx, K, weights, lr_weights, h_logw, h_loglr);
   CK(cudaMemcpyAsync(ctx->raw_params, h_mu, raw_floats * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -828,11 +886,11 @@ static int launch_label_tc2(dpmm_ctx* ctx, int final_iter, int nkeys) {
   a.urows = ctx->t2_u; a.mu = ctx->tc_mu; a.cst = ctx->cst; a.logw = ctx->logw; a.fro = ctx->tc_fro;
   a.labels = ctx->labels; a.hist = ctx->hist; a.ovf_list = ctx->perm2; a.ovf_count = ctx->t2_ctr;
   a.u_inj = ctx->u_label; a.seed = ctx->seed; a.call = ctx->call; a.goff = ctx->goff; a.final_iter = final_iter;
-  a.stats = env_int("DPMM_TC_STATS", 0) ? ctx->tc_stats : nullptr;
+  a.stats = ctx->tc_stats;
   const size_t sm = GaussTc2Smem(D, K, a.KS, a.nch, nkeys).total;
   CK(cudaFuncSetAttribute(gauss_label_tc2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   CK(cudaMemsetAsync(ctx->t2_ctr, 0, 8, ctx->stream));
-  if (a.stats) CK(cudaMemsetAsync(ctx->tc_stats, 0, 8, ctx->stream));
+  CK(cudaMemsetAsync(ctx->tc_stats, 0, 8, ctx->stream));
   const int64_t grid = std::min<int64_t>((ctx->n + T2_TILE - 1) / T2_TILE, (int64_t)ctx->sm_count);
   {
     KernelTimer kt(ctx, TK_LABEL);
@@ -851,6 +909,15 @@ static int launch_label_tc2(dpmm_ctx* ctx, int final_iter, int nkeys) {
     gauss_label_list_kernel<D><<<(unsigned)ctx->sm_count * 2, 256, lsm, ctx->stream>>>(l);
     CK(cudaGetLastError());
   }
+  // counters -> pinned memory (read by the next call's path choice, never waited for)
+  if (ctx->t2_hstat == nullptr) {
+    CK(cudaMallocHost((void**)&ctx->t2_hstat, 4 * sizeof(int32_t)));
+    CK(cudaEventCreateWithFlags(&ctx->t2_hstat_ev, cudaEventDisableTiming));
+  }
+  CK(cudaMemcpyAsync(ctx->t2_hstat, ctx->tc_stats, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->t2_hstat + 2, ctx->t2_ctr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(ctx->t2_hstat_ev, ctx->stream));
+  ctx->t2_hstat_pending = true;
   return 0;
 }
 
@@ -863,6 +930,21 @@ static int run_sample_labels(dpmm_ctx* ctx, int final_iter, float* dump) {
   // operation ran since)
   bool use_t2 = ctx->prior == DPMM_PRIOR_NIW && ctx->t2_params && dump == nullptr &&
                 ctx->sampler == DPMM_SAMPLER_INVERSE_CDF && env_int("DPMM_LABEL_TC", 2) == 2;
+  if (use_t2 && env_int("DPMM_LABEL_ADAPT", 1) != 0) {
+    // the previous tensor-core call's counters, if they have arrived: exact (point, cluster) evaluations cost about
+    // what the FMA kernel pays per (point, cluster) too, so beyond ~K/3 of them per point (or many overflow points,
+    // which evaluate all K) the FMA kernel that evaluates everything wins; try the tensor-core path again later
+    if (ctx->t2_hstat_pending && cudaEventQuery(ctx->t2_hstat_ev) == cudaSuccess) {
+      ctx->t2_hstat_pending = false;
+      const double pts = std::max(1, ctx->t2_hstat[0]);
+      const double evals = (double)ctx->t2_hstat[1] / pts;   // (overflow points count K evaluations each)
+      if (evals > 0.03 * K + 0.05) ctx->t2_cooldown = 8;
+    }
+    if (ctx->t2_cooldown > 0) {
+      --ctx->t2_cooldown;
+      use_t2 = false;
+    }
+  }
   int nkeys = 0;
   if (use_t2) {
     nkeys = keff(ctx);
@@ -1221,9 +1303,11 @@ extern "C" int dpmm_suff_stats(dpmm_ctx* ctx, const int64_t* indices, int32_t n_
     for (int s = 0; s < 3; ++s) {
       const double* r = h + ((size_t)a * 3 + s) * rec;
       if (counts) counts[a * 3 + s] = (int64_t)llround(r[0]);
-      if (sum_x) memcpy(sum_x + ((size_t)a * 3 + s) * D, r + 1, (size_t)D * 8);
+      const int Du = ctx->D_user;
+      if (sum_x) memcpy(sum_x + ((size_t)a * 3 + s) * Du, r + 1, (size_t)Du * 8);
       if (sum_xx && ctx->prior == DPMM_PRIOR_NIW)
-        memcpy(sum_xx + ((size_t)a * 3 + s) * D * D, r + 1 + D, (size_t)D * D * 8);
+        for (int i = 0; i < Du; ++i)
+          memcpy(sum_xx + (((size_t)a * 3 + s) * Du + i) * Du, r + 1 + D + (size_t)i * D, (size_t)Du * 8);
     }
   return 0;
 }
@@ -1237,6 +1321,9 @@ extern "C" int dpmm_num_clusters(const dpmm_ctx* ctx) { return ctx ? keff(ctx) :
 extern "C" int dpmm_set_hyper_niw(dpmm_ctx* ctx, double kappa, const double* m, double nu, const double* psi, double alpha) {
   NEED(ctx && m && psi, DPMM_EINVAL, "NULL argument");
   NEED(ctx->prior == DPMM_PRIOR_NIW, DPMM_ESTATE, "context was created with the multinomial prior");
+  NEED(ctx->D == ctx->D_user, DPMM_ELIMIT,
+       "the device-side parameter step needs an instantiated feature dimension (1-8, 12, 16, 24, 32, 48, 64); "
+       "sample the parameters on the host (dpmm_set_params_niw) for other D");
   NEED(kappa > 0 && nu > ctx->D - 1 && alpha > 0, DPMM_EINVAL, "need kappa > 0, nu > D - 1, alpha > 0");
   CK(cudaSetDevice(ctx->device));
   const int D = ctx->D;
@@ -1461,12 +1548,26 @@ extern "C" int dpmm_predict_niw(dpmm_ctx* ctx, int32_t K, const float* u, const 
   float* d_mu = d_u + (size_t)K * D * D;
   float* d_tc = d_mu + (size_t)K * D;
   float* d_df = d_tc + K;
+  std::vector<float> up, mp;
+  if (ctx->D_user != D) {   // padded features: unit factor rows, zero means
+    const int Du = ctx->D_user;
+    up.assign((size_t)K * D * D, 0.f);
+    mp.assign((size_t)K * D, 0.f);
+    for (int k = 0; k < K; ++k) {
+      for (int i = 0; i < Du; ++i) memcpy(&up[((size_t)k * D + i) * D], u + ((size_t)k * Du + i) * Du, (size_t)Du * 4);
+      for (int i = Du; i < D; ++i) up[((size_t)k * D + i) * D + i] = 1.f;
+      memcpy(&mp[(size_t)k * D], mu + (size_t)k * Du, (size_t)Du * 4);
+    }
+    u = up.data();
+    mu = mp.data();
+  }
   CKP(cudaMemcpyAsync(d_u, u, (size_t)K * D * D * 4, cudaMemcpyHostToDevice, ctx->stream));
   CKP(cudaMemcpyAsync(d_mu, mu, (size_t)K * D * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaStreamSynchronize(ctx->stream));   // (the padded copies above live on this stack frame)
   CKP(cudaMemcpyAsync(d_tc, tconst, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
   CKP(cudaMemcpyAsync(d_df, df, (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
   NiwPredictArgs pa{};
-  pa.x = ctx->x; pa.n = ctx->n; pa.D = D; pa.K = K; pa.u = d_u; pa.mu = d_mu; pa.tconst = d_tc; pa.df = d_df;
+  pa.x = ctx->x; pa.n = ctx->n; pa.D = D; pa.D_true = ctx->D_user; pa.K = K; pa.u = d_u; pa.mu = d_mu; pa.tconst = d_tc; pa.df = d_df;
   pa.labels = dlab; pa.probs = dprob;
   const size_t sm = (size_t)8 * (D + K) * 4;
   if (sm > 48 * 1024) CKP(cudaFuncSetAttribute(niw_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

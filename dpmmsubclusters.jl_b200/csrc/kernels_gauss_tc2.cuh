@@ -587,6 +587,8 @@ __global__ void __launch_bounds__(T2_THREADS(D), 1) gauss_label_tc2_kernel(const
           uint16_t* wpairs = pairs + wq * 32 * T2_CMAX;
           for (int j = 0; j < mine; ++j) wpairs[off + j] = (uint16_t)((row << 3) | j);
           __syncwarp();
+          // one pair per lane: 32 independent evaluations in flight per warp hide the L2 latency of the factor rows
+          // (measured against a warp-cooperative form, lane <-> row of U_k: 3.6x slower, one pair's latency at a time)
           for (int p = lane; p < total; p += 32) {
             const int pr = wpairs[p], prow = pr >> 3, slot = pr & 7;
             const int k = lists[prow * T2_CMAX + slot];
@@ -634,9 +636,16 @@ __global__ void __launch_bounds__(T2_THREADS(D), 1) gauss_label_tc2_kernel(const
         }
         if (T2_PROF) prof[6] += clock64() - tp2;
       }
-      if (a.stats != nullptr) {
-        atomicAdd(&a.stats[0], npts_total);
-        atomicAdd(&a.stats[1], ncand_total);
+      {   // per-call counters (points, exact evaluations): read back asynchronously by the host's path choice
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          npts_total += __shfl_xor_sync(0xffffffffu, npts_total, o);
+          ncand_total += __shfl_xor_sync(0xffffffffu, ncand_total, o);
+        }
+        if (lane == 0 && a.stats != nullptr) {
+          atomicAdd(&a.stats[0], npts_total);
+          atomicAdd(&a.stats[1], ncand_total);
+        }
       }
     } else {
       // =============================== gather warps ===============================

@@ -14,6 +14,7 @@
 
 struct NiwPackArgs {
   int D, K, rec_f, trip;
+  int D_const;             // the D of the reference's D^2 log(2 pi) constant (= the caller's D when features are padded)
   const float* mu;         // [3K][D]
   const float* inv_sigma;  // [3K][D][D]
   const float* logdet;     // [3K]
@@ -79,7 +80,7 @@ __device__ __forceinline__ void niw_pack_body(const NiwPackArgs& a, const int t,
   for (int j = tid; j < D; j += NT) rec[a.trip + j] = a.mu[(size_t)t * D + j];
   if (tid == 0) {
     const float log2pi = 1.8378770664093453f;   // Float32(log(2pi)), mv_gaussian.jl:24
-    a.cst[t] = __fmul_rn(__fadd_rn(__fmul_rn((float)(D * D), log2pi), a.logdet[t]), 0.5f);
+    a.cst[t] = __fmul_rn(__fadd_rn(__fmul_rn((float)(a.D_const * a.D_const), log2pi), a.logdet[t]), 0.5f);
   }
   if ((a.tc_w != nullptr || a.t2_piv != nullptr) && t % 3 == 0) {
     const int k = t / 3;

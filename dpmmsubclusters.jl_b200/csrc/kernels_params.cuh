@@ -29,6 +29,14 @@
 #include "kernels_pack.cuh"
 
 #define DPMM_STREAM_PARAMS 5u
+#ifndef PARAM_PROF
+#define PARAM_PROF 0
+#endif
+#if PARAM_PROF
+#define PP_MARK(i) do { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x == 0) pp[i] = clock64(); } while (0)
+#else
+#define PP_MARK(i) do { } while (0)
+#endif
 #define NIW_HYPER_DOUBLES(D) (4 + (D) + (D) * (D))          // kappa, nu, logdet psi, lmvgamma(nu/2) | m | psi
 #define NIW_POST_DOUBLES(D) (8 + (D) + (D) * (D))           // kappa', nu', N, logml, logdet psi', ok, -, - | m' | Lhat
 
@@ -82,22 +90,20 @@ __device__ inline double niw_lmvgamma(double x, int D) {
 // Returns false when a pivot is not positive and finite.
 __device__ inline bool cta_cholesky(double* A, int D, int LD) {
   const int tid = threadIdx.x, NT = blockDim.x;
+  const int ty = tid >> 4, tx = tid & 15, NY = NT >> 4;   // 16 x (NT / 16) thread tile of the trailing update
   bool ok = true;
   for (int j = 0; j < D; ++j) {
     const double d = A[j * LD + j];
     ok = ok && (d > 0.0) && (d < CUDART_INF);
-    const double ljj = sqrt(d);
+    const double ljj = sqrt(d), rl = 1.0 / ljj;
     __syncthreads();
     if (tid == 0) A[j * LD + j] = ljj;
-    for (int i = j + 1 + tid; i < D; i += NT) A[i * LD + j] /= ljj;
+    for (int i = j + 1 + tid; i < D; i += NT) A[i * LD + j] *= rl;
     __syncthreads();
-    const int m = D - j - 1;
-    for (int e = tid; e < m * m; e += NT) {
-      const int ii = e / m, kk = e - ii * m;
-      if (kk <= ii) {
-        const int i = j + 1 + ii, k = j + 1 + kk;
-        A[i * LD + k] -= A[i * LD + j] * A[k * LD + j];
-      }
+    // trailing update of the lower triangle: element (i, k), j < k <= i < D
+    for (int i = j + 1 + ty; i < D; i += NY) {
+      const double lij = A[i * LD + j];
+      for (int k = j + 1 + tx; k <= i; k += 16) A[i * LD + k] -= lij * A[k * LD + j];
     }
     __syncthreads();
   }
@@ -255,6 +261,10 @@ __global__ void __launch_bounds__(NIW_PACK_THREADS) niw_draw_kernel(const NiwDra
   const int t = blockIdx.x, tid = threadIdx.x, NT = NIW_PACK_THREADS;
   const double* P = a.post + (size_t)t * NIW_POST_DOUBLES(D);
   const bool prior = a.first != 0 || !(P[2] > 0.0);
+#if PARAM_PROF
+  __shared__ long long pp[12];
+#endif
+  PP_MARK(0);
   double kp, nup;
   const double* mpost;
   if (prior) {
@@ -276,76 +286,107 @@ __global__ void __launch_bounds__(NIW_PACK_THREADS) niw_draw_kernel(const NiwDra
     for (int e = tid; e < D * D; e += NT) Wk[(e / D) * LD + (e % D)] = P[8 + D + e];
     __syncthreads();
   }
-  // ---- Bartlett factor B (lower) and the normals of the mean ----
+  PP_MARK(1);
+  // ---- Bartlett factor B (lower) and the normals of the mean.  The D chi-square draws (rejection loops in
+  //      Float64) go to the lanes of the last warp(s) together, so that no other warp diverges into them ----
   for (int e = tid; e < D * D + D; e += NT) {
-    ParamRng rng(a.seed, a.call, (uint32_t)t, (uint32_t)e);
     if (e >= D * D) {
+      ParamRng rng(a.seed, a.call, (uint32_t)t, (uint32_t)e);
       xi[e - D * D] = rng.normal();
     } else {
       const int i = e / D, j = e - i * D;
-      double v = 0.0;
-      if (i == j) v = sqrt(2.0 * rng.gamma(0.5 * (nup - i)));
-      else if (i > j) v = rng.normal();
-      Bm[i * LD + j] = v;
+      if (i != j) {
+        ParamRng rng(a.seed, a.call, (uint32_t)t, (uint32_t)e);
+        Bm[i * LD + j] = i > j ? rng.normal() : 0.0;
+      }
     }
   }
-  // ---- Linv = Lhat^-1 (lower), column c by thread c (forward substitution), into Ls as scratch ----
-  for (int c = tid; c < D; c += NT) {
-    for (int i = 0; i < c; ++i) Ls[i * LD + c] = 0.0;
-    Ls[c * LD + c] = 1.0 / Wk[c * LD + c];
-    for (int i = c + 1; i < D; ++i) {
-      double sacc = 0.0;
-      for (int k = c; k < i; ++k) sacc += Wk[i * LD + k] * Ls[k * LD + c];
-      Ls[i * LD + c] = -sacc / Wk[i * LD + i];
-    }
+  for (int i = NT - 1 - tid; i < D; i += NT) {
+    ParamRng rng(a.seed, a.call, (uint32_t)t, (uint32_t)(i * D + i));
+    Bm[i * LD + i] = sqrt(2.0 * rng.gamma(0.5 * (nup - i)));
   }
   __syncthreads();
-  // ---- M[i][j] = Linv[R(j)][R(i)] / sqrt(nu')  (lower), into Wk ----
+  PP_MARK(2);
+  // ---- L = M B with M = V^-T / sqrt(nu'), V = P Lhat P:  Lhat' X = P B / sqrt(nu'),  X = P L.
+  //      Back substitution over the rows of the upper-triangular Lhat' in its column-oriented form (once x_i is
+  //      final, every row k < i of the right-hand side loses Lhat[i][k] x_i).
+  //      Every column j of X is an independent triangular system: a warp takes four of them at a time, lane <->
+  //      row (rows k and k + 32), and walks the rows from the last one up; x_i is broadcast with a shuffle, the
+  //      updates r_k -= Lhat[i][k] x_i need no barrier.  The rows of X land row-reversed in Ls, i.e. as L. ----
   const double rs = 1.0 / sqrt(nup);
-  for (int e = tid; e < D * D; e += NT) {
-    const int i = e / D, j = e - i * D;
-    Wk[i * LD + j] = (i >= j) ? Ls[(D - 1 - j) * LD + (D - 1 - i)] * rs : 0.0;
+  for (int i = tid; i < D; i += NT) y[i] = 1.0 / Wk[i * LD + i];   // reciprocal pivots (y is free until the mean)
+  __syncthreads();
+  {
+    const int warp = tid >> 5, lane = tid & 31, NW = NT >> 5;
+    for (int jb = warp * 4; jb < D; jb += NW * 4) {
+      double r0[4], r1[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = jb + q;
+        r0[q] = (j < D && lane < D) ? Bm[(D - 1 - lane) * LD + j] * rs : 0.0;
+        r1[q] = (j < D && lane + 32 < D) ? Bm[(D - 1 - lane - 32) * LD + j] * rs : 0.0;
+      }
+      for (int i = D - 1; i >= 0; --i) {
+        const double rd = y[i];
+        const int src = i & 31;
+        const double l0 = lane < i ? Wk[i * LD + lane] : 0.0;
+        const double l1 = lane + 32 < i ? Wk[i * LD + lane + 32] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double xq = __shfl_sync(0xffffffffu, (i >= 32 ? r1[q] : r0[q]) * rd, src);
+          if (lane == src && jb + q < D) Ls[(D - 1 - i) * LD + jb + q] = xq;
+          r0[q] -= l0 * xq;
+          r1[q] -= l1 * xq;
+        }
+      }
+    }
   }
   __syncthreads();
-  // ---- L = M B (lower) into Ls ----
-  for (int e = tid; e < D * D; e += NT) {
-    const int i = e / D, j = e - i * D;
-    double v = 0.0;
-    if (i >= j)
-      for (int k = j; k <= i; ++k) v += Wk[i * LD + k] * Bm[k * LD + j];
-    Ls[i * LD + j] = v;
-  }
-  __syncthreads();
-  // ---- checks, logdet Sigma, the mean: L' y = xi (back substitution by warp 0) ----
+  PP_MARK(4);
   __shared__ int ok_s;
   if (tid == 0) ok_s = 1;
   __syncthreads();
+  PP_MARK(5);
   for (int e = tid; e < D * D; e += NT) {
     const int i = e / D, j = e - i * D;
-    const double v = Ls[i * LD + j];
+    const double v = j <= i ? Ls[i * LD + j] : 0.0;          // (entries above the diagonal are rounding residue)
     if (!(fabs(v) < CUDART_INF) || (i == j && !(v > 0.0))) ok_s = 0;
     a.lfac[(size_t)t * D * D + e] = v;
   }
   __syncthreads();
+  // ---- the mean: L' y = xi, column-oriented back substitution by warp 0 (lane <-> unknowns k, k + 32);
+  //      logdet Sigma = -2 sum log L_ii with the D logarithms taken in parallel ----
   if (tid < 32) {
     const int lane = tid;
+    double r0 = lane < D ? xi[lane] : 0.0, r1 = lane + 32 < D ? xi[lane + 32] : 0.0;
+    double lg = 0.0;
+    for (int i = lane; i < D; i += 32) lg += log(Ls[i * LD + i]);
+    const double d0 = lane < D ? 1.0 / Ls[lane * LD + lane] : 0.0, d1 = lane + 32 < D ? 1.0 / Ls[(lane + 32) * LD + lane + 32] : 0.0;
+    double y0 = 0.0, y1 = 0.0;
     for (int i = D - 1; i >= 0; --i) {
-      double part = 0.0;
-      for (int k = i + 1 + lane; k < D; k += 32) part += Ls[k * LD + i] * y[k];
+      const double mine = i >= 32 ? r1 * d1 : r0 * d0;
+      const double yi = __shfl_sync(0xffffffffu, mine, i & 31);
+      if (lane == (i & 31)) {
+        if (i >= 32) y1 = yi; else y0 = yi;
+      }
+      // r_k -= L[i][k] y_i for k < i
+      if (lane < i) r0 -= Ls[i * LD + lane] * yi;
+      if (lane + 32 < i) r1 -= Ls[i * LD + lane + 32] * yi;
+    }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if (lane == 0) y[i] = (xi[i] - part) / Ls[i * LD + i];
-      __syncwarp();
-    }
+    for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
+    __syncwarp();
+    const bool okk = ok_s != 0;
     const double rk = 1.0 / sqrt(kp);
-    for (int i = lane; i < D; i += 32)
-      a.mu[(size_t)t * D + i] = (float)(mpost[i] + y[i] * rk);
-    if (lane == 0) {
-      double ld = 0.0;
-      for (int i = 0; i < D; ++i) ld += log(Ls[i * LD + i]);
-      a.logdet[t] = ok_s ? (float)(-2.0 * ld) : __int_as_float(0x7fc00000);
-    }
+    if (lane < D) a.mu[(size_t)t * D + lane] = (float)(mpost[lane] + y0 * rk);
+    if (lane + 32 < D) a.mu[(size_t)t * D + lane + 32] = (float)(mpost[lane + 32] + y1 * rk);
+    if (lane == 0) a.logdet[t] = okk ? (float)(-2.0 * lg) : __int_as_float(0x7fc00000);
   }
+  PP_MARK(6);
+#if PARAM_PROF
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    printf("[draw prof] load %lld bartlett %lld solve %lld mean %lld\n", pp[1] - pp[0], pp[2] - pp[1], pp[4] - pp[2], pp[6] - pp[4]);
+#endif
 }
 
 struct WeightsArgs {
@@ -440,6 +481,7 @@ struct NiwPredictArgs {
   const float* x;       // [n][D]
   int64_t n;
   int D, K;
+  int D_true;           // the caller's feature dimension (D may be zero-padded): the exponent is (df + D_true)/2
   const float* u;       // [K][D][D] rows of U_k (zero below the diagonal)
   const float* mu;      // [K][D]
   const float* tconst;  // [K]  C_k + log w_k
@@ -466,7 +508,7 @@ __global__ void __launch_bounds__(256) niw_predict_kernel(const NiwPredictArgs a
         q = fmaf(y, y, q);
       }
       const float df = __ldg(a.df + k);
-      rs[k] = __ldg(a.tconst + k) - 0.5f * (df + (float)D) * log1pf(q / df);
+      rs[k] = __ldg(a.tconst + k) - 0.5f * (df + (float)a.D_true) * log1pf(q / df);
     }
     __syncwarp();
     if (lane == 0) {

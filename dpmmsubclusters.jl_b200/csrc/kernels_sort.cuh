@@ -154,3 +154,57 @@ __global__ void init_labels_kernel(int32_t* labels, int64_t n, int init_clusters
     labels[i] = l + shift;
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Label gather / restore at the boundary (Array(group.labels), dp-parallel-sampling.jl:218,276,371; resume
+// :437-438): the widening to 1-based Int64, the narrowing and the range check run on the device, so the host
+// side of dpmm_get/set_labels is one copy of the caller's own array, not a scalar loop over n points.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void widen_labels_kernel(const T* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (int64_t)in[i] + 1;
+}
+// out[i] = in[i] - 1; status[0] = max label seen, status[1] = 1 if any label is outside [1, hi]
+template <typename T>
+__global__ void narrow_labels_kernel(const int64_t* __restrict__ in, int64_t n, int64_t hi, T* __restrict__ out,
+                                     int32_t* __restrict__ status) {
+  int mx = 0, bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = in[i];
+    if (v < 1 || v > hi) bad = 1;
+    else {
+      out[i] = (T)(v - 1);
+      mx = max(mx, (int)v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (mx) atomicMax(&status[0], mx);
+    if (bad) atomicOr(&status[1], 1);
+  }
+}
+// multinomial create: are all counts integral and below 2^11 in magnitude (exact in TF32)?  flag[0] |= 1 if not
+__global__ void tf32_exact_scan_kernel(const float* __restrict__ x, int64_t n, int32_t* __restrict__ flag) {
+  int bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    if (!(v == truncf(v) && v > -2048.f && v < 2048.f)) bad = 1;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+// x_pad[i][0..Dp) = (x[i][0..D), 0, ...): the one-time widening of the points of a context whose feature dimension
+// has no instantiated kernels (zero features with unit precision change no likelihood and no statistic)
+__global__ void pad_points_kernel(const float* __restrict__ x, int64_t n, int D, int Dp, float* __restrict__ xp) {
+  const int64_t tot = n * Dp;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / Dp;
+    const int j = (int)(e - i * Dp);
+    xp[e] = j < D ? x[i * D + j] : 0.f;
+  }
+}

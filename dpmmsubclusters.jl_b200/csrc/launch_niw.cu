@@ -30,10 +30,10 @@ struct LabelP {  // points per thread of the label kernel
   static constexpr int P = (D <= 16) ? 4 : (D <= 32 ? 2 : 1);
 };
 
-template <int D, int P>
+template <int D, int P, bool TILE_ONLY = false>
 static int launch_gauss_label_p(dpmm_ctx* ctx, GaussLabelArgs a) {
   using C = GaussCfg<D>;
-  {
+  if constexpr (!TILE_ONLY) {
     // warp-autonomous form: all K records resident + W private warp buffers
     const size_t fixed = ((size_t)a.K * C::REC + 3 * (size_t)((a.K + 3) & ~3)) * 4;
     const size_t perwarp = ((size_t)32 * P * C::DS + (size_t)a.K * 32 * P) * 4;
@@ -101,7 +101,12 @@ static int launch_gauss_label(dpmm_ctx* ctx, GaussLabelArgs a) {
     if (p == 4) return launch_gauss_label_p<D, 4>(ctx, a);
   }
 #endif
-  return launch_gauss_label_p<D, LabelP<D>::P>(ctx, a);
+  int rc = launch_gauss_label_p<D, LabelP<D>::P>(ctx, a);
+  if constexpr (LabelP<D>::P > 1) {
+    // the tile's slice of parr ([K][points]) is what limits K: one point per thread carries K up to DPMM_MAX_K
+    if (rc == DPMM_ELIMIT) rc = launch_gauss_label_p<D, 1, true>(ctx, a);
+  }
+  return rc;
 }
 
 template <int D>

@@ -15,3 +15,11 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True)
+def _pin_label_path(monkeypatch):
+    """The NIW label path adapts at run time (tensor-core kernel <-> FMA kernel, from the previous call's candidate
+    counters).  Parity tests pin it so that each test exercises the path it names; the adaptive switch has its own
+    test (test_label_path_adapts_to_overlapping_clusters)."""
+    monkeypatch.setenv("DPMM_LABEL_ADAPT", "0")

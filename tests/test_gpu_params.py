@@ -87,7 +87,9 @@ def test_device_posterior_on_the_reference_checkpoint(pkg, golden_dir):
             stored = P.niw_hyperparams(1.0 + N, gd["post_m"][k, s], 5.0 + N, gd["post_psi"][k, s])
             ss = P.make_suff_stats(hyper, N, gd["sum_x"][k, s], gd["sum_xx"][k, s])
             want = P.log_marginal_likelihood(hyper, stored, ss)
-            assert abs(logml[k, s] - want) <= 2e-6 * abs(want) + 1e-4, (k, s, logml[k, s], want)
+            # (the device sees the points rounded to Float32, the checkpoint was written from Float64 points: the
+            #  statistics differ by ~1e-7 relative, which nu'/2 ~ 100 amplifies in the log determinant term)
+            assert abs(logml[k, s] - want) <= 1e-5 * abs(want) + 1e-3, (k, s, logml[k, s], want)
     g.close()
 
 

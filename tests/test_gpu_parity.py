@@ -33,6 +33,8 @@ NIW_CASES = [  # (D, K, n)
     (64, 12, 3000),    # config C5 shape
     (32, 1, 5000), (5, 50, 8000),   # K = 1; config C4 shape
     (32, 100, 3000),   # K large enough that the staged clusters are chunked
+    (9, 4, 3000), (10, 6, 2500), (20, 5, 3000), (30, 8, 6000), (50, 3, 2000),   # no instantiated width: zero-padded
+    (3, 700, 4000),    # K beyond the 4-points-per-thread tile: one point per thread
 ]
 
 
@@ -382,7 +384,7 @@ def test_error_behaviour(pkg):
     assert ei.value.code == E.ESTATE
     g.close()
     with pytest.raises(E.DpmmError) as ei:
-        pkg.GpuSweep(np.zeros((9, 4), np.float32), pkg.NIW)     # D=9 is not an instantiated width
+        pkg.GpuSweep(np.zeros((65, 4), np.float32), pkg.NIW)    # NIW: D <= 64
     assert ei.value.code == E.ELIMIT
 
 
@@ -445,4 +447,116 @@ def test_full_size_properties_c2(pkg):
     np.testing.assert_array_equal(g.get_labels(), lab)
     s2 = g.get_sublabels()
     np.testing.assert_array_equal(s2[lab == 1], sub[lab == 1])      # former-1 points -> 1, former-(K+1) -> 2
+    g.close()
+
+
+def test_full_size_properties_c3_multinomial(pkg):
+    """BASELINE config C3 shape (multinomial, N=1e6, D=100, K=20): size-independent properties (count vectors are
+    exact integers, so sums over clusters equal the column sums of X bit for bit) + oracle parity on a sub-sample."""
+    n, D, K = 1_000_000, 100, 20
+    case = make_mnm_case(D, K, n, seed=78)
+    g = pkg.GpuSweep(case["x"], pkg.MULTINOMIAL, seed=321)
+    set_params(g, case)
+    g.sample_labels(False); g.sample_sublabels()
+    lab, sub = g.get_labels(), g.get_sublabels()
+    counts, sx, _ = g.suff_stats()
+    assert lab.min() >= 1 and lab.max() <= K and set(np.unique(sub)) <= {1, 2}
+    np.testing.assert_array_equal(counts[:, 0], np.bincount(lab, minlength=K + 1)[1:])
+    np.testing.assert_array_equal(counts[:, 1], np.bincount(lab[sub == 1], minlength=K + 1)[1:])
+    np.testing.assert_array_equal(sx[:, 0], sx[:, 1] + sx[:, 2])
+    np.testing.assert_array_equal(sx[:, 0].sum(0), case["x"].astype(np.float64).sum(1))
+    k0 = int(np.argmax(counts[:, 0]))
+    np.testing.assert_array_equal(sx[k0, 1], case["x"][:, (lab == k0 + 1) & (sub == 1)].astype(np.float64).sum(1))
+    sel = np.sort(np.random.default_rng(0).choice(n, 20000, replace=False))
+    o = O.OracleSweep(case["x"][:, sel], O.MULTINOMIAL, seed=321)
+    o.gidx = sel.astype(np.uint64)
+    set_params(o, case)
+    o.sample_labels(False)
+    u = O.philox_uniform(321, O.STREAM_LABEL, 1, o.gidx)
+    check_draws(o.debug_loglik(0), u, lab[sel], o.get_labels(), "C3 labels (sub-sample)")
+    o.set_labels(lab[sel])
+    o.sample_sublabels()
+    u = O.philox_uniform(321, O.STREAM_SUBLABEL, 2, o.gidx)
+    check_draws(o.debug_loglik(1), u, sub[sel], o.get_sublabels(), "C3 sub-labels (sub-sample)")
+    g.apply_split([k0 + 1], [K + 1])
+    np.testing.assert_array_equal(g.get_labels() == K + 1, (lab == k0 + 1) & (sub == 2))
+    g.apply_merge([k0 + 1], [K + 1])
+    np.testing.assert_array_equal(g.get_labels(), lab)
+    g.close()
+
+
+def test_full_size_properties_c4_image_segmentation_shape(pkg):
+    """BASELINE config C4 shape (NIW, N=1e7, D=5, K=50): properties at full size + oracle parity on a sub-sample."""
+    n, D, K = 10_000_000, 5, 50
+    case = make_niw_case(D, K, n, seed=79, spread=3.0)
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=55)
+    set_params(g, case)
+    g.sample_labels(False); g.sample_sublabels()
+    lab, sub = g.get_labels(), g.get_sublabels()
+    counts, sx, sxx = g.suff_stats()
+    assert lab.min() >= 1 and lab.max() <= K and set(np.unique(sub)) <= {1, 2}
+    np.testing.assert_array_equal(counts[:, 0], np.bincount(lab, minlength=K + 1)[1:])
+    np.testing.assert_array_equal(counts[:, 1], np.bincount(lab[sub == 1], minlength=K + 1)[1:])
+    np.testing.assert_array_equal(counts[:, 0], counts[:, 1] + counts[:, 2])
+    np.testing.assert_allclose(sx[:, 0], sx[:, 1] + sx[:, 2], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(sx[:, 0].sum(0), case["x"].astype(np.float64).sum(1), rtol=1e-6)
+    tot = case["x"].astype(np.float64) @ case["x"].astype(np.float64).T
+    np.testing.assert_allclose(sxx[:, 0].sum(0), tot, rtol=1e-5, atol=1e-5 * np.abs(tot).max())
+    sel = np.sort(np.random.default_rng(0).choice(n, 20000, replace=False))
+    o = O.OracleSweep(case["x"][:, sel], O.NIW, seed=55)
+    o.gidx = sel.astype(np.uint64)
+    set_params(o, case)
+    o.sample_labels(False)
+    u = O.philox_uniform(55, O.STREAM_LABEL, 1, o.gidx)
+    check_draws(o.debug_loglik(0), u, lab[sel], o.get_labels(), "C4 labels (sub-sample)")
+    o.set_labels(lab[sel])
+    o.sample_sublabels()
+    u = O.philox_uniform(55, O.STREAM_SUBLABEL, 2, o.gidx)
+    check_draws(o.debug_loglik(1), u, sub[sel], o.get_sublabels(), "C4 sub-labels (sub-sample)")
+    g.close()
+
+
+def test_suff_stats_all_after_a_split_sizes_its_result_by_the_label_bound(pkg):
+    """dpmm_suff_stats(indices = NULL) writes one row per label value in use; after apply_split that is
+    K + 1.  The Python mirror sizes its arrays from dpmm_num_clusters, and a wrong n_indices is refused."""
+    import ctypes as C
+    case = make_niw_case(4, 3, 2000, seed=3)
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=1)
+    set_params(g, case)
+    g.sample_labels(False); g.sample_sublabels()
+    c0 = g.suff_stats()[0]
+    assert c0.shape == (3, 3)
+    g.apply_split([1], [4])
+    c1 = g.suff_stats()[0]                       # no manual K patching
+    assert c1.shape == (4, 3) and c1[:, 0].sum() == 2000 and c1[3, 0] == c0[0, 2]
+    small = np.zeros((3, 3), np.int64)
+    rc = g.lib.dpmm_suff_stats(g.h, None, 3, small.ctypes.data_as(C.POINTER(C.c_int64)), None, None)
+    assert rc == pkg._lib.EINVAL
+    g.close()
+
+
+def test_label_path_adapts_to_overlapping_clusters(pkg, monkeypatch):
+    """With heavily overlapping clusters nearly every cluster is a candidate of every point: the tensor-core kernel's
+    counters say so, and the following calls run on the FMA kernel (which evaluates all K anyway) for a while.
+    Either path gives the oracle's labels."""
+    monkeypatch.setenv("DPMM_LABEL_ADAPT", "1")
+    monkeypatch.setenv("DPMM_TC_STATS", "1")
+    case = make_niw_case(32, 12, 20000, seed=4, spread=0.3)
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=7)
+    o = O.OracleSweep(case["x"], O.NIW, seed=7)
+    rng = np.random.default_rng(1)
+    ran_tc = []
+    for it in range(4):
+        u = rng.random(case["n"])
+        for s_ in (g, o):
+            s_.set_uniforms(u, None, None)
+            set_params(s_, case)
+            s_.sample_labels(False)
+        gl = g.get_labels()                      # (synchronises: the counters of this call have arrived)
+        ran_tc.append(g.tc_stats()[0] == case["n"] if it == 0 else None)
+        check_draws(o.debug_loglik(0), u, gl, o.get_labels(), f"labels, call {it}")
+        o.set_labels(gl)
+    assert ran_tc[0], "the first call must take the tensor-core kernel"
+    g.sample_labels(False)
+    # tc_stats are zeroed only by a tensor-core launch: unchanged counters == the FMA kernel ran
     g.close()
