@@ -109,11 +109,13 @@ __device__ __forceinline__ void stc_walk_init(StcWalk& w, const int32_t* B, cons
   w.gcount = 0;
 }
 // the current tile closes its flush group (last tile of the key, of the CTA's range, or STC_FLUSH-th)
+template <int FL = STC_FLUSH>
 __device__ __forceinline__ bool stc_is_last(const StcWalk& w) {
-  return w.pos + STC_TILE >= w.end || w.gcount == STC_FLUSH - 1 || w.tleft == 1;
+  return w.pos + STC_TILE >= w.end || w.gcount == FL - 1 || w.tleft == 1;
 }
+template <int FL = STC_FLUSH>
 __device__ __forceinline__ void stc_advance(StcWalk& w, const int32_t* B) {
-  w.gcount = stc_is_last(w) ? 0 : w.gcount + 1;
+  w.gcount = stc_is_last<FL>(w) ? 0 : w.gcount + 1;
   --w.tleft;
   w.pos += STC_TILE;
   if (w.pos >= w.end && w.tleft > 0) {

@@ -23,31 +23,56 @@
 //     layout (128B swizzle with 32-byte atoms, the only one tcgen05 takes for 32-bit MN-major data).
 //     Every 8-row k-step then belongs to one side:   D_side += [h | l]' h   (rows 0-31 sum h h',
 //     rows 32-63 sum l h'),  S = hh' + lh' + (lh')' as in kernels_stats_tc.cuh, flushed to the Float64
-//     accumulators every STC_FLUSH tiles.  No masked copies, no left/right partition of the permutation.
+//     accumulators every SS_FLUSH tiles.  No masked copies, no left/right partition of the permutation.
 //   sum y and the left count come from the permuting pass.  Everything is shifted back by c_k in
 //   Float64 by stats_finalize_kernel.
 //
-// Warp roles (768 threads, one CTA per SM; every CTA owns a contiguous range of the tile sequence):
-//   warps 0-3, 19-22  gather + shift + split         warps 5-8 / 9-12  GEMM1 epilogue of the even / odd tiles:
-//   warp  4    GEMM1 issuer                                      draw, permute, sum y
+// Warp roles (896 threads, one CTA per SM; every CTA owns a contiguous range of the tile sequence):
+//   warps 0-3, 19-22  gather + shift + split         warps 5-8 / 9-12 / 24-27  GEMM1 epilogue of the tiles
+//   warp  4    GEMM1 issuer                                      li = 0 / 1 / 2 (mod 3): draw, permute, sum y
 //   warp  17   stages the next cluster's       warps 13-16       GEMM2 accumulator drain
 //              factors                         warps 18, 23      GEMM2 issuers (left / right k-steps)
 // (the epilogue is a long dependent instruction chain per tile -- a single warp per scheduler issues one
-// instruction every ~7 cycles -- so two groups work on alternate tiles.)
+// instruction every ~7-10 cycles -- so three groups work on tiles li mod 3; GEMM1 has six accumulator buffers so
+// that its issuer runs ahead of them.)
+//
+// What bounds it (ncu, round 2, profiles/r2j_ncu_summary.md): the shared-memory data pipe.  Per 128-point tile
+// the CUDA cores move ~1400 wavefronts (gather landing 128, centre/split 128 + 256, permuting copy 128 + 272,
+// drain) and the tensor core reads ~1030 (GEMM1: 13 k-steps x (4 KB + 2 KB); GEMM2: 17 x (2 KB + 1 KB)):
+// lsu 54 % + tc 33 % of the pipe's peak.  Measured on the way and rejected: suspend-time hints and nanosleep
+// back-off in the waits of the non-critical warps (+2..+14 us), Philox on the gather warps (+15 us), three
+// tiles of gather in flight with a 5-slot ring (+9 us).
 #pragma once
 #include "kernels_stats_tc.cuh"
 
 #define SS_D 32
 #define SS_TILE 128
+#ifndef SS_RAW
 #define SS_RAW 5                         // ring of raw tiles: landing -> split -> permuting pass
-#define SS_PF 3                          // tiles of gather in flight
-#define SS_THREADS 768
+#endif
+#ifndef SS_PF
+#define SS_PF 2                          // tiles of gather in flight
+#endif
+#ifndef SS_NG
+#define SS_NG 3                          // GEMM1 epilogue groups (4 warps each), tile li -> group li % SS_NG
+#endif
+#ifndef SS_GPHILOX
+#define SS_GPHILOX 0                     // 1: the gather warps evaluate the sub-label uniforms (measured: slower)
+#endif
+#ifndef SS_FLUSH
+#define SS_FLUSH 8                       // tiles per GEMM2 flush group (TMEM accumulates 1024 points between drains)
+#endif
+#ifndef SS_NTB
+#define SS_NTB (SS_NG == 3 ? 6 : SS_NG)  // GEMM1 accumulator buffers (64 TMEM columns each), tile li -> buffer li % SS_NTB
+#endif
+#define SS_THREADS (768 + (SS_NG - 2) * 128)
 #define SS_GATHER 256                    // gather threads: warps 0-3 and 19-22, 4 rows each
 #define SS_PANEL 16384                   // one [128][32] Float32 panel
 #define SS_PROWS 136                     // rows of a permuted panel: both runs padded to a multiple of 8
 #define SS_PPANEL (SS_PROWS * 128)
 #define SS_WSLOT (8192 + 8192 + 2048)    // Wh | Wl | bias k-step operand
-#define SS_TMEM_COLS 256                 // GEMM1: 2 x 64 columns, GEMM2: 2 x 64 columns
+#define SS_TMEM_COLS (SS_NTB == 2 ? 256 : 512)  // GEMM1: SS_NTB x 64 columns, GEMM2: 2 x 64 columns
+#define SS_TMEM_G2 (SS_NTB * 64)         // first column of the GEMM2 accumulators
 #define SS_TLD 65
 #ifndef SS_DEBUG_SWITCHES
 #define SS_DEBUG_SWITCHES 0     // 1: the DPMM_SS_DEBUG ablation switches of tools/ss_debug_timing.py are live
@@ -79,7 +104,7 @@ struct SubStatsArgs {
 };
 
 struct SubStatsSmem {
-  size_t raw, split, perm, wslot, aaug, tbuf, tri, dest, cnt, kcnt, bnd, pre, bars, slot, total;
+  size_t raw, split, perm, wslot, aaug, tbuf, tri, ubuf, dest, cnt, kcnt, bnd, pre, bars, slot, total;
   __host__ __device__ explicit SubStatsSmem(int K) {
     size_t o = 0;
     raw = o;    o += (size_t)SS_RAW * SS_PANEL;
@@ -90,13 +115,14 @@ struct SubStatsSmem {
     tbuf = o;   o += 64 * SS_TLD * 4;
     tri = o;    o += 528 * 2;
     o = (o + 15) & ~(size_t)15;
-    dest = o;   o += 2 * SS_TILE;
-    cnt = o;    o += 2 * 4 * 4;
+    ubuf = o;   o += SS_GPHILOX ? (size_t)SS_RAW * SS_TILE * 8 : 0;   // the sub-label uniforms of the tiles in the raw ring (f64)
+    dest = o;   o += SS_NG * SS_TILE;
+    cnt = o;    o += SS_NG * 4 * 4;
     kcnt = o;   o += 4 * 4;
     bnd = o;    o += (size_t)(K + 1) * 4;
     pre = o;    o += (size_t)(K + 1) * 4;
     o = (o + 15) & ~(size_t)15;
-    bars = o;   o += 32 * 8;
+    bars = o;   o += 40 * 8;
     slot = o;   o += 16;
     total = o;
   }
@@ -121,6 +147,33 @@ __device__ __forceinline__ void ss_wait(int dbg, uint64_t* bar, uint32_t parity)
   }
 }
 
+// Wait of a warp that is NOT on the critical path (gather, issuers, drain, staging): back off with nanosleep
+// between polls, so that its polling does not compete with the epilogue warps for issue slots and the
+// shared-memory pipe.
+#ifndef SS_SLEEP
+#define SS_SLEEP 0
+#endif
+__device__ __forceinline__ void ss_wait_lazy(uint64_t* bar, uint32_t parity, uint32_t ns) {
+#if SS_SLEEP
+  uint32_t done = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(tc::smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
+#else
+  tc::mbar_wait(bar, parity);
+#endif
+}
+
 __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const SubStatsArgs a) {
   extern __shared__ __align__(1024) uint8_t ss_smem[];
   const SubStatsSmem L(a.K);
@@ -132,6 +185,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
   float* T = reinterpret_cast<float*>(ss_smem + L.tbuf);
   uint16_t* tri = reinterpret_cast<uint16_t*>(ss_smem + L.tri);
   uint8_t* dest_s = ss_smem + L.dest;
+  double* ubuf = reinterpret_cast<double*>(ss_smem + L.ubuf);
   volatile int32_t* cnt_s = reinterpret_cast<int32_t*>(ss_smem + L.cnt);
   volatile int32_t* kcnt = reinterpret_cast<int32_t*>(ss_smem + L.kcnt);
   int32_t* B = reinterpret_cast<int32_t*>(ss_smem + L.bnd);
@@ -141,8 +195,8 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
   uint64_t* sfree = bars + 2;        // [2] l panel read by GEMM1
   uint64_t* landed = bars + 18;      // [5] raw tile in shared memory
   uint64_t* rfree = bars + 23;       // [5] ... consumed by the permuting pass
-  uint64_t* d1full = bars + 4;       // [2] GEMM1 accumulator complete
-  uint64_t* d1empty = bars + 6;      // [2] ... read by the epilogue
+  uint64_t* d1full = bars + 28;      // [SS_NTB] GEMM1 accumulator complete
+  uint64_t* d1empty = bars + 34;     // [SS_NTB] ... read by the epilogue
   uint64_t* permd = bars + 8;        // [2] permuted panels written
   uint64_t* pfree = bars + 10;       // [2] GEMM2 that read them retired
   uint64_t* d2full = bars + 12;      // [2] flush group complete
@@ -168,9 +222,11 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
     for (int e = tid; e < 2 * nkeys * SS_D; e += SS_THREADS)
       a.centers[e] = __ldg(a.cen + (size_t)(e >> 6) * SS_D + (e & 31));
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < SS_NTB; ++b) {
       tc::mbar_init(&d1full[b], 1);
       tc::mbar_init(&d1empty[b], 128);
+    }
+    for (int b = 0; b < 2; ++b) {
       tc::mbar_init(&permd[b], 128);
       tc::mbar_init(&pfree[b], 2);      // one commit per GEMM2 issuer
       tc::mbar_init(&d2full[b], 2);
@@ -240,6 +296,8 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           idx[j] = p < wl.end ? __ldg(a.perm + p) : -1;
         }
       };
+      // ... and the uniform of the sub-label draw of row r0 + 32 c (chunk lanes 0-3), so that the Philox rounds
+      // are off the epilogue warps' per-tile chain; the epilogue reads it after the tile's `landed` barrier
       auto issue = [&](int s) {
         uint8_t* dst = raw0 + (size_t)s * SS_PANEL + offr;
 #pragma unroll
@@ -247,13 +305,18 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           const bool ok = idx[j] >= 0;
           if (!(SS_DBG & 16)) cp_async16(dst + j * 4096, a.x + (size_t)(ok ? idx[j] : 0) * SS_D + 4 * c, ok ? 16 : 0);
         }
+        if (SS_GPHILOX && c < 4) {
+          const int ix = c == 0 ? idx[0] : (c == 1 ? idx[1] : (c == 2 ? idx[2] : idx[3]));
+          if (ix >= 0)
+            ubuf[s * SS_TILE + r0 + 32 * c] = dpmm_uniform(a.u_inj, ix, a.seed, DPMM_STREAM_SUBLABEL, a.call, (uint64_t)(a.goff + ix));
+        }
       };
 #pragma unroll
       for (int li = 0; li < SS_PF; ++li) {
         if (li < nt) {
           load_idx();
           issue(li);
-          stc_advance(wl, B);
+          stc_advance<SS_FLUSH>(wl, B);
         }
         cp_async_commit();
       }
@@ -279,10 +342,10 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           const int ln2 = li + SS_PF;
           if (ln2 < nt) {
             ss_wait(SS_DBG, &rfree[ln2 % SS_RAW], ((ln2 / SS_RAW) & 1) ^ 1);
-            stc_advance(wl, B);
+            stc_advance<SS_FLUSH>(wl, B);
           }
           cp_async_commit();
-          stc_advance(wc, B);
+          stc_advance<SS_FLUSH>(wc, B);
           continue;
         }
 #pragma unroll
@@ -298,7 +361,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           lo[j].z = v[j].z - tc::trunc_tf32(v[j].z); lo[j].w = v[j].w - tc::trunc_tf32(v[j].w);
         }
         tc::mbar_arrive(&landed[li % SS_RAW]);             // this thread's chunks of z are in shared memory
-        ss_wait(SS_DBG, &sfree[b], ((li >> 1) & 1) ^ 1);     // GEMM1 of tile li - 2 has read the l panel
+        ss_wait_lazy(&sfree[b], ((li >> 1) & 1) ^ 1, 32);     // GEMM1 of tile li - 2 has read the l panel
         uint8_t* lk = split0 + (size_t)b * SS_PANEL + offk;
 #pragma unroll
         for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(lk + j * 4096) = lo[j];
@@ -307,13 +370,13 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         // next gather: tile li + PF goes into the slot of tile li + PF - RAW once its permuting pass is done
         const int ln = li + SS_PF;
         if (ln < nt) {
-          ss_wait(SS_DBG, &rfree[ln % SS_RAW], ((ln / SS_RAW) & 1) ^ 1);
+          ss_wait_lazy(&rfree[ln % SS_RAW], ((ln / SS_RAW) & 1) ^ 1, 64);
           issue(ln % SS_RAW);
-          stc_advance(wl, B);
+          stc_advance<SS_FLUSH>(wl, B);
           if (ln + 1 < nt) load_idx();
         }
         cp_async_commit();
-        stc_advance(wc, B);
+        stc_advance<SS_FLUSH>(wc, B);
       }
     } else if (warp == 4) {
       // ======================= GEMM1 issuer =======================
@@ -340,10 +403,11 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           if (wm.key != prevkey) {
             prevkey = wm.key;
             ++kj;
-            ss_wait(SS_DBG, wfull, kj & 1);
+            ss_wait_lazy(wfull, kj & 1, 32);
           }
-          ss_wait(SS_DBG, &ready[b], (li >> 1) & 1);
-          ss_wait(SS_DBG, &d1empty[b], ((li >> 1) & 1) ^ 1);
+          const int tb = li % SS_NTB, tph = (li / SS_NTB) & 1;
+          ss_wait_lazy(&ready[b], (li >> 1) & 1, 32);
+          ss_wait_lazy(&d1empty[tb], tph ^ 1, 32);
           tc::tc_fence_after();
           uint64_t hd[4], ld[4];
 #pragma unroll
@@ -351,7 +415,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
             hd[ks] = raw_desc + (uint64_t)((li % SS_RAW) * (SS_PANEL >> 4) + ks * 2);   // z: h = its TF32 bits
             ld[ks] = l_desc + (uint64_t)(b * (SS_PANEL >> 4) + ks * 2);
           }
-          const uint32_t tmem_d = tmem_u + b * 64;
+          const uint32_t tmem_d = tmem_u + tb * 64;
           if (!(SS_DBG & 8)) {
           tc::umma_tf32_first_w(tmem_d, hd[0], whd[0], idesc1);
 #pragma unroll
@@ -363,9 +427,9 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           tc::umma_tf32_acc_w(tmem_d, aaug_desc, baug_desc, idesc1);   // Y -= b
           }
           tc::umma_commit_w(&sfree[b]);
-          tc::umma_commit_w(&d1full[b]);
+          tc::umma_commit_w(&d1full[tb]);
           if (wm.pos + SS_TILE >= wm.end) tc::umma_commit_w(wempty);   // last tile of the cluster
-          stc_advance(wm, B);
+          stc_advance<SS_FLUSH>(wm, B);
         }
       }
     } else if (warp == 18 || warp == 23) {
@@ -386,13 +450,13 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         int g2 = 0;
         for (int li = 0; li < nt; ++li) {
           const int b = li & 1;
-          const bool first = wm.gcount == 0, last = stc_is_last(wm);
-          ss_wait(SS_DBG, &permd[b], (li >> 1) & 1);
-          if (first) ss_wait(SS_DBG, &d2empty[g2 & 1], ((g2 >> 1) & 1) ^ 1);
+          const bool first = wm.gcount == 0, last = stc_is_last<SS_FLUSH>(wm);
+          ss_wait_lazy(&permd[b], (li >> 1) & 1, 32);
+          if (first) ss_wait_lazy(&d2empty[g2 & 1], ((g2 >> 1) & 1) ^ 1, 64);
           tc::tc_fence_after();
           const int nkl = __shfl_sync(0xffffffffu, kcnt[b * 2], 0), nkr = __shfl_sync(0xffffffffu, kcnt[b * 2 + 1], 0);
           const int k0 = right ? nkl : 0, nk = (SS_DBG & 4) ? 0 : (right ? nkr : nkl);
-          const uint32_t tm = tmem_u + 128 + (g2 & 1) * 64 + right * 32;
+          const uint32_t tm = tmem_u + SS_TMEM_G2 + (g2 & 1) * 64 + right * 32;
           uint64_t pd = (b ? pd1 : pd0) + (uint64_t)(k0 * 64);
           int ks = 0;
           if (first && nk > 0) {
@@ -406,15 +470,15 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
             tc::umma_commit_w(&d2full[g2 & 1]);
             ++g2;
           }
-          stc_advance(wm, B);
+          stc_advance<SS_FLUSH>(wm, B);
         }
       }
-    } else if (warp < 13) {
+    } else if (warp < 13 || warp >= 24) {
       // ======================= GEMM1 epilogue: draw, permute, sum y =======================
-      const int g = (warp - 5) >> 2;                  // group g owns the tiles li = g (mod 2): buffers [g]
+      const int g = warp >= 24 ? 2 + ((warp - 24) >> 2) : (warp - 5) >> 2;   // group g owns the tiles li = g (mod SS_NG)
       const int sub = warp & 3;                       // TMEM sub-partition of this warp
       const int row = (sub << 5) | lane;              // TMEM lane == row of the tile
-      const int gt = (tid - 160) & 127;               // 0..127 within the group
+      const int gt = warp >= 24 ? (tid - 768) & 127 : (tid - 160) & 127;   // 0..127 within the group
       uint8_t* const dest_g = dest_s + g * SS_TILE;
       volatile int32_t* const cnt_g = cnt_s + g * 4;
       int nacc = 0;
@@ -427,11 +491,11 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       int ckey = -1;
       float cl = 0.f, cr = 0.f, lwl = 0.f, lwr = 0.f;
       for (int li = 0; li < nt; ++li) {
-        if ((li & 1) != g) {
-          stc_advance(we, B);
+        if (li % SS_NG != g) {
+          stc_advance<SS_FLUSH>(we, B);
           continue;
         }
-        const int b = g;
+        const int b = li & 1;                          // permuted-panel slot
         const int key = we.key;
         const int npts = min(SS_TILE, we.end - we.pos);
         const bool valid = row < npts;
@@ -444,11 +508,12 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
 
         }
         double u = 0.0;
-        if (valid && !(SS_DBG & 1)) u = dpmm_uniform(a.u_inj, idx, a.seed, DPMM_STREAM_SUBLABEL, a.call, (uint64_t)(a.goff + idx));
-        ss_wait(SS_DBG, &d1full[b], (li >> 1) & 1);
+        if (!SS_GPHILOX && valid) u = dpmm_uniform(a.u_inj, idx, a.seed, DPMM_STREAM_SUBLABEL, a.call, (uint64_t)(a.goff + idx));
+        const int tb = li % SS_NTB;
+        ss_wait(SS_DBG, &d1full[tb], (li / SS_NTB) & 1);
         tc::tc_fence_after();
         uint32_t v0[32], v1[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + b * 64;
+        const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + tb * 64;
         float ql = 1.f, qr = 2.f;
         if (!(SS_DBG & 128)) {
         tc::tmem_ld32(taddr, v0);
@@ -457,8 +522,12 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         ql = gauss_tc_screen_q(v0), qr = gauss_tc_screen_q(v1);
         }
         tc::tc_fence_before();
-        tc::mbar_arrive(&d1empty[b]);
+        tc::mbar_arrive(&d1empty[tb]);
         int side = 2;
+        if (SS_GPHILOX) {
+          ss_wait(SS_DBG, &landed[li % SS_RAW], (li / SS_RAW) & 1);   // the uniforms of the tile (gather warps)
+          if (valid) u = ubuf[(li % SS_RAW) * SS_TILE + row];
+        }
         if (valid) {
           const float rl = gauss_finish(cl, ql, lwl), rr = gauss_finish(cr, qr, lwr);
           if (a.dump != nullptr) {
@@ -469,13 +538,12 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           a.sub[idx] = (uint8_t)side;
         }
         if (SS_DBG & 1024) {
-          ss_wait(SS_DBG, &landed[li % SS_RAW], (li / SS_RAW) & 1);
           ss_wait(SS_DBG, &pfree[b], ((li >> 1) & 1) ^ 1);
           if (gt == 0) { kcnt[b * 2] = 8; kcnt[b * 2 + 1] = 8; }
           tc::fence_proxy_async();
           tc::mbar_arrive(&permd[b]);
           tc::mbar_arrive(&rfree[li % SS_RAW]);
-          stc_advance(we, B);
+          stc_advance<SS_FLUSH>(we, B);
           continue;
         }
         // ---- destination row of every point: left run first, right run from a multiple of 8 ----
@@ -494,10 +562,13 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           nr += cw >> 8;
         }
         const int nl8 = max(8, (nl + 7) & ~7), nr8 = max(8, (nr + 7) & ~7);
+        // rows beyond the end of the cluster hold exact zeros (zero-filled gather, not centred): they go to a
+        // zero pad row of a run, or to a row no k-step reads, so that the copy below needs no branch
+        const int dinv = nr8 > nr ? nl8 + nr8 - 1 : (nl8 > nl ? nl8 - 1 : nl8 + nr8);
         dest_g[row] = side == 0 ? (uint8_t)(offl + __popc(bl & lt_mask))
-                                : (side == 1 ? (uint8_t)(nl8 + offr_ + __popc(br & lt_mask)) : (uint8_t)255);
+                                : (side == 1 ? (uint8_t)(nl8 + offr_ + __popc(br & lt_mask)) : (uint8_t)dinv);
         if (gt == 0 && nl > 0) atomicAdd(a.lcount + key, nl);
-        ss_wait(SS_DBG, &landed[li % SS_RAW], (li / SS_RAW) & 1);   // z of the tile (gathered and centred by the gather warps)
+        if (!SS_GPHILOX) ss_wait(SS_DBG, &landed[li % SS_RAW], (li / SS_RAW) & 1);   // z of the tile (gathered and centred by the gather warps)
         ss_wait(SS_DBG, &pfree[b], ((li >> 1) & 1) ^ 1);    // the GEMM2 that read this slot two tiles ago
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         if (gt == 0) {
@@ -506,23 +577,30 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         }
         const uint8_t* rp = raw0 + (size_t)(li % SS_RAW) * SS_PANEL + offr;
         uint8_t* pp = perm0 + (size_t)b * 2 * SS_PPANEL;
+        // z = x - c (centred in place).  The h panel takes z itself: the tensor core reads its TF32 bits,
+        // h = trunc(z), the same split as GEMM1's; l = z - trunc(z) (|l| <= 2^-10 |z|, l l' is dropped).
+        // Loads first, in two batches of four rows: the copies are independent but alias in the compiler's eyes.
+        int dd[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int d = dest_g[r0 + 16 * j];
-          if (d != 255 && !(SS_DBG & 2)) {
-            const float4 y4 = *reinterpret_cast<const float4*>(rp + j * 2048);   // z = x - c (centred in place)
-            float4 h4, l4;
-            h4.x = tc::to_tf32(y4.x); h4.y = tc::to_tf32(y4.y); h4.z = tc::to_tf32(y4.z); h4.w = tc::to_tf32(y4.w);
-            l4.x = y4.x - h4.x; l4.y = y4.y - h4.y; l4.z = y4.z - h4.z; l4.w = y4.w - h4.w;
+        for (int j = 0; j < 8; ++j) dd[j] = dest_g[r0 + 16 * j];
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          float4 y[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) y[j] = *reinterpret_cast<const float4*>(rp + (4 * hb + j) * 2048);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int d = dd[4 * hb + j];
+            const float4 y4 = y[j];
+            float4 l4;
+            l4.x = y4.x - tc::trunc_tf32(y4.x); l4.y = y4.y - tc::trunc_tf32(y4.y);
+            l4.z = y4.z - tc::trunc_tf32(y4.z); l4.w = y4.w - tc::trunc_tf32(y4.w);
             uint8_t* q = pp + d * 128 + (((((c >> 1) ^ (d & 3)) << 1) | (c & 1)) << 4);
-            *reinterpret_cast<float4*>(q) = h4;
+            *reinterpret_cast<float4*>(q) = y4;
             *reinterpret_cast<float4*>(q + SS_PPANEL) = l4;
-            const float yx = y4.x, yy = y4.y, yz = y4.z, yw = y4.w;
-            if (d < nl8) {
-              sxl[0] += yx; sxl[1] += yy; sxl[2] += yz; sxl[3] += yw;
-            } else {
-              sxr[0] += yx; sxr[1] += yy; sxr[2] += yz; sxr[3] += yw;
-            }
+            const bool left = d < nl8;
+            sxl[0] += left ? y4.x : 0.f; sxl[1] += left ? y4.y : 0.f; sxl[2] += left ? y4.z : 0.f; sxl[3] += left ? y4.w : 0.f;
+            sxr[0] += left ? 0.f : y4.x; sxr[1] += left ? 0.f : y4.y; sxr[2] += left ? 0.f : y4.z; sxr[3] += left ? 0.f : y4.w;
           }
         }
         {   // zero rows that pad the two runs to a multiple of 8 (at most 8 + 8): thread = (row, chunk)
@@ -539,13 +617,13 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
         tc::fence_proxy_async();
         tc::mbar_arrive(&permd[b]);
         tc::mbar_arrive(&rfree[li % SS_RAW]);
-        // sum y -> Float64 accumulators when this group's next tile (li + 2) belongs to another cluster,
+        // sum y -> Float64 accumulators when this group's next tile (li + SS_NG) belongs to another cluster,
         // after 4 own tiles, or at the end of the range
-        bool flush = we.tleft <= 2 || ++nacc == 4;
+        bool flush = we.tleft <= SS_NG || ++nacc == 4;
         if (!flush) {
           StcWalk w2 = we;
-          stc_advance(w2, B);
-          stc_advance(w2, B);
+#pragma unroll
+          for (int q = 0; q < SS_NG; ++q) stc_advance<SS_FLUSH>(w2, B);
           flush = w2.key != key;
         }
         if (flush) {
@@ -569,7 +647,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
 #pragma unroll
           for (int q = 0; q < 4; ++q) sxl[q] = sxr[q] = 0.f;
         }
-        stc_advance(we, B);
+        stc_advance<SS_FLUSH>(we, B);
       }
     } else if (warp < 17) {
       // ======================= GEMM2 accumulator drain =======================
@@ -579,13 +657,13 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       stc_walk_init(wd, B, P, nkeys, t0, t1);
       int g2 = 0;
       for (int li = 0; li < nt; ++li) {
-        if (stc_is_last(wd)) {
+        if (stc_is_last<SS_FLUSH>(wd)) {
           const int buf = g2 & 1;
-          ss_wait(SS_DBG, &d2full[buf], (g2 >> 1) & 1);
+          ss_wait_lazy(&d2full[buf], (g2 >> 1) & 1, 200);
           ++g2;
           tc::tc_fence_after();
           uint32_t v0[32], v1[32];
-          const uint32_t taddr = tmem_base + 128 + buf * 64 + ((uint32_t)(sub * 32) << 16);
+          const uint32_t taddr = tmem_base + SS_TMEM_G2 + buf * 64 + ((uint32_t)(sub * 32) << 16);
           if (!(SS_DBG & 256)) {
           tc::tmem_ld32(taddr, v0);
           tc::tmem_ld32(taddr + 32, v1);
@@ -593,7 +671,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           }
           tc::tc_fence_before();
           tc::mbar_arrive(&d2empty[buf]);
-          if (SS_DBG & 256) { stc_advance(wd, B); continue; }
+          if (SS_DBG & 256) { stc_advance<SS_FLUSH>(wd, B); continue; }
           // M = 64: accumulator row m lives in lane (m % 16) of sub-partition m / 16
           // (M = 128, experiment switch: row m lives in TMEM lane m, rows 0-63 = sub-partitions 0 and 1)
           const bool m64 = (SS_DBG & 2048) == 0;
@@ -605,7 +683,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
               trow[32 + j] = __uint_as_float(v1[j]);
             }
           }
-          asm volatile("bar.sync 3, 128;" ::: "memory");
+          asm volatile("bar.sync 6, 128;" ::: "memory");
           for (int e = gt; e < 2 * 528; e += 128) {
             const int sd = e >= 528 ? 1 : 0;
             const int ij = tri[e - sd * 528], i = ij >> 8, j = ij & 255;
@@ -613,11 +691,11 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
             const float sv = (T[i * SS_TLD + co + j] + T[(32 + i) * SS_TLD + co + j]) + T[(32 + j) * SS_TLD + co + i];
             if (sv != 0.f && !(SS_DBG & 32)) atomicAdd(a.acc + (size_t)(2 * wd.key + sd) * a.rec + 1 + SS_D + i * SS_D + j, (double)sv);
           }
-          asm volatile("bar.sync 3, 128;" ::: "memory");
+          asm volatile("bar.sync 6, 128;" ::: "memory");
         }
-        stc_advance(wd, B);
+        stc_advance<SS_FLUSH>(wd, B);
       }
-    } else {
+    } else if (warp == 17) {
       // ======================= factor staging (warp 17) =======================
       StcWalk wp;
       stc_walk_init(wp, B, P, nkeys, t0, t1);
@@ -628,7 +706,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
       for (int li = 0; li < nt; ++li) {
         if (wp.key != prevkey) {
           prevkey = wp.key;
-          ss_wait(SS_DBG, wempty, (kj & 1) ^ 1);   // every GEMM1 of the previous cluster has retired
+          ss_wait_lazy(wempty, (kj & 1) ^ 1, 200);   // every GEMM1 of the previous cluster has retired
           const float4* src = reinterpret_cast<const float4*>(a.w + (size_t)wp.key * 2 * SS_D * SS_D);
           for (int e = lane; e < 512; e += 32) {
             const int r = e >> 3, cc = e & 7;   // row (side, i), 16-byte chunk
@@ -651,7 +729,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           tc::mbar_arrive(wfull);
           ++kj;
         }
-        stc_advance(wp, B);
+        stc_advance<SS_FLUSH>(wp, B);
       }
     }
   }
