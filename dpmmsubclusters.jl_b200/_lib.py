@@ -51,6 +51,9 @@ SIGNATURES = {
     "dpmm_apply_split": (C.c_int, [_p, _i64p, _i64p, _i32]),
     "dpmm_apply_merge": (C.c_int, [_p, _i64p, _i64p, _i32]),
     "dpmm_remove_empty": (C.c_int, [_p, _i64p, _i32]),
+    "dpmm_smart_project": (C.c_int, [_p, _i64, _f64p, _f64p, _f64p, _i64p]),
+    "dpmm_smart_kmeans_iter": (C.c_int, [_p, C.c_double, C.c_double, _f64p]),
+    "dpmm_smart_set_sublabels": (C.c_int, [_p, _i64]),
     "dpmm_nccl_unique_id": (C.c_int, [_p]),
     "dpmm_comm_init": (C.c_int, [_p, _p, _i32, _i32]),
     "dpmm_set_uniforms": (C.c_int, [_p, _f64p, _f64p, _u8p]),

@@ -14,6 +14,7 @@
 #include <vector>
 
 struct StatsItem;
+struct SmartState;   // smart.cu
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -179,6 +180,8 @@ struct dpmm_ctx {
   uint32_t pcall = 0;
   int Kcap_tab = 0;
 
+  SmartState* smart = nullptr;   // buffers of the smart-split worker functions (smart.cu)
+
   NcclApi nccl;
   void* comm = nullptr;
   int world = 1, rank = 0;
@@ -190,6 +193,9 @@ struct dpmm_ctx {
   size_t ipc_cap = 0;        // doubles per buffer
   uint32_t ipc_epoch = 0;
 };
+
+void dpmm_internal_smart_free(dpmm_ctx* ctx);      // smart.cu
+int dpmm_internal_ensure_sorted(dpmm_ctx* ctx);    // dpmm_b200.cu
 
 inline thread_local std::string g_err;
 

@@ -347,6 +347,7 @@ extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
   for (int p = 0; p < IPC_MAX_WORLD; ++p)
     if (ctx->ipc_peer[p]) cudaIpcCloseMemHandle(ctx->ipc_peer[p]);
   if (ctx->ipc_local) cudaFree(ctx->ipc_local);
+  dpmm_internal_smart_free(ctx);
   if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
   for (auto& t : ctx->tev) {
     cudaEventDestroy(t.a);
@@ -1055,6 +1056,8 @@ static int ensure_sorted(dpmm_ctx* ctx) {
   ctx->cursors_fresh = true;
   return 0;
 }
+
+int dpmm_internal_ensure_sorted(dpmm_ctx* ctx) { return ensure_sorted(ctx); }
 
 // sub-label draw (sample=true) or partition only (sample=false); both leave perm2 partitioned.
 static int run_sublabels(dpmm_ctx* ctx, bool sample, float* dump) {

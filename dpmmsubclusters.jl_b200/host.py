@@ -86,6 +86,15 @@ class Settings:
     outlier_mod: float = 0.0
     use_verbose: bool = False
     ground_truth: object = None
+    use_smart_splits: bool = False
+    max_split_iter: int = 20             # global_params.jl:15
+    # checkpoints (global_params.jl:34-40; dp-parallel-sampling.jl:395-399)
+    should_save_model: bool = False
+    model_save_interval: int = 1000
+    save_path: str = ""
+    save_file_prefix: str = "checkpoint_"
+    data_path: str = ""
+    data_prefix: str = ""
 
 
 # ---------------------------------------------------------------- shared_actions.jl --------------
@@ -269,6 +278,9 @@ def check_and_split(group, final, cfg, rng):
         new_index += 1
     if indices:
         group.sweep.apply_split(indices, new_indices)      # split_cluster_local_worker! :265-278
+        if cfg.use_smart_splits:                           # :374-378
+            for i in indices + new_indices:
+                smart_cluster_init(group, i, cfg)
     return indices + new_indices
 
 
@@ -307,6 +319,43 @@ def remove_empty_clusters(group, cfg):
             new_vec.append(cluster)
     group.sweep.remove_empty(pts_count)                    # remove_empty_clusters_worker! :446-455
     group.local_clusters = new_vec
+
+
+def smart_split_direction(N, sum_x, S):
+    """The master-side linear algebra of smart_cluster_init! (:557-569): M = S/N - mu mu', eigen(M), and -- as the
+    reference writes it -- ROW `mxindx` of the eigenvector matrix (`vecs[mxindx,:]`), not the eigenvector itself."""
+    mu = np.asarray(sum_x, np.float64) / N
+    M = np.asarray(S, np.float64) / N - np.outer(mu, mu)
+    vals, vecs = np.linalg.eigh(M)
+    return vecs[int(np.argmax(vals)), :].copy(), mu
+
+
+def smart_kmeans(sweep, cluster_num, v1, mu, max_split_iter):
+    """The worker-driving part of smart_cluster_init! (:570-623): projection + percentiles, the distributed 1-D
+    2-means loop, and the sub-label write-back.  Shared by the host and the device parameter paths."""
+    min_mean, max_mean, count = sweep.smart_project(cluster_num, v1, mu)
+    if count == 0 or np.isnan(min_mean):                       # `if length(min_pts) == 0 return`
+        return
+    it, converged = 0, False
+    while it < max_split_iter and not converged:
+        s1, c1, s2, c2 = sweep.smart_kmeans_iter(min_mean, max_mean)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            new_min, new_max = np.float64(s1) / np.float64(c1), np.float64(s2) / np.float64(c2)
+        if new_min == min_mean and new_max == max_mean:
+            converged = True
+        else:
+            min_mean, max_mean = float(new_min), float(new_max)
+        it += 1
+    sweep.smart_set_sublabels(cluster_num)
+
+
+def smart_cluster_init(group, cluster_num, cfg):
+    """smart_cluster_init! :555-623."""
+    ss = group.local_clusters[cluster_num - 1].cluster_params.cluster_params.suff_statistics
+    if ss.N == 0:
+        return
+    v1, mu = smart_split_direction(ss.N, ss.points_sum, ss.S)
+    smart_kmeans(group.sweep, cluster_num, v1, mu, cfg.max_split_iter)
 
 
 def group_step(group, no_more_splits, final, first, cfg, rng):
@@ -374,6 +423,10 @@ def init_first_clusters(dp_model, cfg, rng):
     for _ in range(cfg.initial_clusters):
         g.local_clusters.append(create_first_local_cluster(g, cfg, rng))
     update_suff_stats_posterior(g)
+    if cfg.use_smart_splits:                               # :70-75
+        for i in range(1, len(g.local_clusters) + 1):
+            smart_cluster_init(g, i, cfg)
+        update_suff_stats_posterior(g)
     sample_clusters(g, False, cfg, rng)
     g.weights = np.full(len(g.local_clusters), 1.0 / len(g.local_clusters), F32) if len(g.local_clusters) > 1 else np.ones(1, F32)
     broadcast_cluster_params(g)
@@ -442,13 +495,16 @@ def dp_parallel(all_data, local_hyper_params, α_param, iters=100, init_clusters
     counterpart: they select the device / inject a test double / attach the multi-GPU communicator / choose
     where the parameter step runs (default: on the device for the NIW prior; False = the Python
     mirror of the reference's master functions below)."""
-    if outlier_weight or smart_splits or save_model:
-        raise NotImplementedError("outlier component, smart splits and checkpoints are out of scope (DESIGN.md 6)")
+    if outlier_weight:
+        raise NotImplementedError("the outlier component is out of scope (DESIGN.md 6)")
+    if smart_splits and not isinstance(local_hyper_params, P.niw_hyperparams):
+        raise ValueError("smart splits are Gaussian only (dp-parallel-sampling.jl:111)")
     if (comm is not None or shard is not None) and seed is None:
         # every rank must draw the same parameters and take the same split / merge decisions
         raise ValueError("multi-GPU runs (comm / shard) need an explicit seed shared by all ranks")
     cfg = Settings(iterations=int(iters), initial_clusters=int(init_clusters), burnout_period=int(burnout),
-                   max_num_of_clusters=max_clusters, use_verbose=bool(verbose), ground_truth=gt)
+                   max_num_of_clusters=max_clusters, use_verbose=bool(verbose), ground_truth=gt,
+                   use_smart_splits=bool(smart_splits))
     rng = np.random.default_rng(seed)
     dp_model = init_model_from_data(all_data, local_hyper_params, α_param, cfg, seed,
                                     sweep_factory or _gpu_factory(device), shard)

@@ -103,6 +103,8 @@ def group_step_device(sw, st, α, no_more_splits, final, cfg, rng, keep_params=F
             st.hist[both] = -np.inf                       # create_splittable_from_params: fresh window, not splittable
             st.splittable[both] = False
             sw.apply_split(split + 1, new + 1)
+            if cfg.use_smart_splits:                      # check_and_split! :374-378
+                smart_init_device(sw, both + 1, cfg)
             c, l, _ = sw.posterior_step(both + 1)
             _update(st, both, c, l)
         # check_and_merge!: pairs i < j in order, both splittable and non-empty
@@ -153,6 +155,19 @@ def group_step_device(sw, st, α, no_more_splits, final, cfg, rng, keep_params=F
         st.keep(mask)
 
 
+def smart_init_device(sw, clusters, cfg):
+    """smart_cluster_init! (:555-623) for the listed clusters (1-based): the cluster statistics come back through
+    dpmm_suff_stats, the D x D eigen-decomposition stays on the host, the rest is the three worker calls."""
+    from .host import smart_split_direction, smart_kmeans
+    clusters = [int(c) for c in clusters]
+    counts, sum_x, sum_xx = sw.suff_stats(clusters)
+    for a, c in enumerate(clusters):
+        if counts[a, 0] == 0:
+            continue
+        v1, mu = smart_split_direction(float(counts[a, 0]), sum_x[a, 0], sum_xx[a, 0])
+        smart_kmeans(sw, c, v1, mu, cfg.max_split_iter)
+
+
 def run_model_device(dp_model, cfg, rng, normalized_mutual_info):
     """init_first_clusters! (:62-78) + run_model (:336-404) with the parameter step on the device."""
     g = dp_model.group
@@ -164,6 +179,9 @@ def run_model_device(dp_model, cfg, rng, normalized_mutual_info):
     for _ in range(cfg.initial_clusters):
         sw.randomize_sublabels(None)                       # split_first_cluster_worker! per first cluster
     counts, logml, _ = sw.posterior_step(None)
+    if cfg.use_smart_splits:                               # init_first_clusters! :70-75
+        smart_init_device(sw, np.arange(1, st.K + 1), cfg)
+        counts, logml, _ = sw.posterior_step(None)
     st.N[:], st.logml[:] = counts[:st.K], logml[:st.K]
     history_step(st, cfg)                                  # sample_clusters!(group, false) of init_first_clusters!
     sw.sample_params(st.K, unit_weights=True)

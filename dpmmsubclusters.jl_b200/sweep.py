@@ -223,6 +223,27 @@ class GpuSweep:
                                            _ptr(df, C.c_float), _ptr(labels, C.c_int64), _ptr(probs, C.c_float)))
         return labels, probs
 
+    # ---- smart splits (smart_cluster_init! local_clusters_actions.jl:555-623) ----
+    def smart_project(self, cluster, v, mu):
+        """tranform_points_worker! on every shard + the master's min / max: returns (lo, hi, count)."""
+        v = np.ascontiguousarray(v, np.float64); mu = np.ascontiguousarray(mu, np.float64)
+        assert v.shape == (self.D,) and mu.shape == (self.D,)
+        lohi = np.empty(2, np.float64)
+        cnt = np.zeros(1, np.int64)
+        self._ck(self.lib.dpmm_smart_project(self.h, int(cluster), _ptr(v, C.c_double), _ptr(mu, C.c_double),
+                                             _ptr(lohi, C.c_double), _ptr(cnt, C.c_int64)))
+        return float(lohi[0]), float(lohi[1]), int(cnt[0])
+
+    def smart_kmeans_iter(self, min_mean, max_mean):
+        """kmeans_iter_worker! on every shard + the master's sums: returns (sum_1, count_1, sum_2, count_2)."""
+        out = np.empty(4, np.float64)
+        self._ck(self.lib.dpmm_smart_kmeans_iter(self.h, float(min_mean), float(max_mean), _ptr(out, C.c_double)))
+        return tuple(float(o) for o in out)
+
+    def smart_set_sublabels(self, cluster):
+        """set_smart_labels_in_worker!."""
+        self._ck(self.lib.dpmm_smart_set_sublabels(self.h, int(cluster)))
+
     # ---- relabel ----
     def apply_split(self, indices, new_indices):
         a, b = _i64(indices), _i64(new_indices)

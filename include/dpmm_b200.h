@@ -177,6 +177,21 @@ int dpmm_apply_merge(dpmm_ctx* ctx, const int64_t* indices, const int64_t* new_i
 /* remove_empty_clusters_worker! (:446-455); pts_count[k] as the host holds it. */
 int dpmm_remove_empty(dpmm_ctx* ctx, const int64_t* pts_count, int32_t k);
 
+/* ---- smart splits (smart_cluster_init! src/local_clusters_actions.jl:555-623) ---- */
+
+/* tranform_points_worker! (:641-652) for every shard + the master's reduction (:578-589): projects the points whose
+ * label is `cluster` (1-based) onto v, t = v'(x - mu) in Float64 (v, mu: double [D]), keeps t on the device and
+ * returns lo_hi[0] = the minimum over shards of percentile(t, 0.10), lo_hi[1] = the maximum over shards of
+ * percentile(t, 0.90) (StatsBase semantics: the p/100 quantile; shards with fewer than 2 such points do not take
+ * part; NaN when none does) and *count = the number of such points over all shards. */
+int dpmm_smart_project(dpmm_ctx* ctx, int64_t cluster, const double* v, const double* mu, double* lo_hi,
+                       int64_t* count);
+/* kmeans_iter_worker! (:633-639) + the master's sums (:601-612): assigns every projected point to the nearer of
+ * (min_mean, max_mean) (ties -> max_mean) and returns out4 = {sum_1, count_1, sum_2, count_2} over all shards. */
+int dpmm_smart_kmeans_iter(dpmm_ctx* ctx, double min_mean, double max_mean, double* out4);
+/* set_smart_labels_in_worker! (:627-631): sub-labels of the projected cluster <- the last assignment. */
+int dpmm_smart_set_sublabels(dpmm_ctx* ctx, int64_t cluster);
+
 /* ---- multi-GPU (one process per GPU) --------------------------------------------------------- */
 
 /* 128-byte ncclUniqueId, created on rank 0 and shipped to the other ranks by the host's own means. */

@@ -28,6 +28,10 @@ g.sample_labels(False)
 g.sample_sublabels()
 counts, sx, sxx = g.suff_stats()
 lab, sub = g.get_labels(), g.get_sublabels()
+# smart splits across shards (dpmm_smart_*): percentiles reduced with min / max, per-side sums summed over ranks
+vdir = np.ones(32) / np.sqrt(32.0)
+sm_lo, sm_hi, sm_cnt = g.smart_project(1, vdir, np.zeros(32))
+sm_sums = g.smart_kmeans_iter(sm_lo, sm_hi)
 gathered = [None] * world
 dist.all_gather_object(gathered, (lo, hi, lab, sub))
 if rank == 0:
@@ -45,6 +49,16 @@ if rank == 0:
     # boundaries depend on the sharding: agreement is to Float32 rounding, not bit-exact
     np.testing.assert_allclose(sx, rsx, rtol=1e-5, atol=1e-3)
     np.testing.assert_allclose(sxx, rsxx, rtol=1e-5, atol=1e-5 * np.abs(rsxx).max())
+    from oracle import dpmm_oracle as O
+    sel = full_lab == 1
+    t = vdir @ case["x"][:, sel].astype(np.float64)
+    assert sm_cnt == int(sel.sum())
+    shard_t = [vdir @ case["x"][:, a:b][:, full_lab[a:b] == 1].astype(np.float64) for a, b, *_ in sorted(gathered)]
+    want_lo = min(O.julia_percentile(s_, 0.10) for s_ in shard_t if s_.size > 1)
+    want_hi = max(O.julia_percentile(s_, 0.90) for s_ in shard_t if s_.size > 1)
+    assert abs(sm_lo - want_lo) < 1e-9 and abs(sm_hi - want_hi) < 1e-9
+    left = np.abs(t - sm_lo) < np.abs(t - sm_hi)
+    np.testing.assert_allclose(sm_sums, [t[left].sum(), left.sum(), t[~left].sum(), (~left).sum()], rtol=1e-10)
     print("MGPU_OK", counts[:, 0].sum(), flush=True)
 g.close()
 dist.barrier()

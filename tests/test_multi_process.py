@@ -36,6 +36,24 @@ class AllReduceSweep(O.OracleSweep):
         return c2, sx2, sxx2
 
 
+    # the master's reductions of smart_cluster_init! (local_clusters_actions.jl:578-612), as dpmm_smart_* do them
+    def smart_project(self, cluster, v, mu):
+        lo, hi, cnt = super().smart_project(cluster, v, mu)
+        inf = float("inf")
+        t = torch.tensor([-lo if cnt > 1 else -inf, hi if cnt > 1 else -inf], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = torch.tensor([float(cnt)], dtype=torch.float64)
+        dist.all_reduce(c)
+        if t[1].item() == -inf:
+            return float("nan"), float("nan"), int(c.item())
+        return -t[0].item(), t[1].item(), int(c.item())
+
+    def smart_kmeans_iter(self, min_mean, max_mean):
+        t = torch.tensor(super().smart_kmeans_iter(min_mean, max_mean), dtype=torch.float64)
+        dist.all_reduce(t)
+        return tuple(t.tolist())
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -62,7 +80,9 @@ def _worker(rank, world, port, q):
         def factory(x, kind, seed, goff):
             return AllReduceSweep(x, kind, seed=seed, global_offset=goff)
         out = H.fit(case["x"][:, lo:hi], 10.0, iters=30, seed=5, burnout=5, sweep_factory=factory, shard=(lo, n))
-        q.put((rank, lo, hi, sw.get_labels(), sw.get_sublabels(), stats, out[0], len(out[1]), out[6]))
+        smart = H.fit(case["x"][:, lo:hi], 10.0, iters=30, seed=5, burnout=5, sweep_factory=factory, shard=(lo, n),
+                      smart_splits=True)
+        q.put((rank, lo, hi, sw.get_labels(), sw.get_sublabels(), stats, out[0], len(out[1]), out[6], smart[6]))
     finally:
         dist.destroy_process_group()
 
@@ -86,6 +106,7 @@ def test_two_process_sharded_sweep_and_fit():
     ref.sample_labels(False)
     ref.sample_sublabels()
     rc, rsx, rsxx = ref.suff_stats()
+    assert res[0][9] == res[1][9] and len(res[0][9]) == 30                  # smart splits: identical decisions on every rank
     for rank, lo, hi, lab, sub, stats, *_ in res:
         np.testing.assert_array_equal(lab, ref.get_labels()[lo:hi])        # (a) shard-invariant draws
         np.testing.assert_array_equal(sub, ref.get_sublabels()[lo:hi])
