@@ -9,4 +9,6 @@ from .priors import (niw_hyperparams, multinomial_hyper, niw_sufficient_statisti
                      multinomial_sufficient_statistics, mv_gaussian, multinomial_dist, calc_posterior,
                      sample_distribution, log_marginal_likelihood, aggregate_suff_stats)
 from .data_generators import generate_gaussian_data, generate_mnmm_data  # noqa: F401
-from .host import fit, dp_parallel, predict, calculate_posterior, get_labels_histogram  # noqa: F401
+from .host import (fit, dp_parallel, predict, calculate_posterior, get_labels_histogram,  # noqa: F401
+                   run_model_from_checkpoint)
+from .checkpoint import load_data, save_model, load_checkpoint  # noqa: F401

@@ -95,6 +95,7 @@ class Settings:
     save_file_prefix: str = "checkpoint_"
     data_path: str = ""
     data_prefix: str = ""
+    global_params: object = "none"       # what save_model records as `global_params` (the parameter file's content)
 
 
 # ---------------------------------------------------------------- shared_actions.jl --------------
@@ -436,6 +437,7 @@ def run_model(dp_model, first_iter, cfg, rng):
     """run_model :336-404."""
     iter_count, nmi_hist, ll_hist, k_hist = [], [], [], []
     g = dp_model.group
+    start_time = time.time()
     for i in range(first_iter, cfg.iterations + 1):
         final = i >= cfg.iterations - cfg.argmax_sample_stop
         no_more_splits = (i >= cfg.iterations - cfg.split_stop) or (len(g.local_clusters) >= cfg.max_num_of_clusters)
@@ -453,6 +455,9 @@ def run_model(dp_model, first_iter, cfg, rng):
                   f"NMI score: {nmi_hist[-1]} || Iter Time:{iter_count[-1]} || Total time:{sum(iter_count)}")
         else:
             ll_hist.append(1)
+        if i % cfg.model_save_interval == 0 and cfg.should_save_model:      # :395-399
+            from .checkpoint import save_model
+            save_model(dp_model, cfg.save_path, cfg.save_file_prefix, i, time.time() - start_time, cfg.global_params)
     return dp_model, iter_count, nmi_hist, ll_hist, k_hist
 
 
@@ -469,18 +474,34 @@ def _clusters_from_device(group, st, cfg):
     sw = group.sweep
     K = st.K
     counts, sum_x, sum_xx = sw.suff_stats(list(range(1, K + 1)))
-    mu, lfac, logdet, w, lr = st.params
+    params = getattr(st, "params", None)
+    if params is not None and params[0].shape[0] != K:
+        params = None                                     # K changed after the parameters were fetched (mid-run checkpoint)
+    if params is not None:
+        mu, lfac, logdet, w, lr = params
+    else:
+        # no sampled parameters at hand: the posterior's centre stands in.  group_step re-draws every
+        # distribution and weight before anything reads them (sample_clusters!, :659), so these never reach a sweep.
+        tot = max(float(counts[:, 0].sum()), 1.0)
+        w = counts[:, 0] / tot
+        lr = (counts[:, 1:3] + 0.5) / (counts[:, 1:3] + 0.5).sum(axis=1, keepdims=True)
     group.local_clusters = []
     for k in range(K):
         cps = []
         for s_ in range(3):
             ss = P.make_suff_stats(hyper, counts[k, s_], sum_x[k, s_], sum_xx[k, s_])
-            L = np.tril(lfac[k, s_])
-            inv = L @ L.T
-            with np.errstate(all="ignore"):
-                Sig = np.linalg.inv(inv) if np.isfinite(inv).all() else np.full_like(inv, np.nan)
-            dist = P.mv_gaussian(mu[k, s_].astype(F32), Sig.astype(F32), inv.astype(F32), float(logdet[k, s_]), L.T.copy())
-            cps.append(cluster_parameters(hyper, dist, ss, P.calc_posterior(hyper, ss)))
+            post = P.calc_posterior(hyper, ss)
+            if params is not None:
+                L = np.tril(lfac[k, s_])
+                inv = L @ L.T
+                with np.errstate(all="ignore"):
+                    Sig = np.linalg.inv(inv) if np.isfinite(inv).all() else np.full_like(inv, np.nan)
+                dist = P.mv_gaussian(mu[k, s_].astype(F32), Sig.astype(F32), inv.astype(F32), float(logdet[k, s_]), L.T.copy())
+            else:
+                inv = np.linalg.inv(post.ψ)
+                dist = P.mv_gaussian(post.m.astype(F32), post.ψ.astype(F32), inv.astype(F32),
+                                     float(np.linalg.slogdet(post.ψ)[1]), np.linalg.cholesky(inv).T)
+            cps.append(cluster_parameters(hyper, dist, ss, post))
         sp = splittable_cluster_params(cps[0], cps[1], cps[2], lr[k].astype(np.float64), bool(st.splittable[k]),
                                        st.hist[k].copy())
         group.local_clusters.append(local_cluster(sp, group.model_hyperparams.total_dim, int(counts[k, 0]),
@@ -488,15 +509,21 @@ def _clusters_from_device(group, st, cfg):
     group.weights = np.asarray(w, F32)
 
 
-def dp_parallel(all_data, local_hyper_params, α_param, iters=100, init_clusters=1, seed=None, verbose=True,
+def dp_parallel(all_data, local_hyper_params=None, α_param=None, iters=100, init_clusters=1, seed=None, verbose=True,
                 save_model=False, burnout=15, gt=None, max_clusters=np.inf, outlier_weight=0, outlier_params=None,
-                smart_splits=False, *, sweep_factory=None, shard=None, comm=None, device=0, device_params=None):
+                smart_splits=False, *, sweep_factory=None, shard=None, comm=None, device=0, device_params=None,
+                save_path=None, save_file_prefix="checkpoint_", model_save_interval=1000):
     """dp_parallel :121-157.  `sweep_factory`, `shard`, `comm`, `device`, `device_params` have no reference
     counterpart: they select the device / inject a test double / attach the multi-GPU communicator / choose
     where the parameter step runs (default: on the device for the NIW prior; False = the Python
     mirror of the reference's master functions below)."""
+    if isinstance(all_data, (str, os.PathLike)):
+        return dp_parallel_params_file(str(all_data), verbose=verbose, gt=gt, sweep_factory=sweep_factory, shard=shard,
+                                       comm=comm, device=device, device_params=device_params)
     if outlier_weight:
         raise NotImplementedError("the outlier component is out of scope (DESIGN.md 6)")
+    if save_model and save_path is None:
+        raise ValueError("save_model=True needs save_path (global_params.jl:37 in the reference)")
     if smart_splits and not isinstance(local_hyper_params, P.niw_hyperparams):
         raise ValueError("smart splits are Gaussian only (dp-parallel-sampling.jl:111)")
     if (comm is not None or shard is not None) and seed is None:
@@ -504,7 +531,18 @@ def dp_parallel(all_data, local_hyper_params, α_param, iters=100, init_clusters
         raise ValueError("multi-GPU runs (comm / shard) need an explicit seed shared by all ranks")
     cfg = Settings(iterations=int(iters), initial_clusters=int(init_clusters), burnout_period=int(burnout),
                    max_num_of_clusters=max_clusters, use_verbose=bool(verbose), ground_truth=gt,
-                   use_smart_splits=bool(smart_splits))
+                   use_smart_splits=bool(smart_splits), should_save_model=bool(save_model), save_path=save_path or "",
+                   save_file_prefix=save_file_prefix, model_save_interval=int(model_save_interval))
+    return _run_from_settings(all_data, local_hyper_params, α_param, cfg, seed, sweep_factory, shard, comm, device,
+                              device_params)
+
+
+def _run_from_settings(all_data, local_hyper_params, α_param, cfg, seed, sweep_factory, shard, comm, device, device_params,
+                       restored=None):
+    """init_model + init_first_clusters! + run_model for fresh runs; create_model_from_saved_data + run_model(iter + 1)
+    when `restored` = (pts_less_group dict, iter) of a checkpoint."""
+    if restored is not None and seed is not None:
+        seed = int(seed) + 1000003 * int(restored[1])     # a resumed run must not replay the random streams of iteration 1
     rng = np.random.default_rng(seed)
     dp_model = init_model_from_data(all_data, local_hyper_params, α_param, cfg, seed,
                                     sweep_factory or _gpu_factory(device), shard)
@@ -513,13 +551,73 @@ def dp_parallel(all_data, local_hyper_params, α_param, iters=100, init_clusters
         sw.comm_init(*comm)
     if device_params is None:
         device_params = os.environ.get("DPMM_DEVICE_PARAMS", "1") != "0"
+    first_iter = 1
+    if restored is not None:                               # create_model_from_saved_data, ds.jl:89-92; :437-439
+        grp, it = restored
+        sw.set_labels(grp["labels"])
+        sw.set_sublabels(grp["labels_subcluster"])
+        dp_model.group.local_clusters = grp["local_clusters"]
+        dp_model.group.weights = grp["weights"]
+        first_iter = it + 1
     if device_params and isinstance(local_hyper_params, P.niw_hyperparams) and hasattr(sw, "sample_params"):
         from . import host_device as HD
-        st, iter_count, nmi, ll, kh = HD.run_model_device(dp_model, cfg, rng, normalized_mutual_info)
+        st, iter_count, nmi, ll, kh = HD.run_model_device(dp_model, cfg, rng, normalized_mutual_info, first_iter=first_iter,
+                                                          resume=restored is not None)
         _clusters_from_device(dp_model.group, st, cfg)
         return dp_model, iter_count, nmi, ll, kh
-    init_first_clusters(dp_model, cfg, rng)
-    return run_model(dp_model, 1, cfg, rng)
+    if restored is None:
+        init_first_clusters(dp_model, cfg, rng)
+    return run_model(dp_model, first_iter, cfg, rng)
+
+
+def _settings_from_params(gp, verbose, gt):
+    return Settings(iterations=int(gp["iterations"]), hard_clustering=bool(gp["hard_clustering"]),
+                    initial_clusters=int(gp["initial_clusters"]), argmax_sample_stop=int(gp["argmax_sample_stop"]),
+                    split_stop=int(gp["split_stop"]), burnout_period=int(gp["burnout_period"]),
+                    max_num_of_clusters=gp["max_clusters"], use_verbose=bool(verbose), ground_truth=gt,
+                    use_smart_splits=bool(gp["smart_splits"]), max_split_iter=int(gp["max_split_iter"]),
+                    should_save_model=bool(gp["enable_saving"]), model_save_interval=int(gp["model_save_interval"]),
+                    save_path=gp["save_path"], save_file_prefix=gp["save_file_prefix"], data_path=gp["data_path"],
+                    data_prefix=gp["data_prefix"])
+
+
+def dp_parallel_params_file(model_params, verbose=True, gt=None, **kw):
+    """dp_parallel(model_params::String; verbose, gt) :317-334 -- the advanced mode: every setting, the prior and the
+    data location come from a parameter file in the style of src/global_params.jl."""
+    from .checkpoint import read_params, load_data
+    gp = read_params(model_params)
+    cfg = _settings_from_params(gp, verbose, gt)
+    cfg.global_params = model_params
+    if gp["hyper_params"] is None:
+        raise ValueError("the parameter file must define hyper_params")
+    data = np.asarray(load_data(cfg.data_path, prefix=cfg.data_prefix), F32)      # init_model :24-25
+    return _run_from_settings(data, gp["hyper_params"], gp["α"], cfg, gp["random_seed"], kw.get("sweep_factory"),
+                              kw.get("shard"), kw.get("comm"), kw.get("device", 0), kw.get("device_params"))
+
+
+def run_model_from_checkpoint(filename, verbose=True, gt=None, data=None, **kw):
+    """run_model_from_checkpoint :428-449: reload the group, re-read the parameter file recorded in the checkpoint and
+    the data it points to (`data=` overrides), restore labels / sub-labels on the device, and continue at iter + 1."""
+    from .checkpoint import load_checkpoint, read_params, load_data
+    grp, mh, it, total_time, gparams = load_checkpoint(filename)
+    params_file = gparams.get("model_params") if isinstance(gparams, dict) else None
+    if params_file and os.path.exists(params_file):
+        gp = read_params(params_file)                       # `include(global_params)`, :433
+        cfg = _settings_from_params(gp, verbose, gt)
+        cfg.global_params = params_file
+        seed = gp["random_seed"]
+    else:
+        cfg = Settings(use_verbose=bool(verbose), ground_truth=gt)
+        for k, v in (gparams or {}).items():
+            if hasattr(cfg, k) and v is not None:
+                setattr(cfg, k, v)
+        cfg.global_params = gparams
+        seed = (gparams or {}).get("random_seed")
+    if data is None:
+        data = load_data(cfg.data_path, prefix=cfg.data_prefix)                   # :435
+    data = np.asarray(data, F32)
+    return _run_from_settings(data, mh.distribution_hyper_params, mh.α, cfg, seed, kw.get("sweep_factory"), kw.get("shard"),
+                              kw.get("comm"), kw.get("device", 0), kw.get("device_params"), restored=(grp, it))
 
 
 def fit(all_data, *args, iters=100, init_clusters=1, seed=None, verbose=False, save_model=False, burnout=20,

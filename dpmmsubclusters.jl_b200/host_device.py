@@ -168,26 +168,39 @@ def smart_init_device(sw, clusters, cfg):
         smart_kmeans(sw, c, v1, mu, cfg.max_split_iter)
 
 
-def run_model_device(dp_model, cfg, rng, normalized_mutual_info):
-    """init_first_clusters! (:62-78) + run_model (:336-404) with the parameter step on the device."""
+def run_model_device(dp_model, cfg, rng, normalized_mutual_info, first_iter=1, resume=False):
+    """init_first_clusters! (:62-78) + run_model (:336-404) with the parameter step on the device.  resume=True: the
+    group was restored from a checkpoint (labels / sub-labels already on the device, local_clusters holding the
+    history windows); the statistics and posterior tables are rebuilt from the labels."""
     g = dp_model.group
     sw = g.sweep
     hyper = g.model_hyperparams.distribution_hyper_params
     α = g.model_hyperparams.α
     sw.set_hyper_niw(hyper.κ, hyper.m, hyper.ν, hyper.ψ, α)
-    st = DeviceState(cfg.initial_clusters, cfg.burnout_period + 5)
-    for _ in range(cfg.initial_clusters):
-        sw.randomize_sublabels(None)                       # split_first_cluster_worker! per first cluster
-    counts, logml, _ = sw.posterior_step(None)
-    if cfg.use_smart_splits:                               # init_first_clusters! :70-75
-        smart_init_device(sw, np.arange(1, st.K + 1), cfg)
+    if resume:
+        K = len(g.local_clusters)
+        st = DeviceState(K, cfg.burnout_period + 5)
+        for k, c in enumerate(g.local_clusters):
+            h = np.asarray(c.cluster_params.logsublikelihood_hist, np.float64)
+            st.hist[k, :min(h.size, st.window)] = h[:st.window]
+            st.splittable[k] = bool(c.cluster_params.splittable)
+        counts, logml, _ = sw.posterior_step(np.arange(1, K + 1))
+        st.N[:], st.logml[:] = counts[:K], logml[:K]
+    else:
+        st = DeviceState(cfg.initial_clusters, cfg.burnout_period + 5)
+        for _ in range(cfg.initial_clusters):
+            sw.randomize_sublabels(None)                       # split_first_cluster_worker! per first cluster
         counts, logml, _ = sw.posterior_step(None)
-    st.N[:], st.logml[:] = counts[:st.K], logml[:st.K]
-    history_step(st, cfg)                                  # sample_clusters!(group, false) of init_first_clusters!
-    sw.sample_params(st.K, unit_weights=True)
+        if cfg.use_smart_splits:                               # init_first_clusters! :70-75
+            smart_init_device(sw, np.arange(1, st.K + 1), cfg)
+            counts, logml, _ = sw.posterior_step(None)
+        st.N[:], st.logml[:] = counts[:st.K], logml[:st.K]
+        history_step(st, cfg)                                  # sample_clusters!(group, false) of init_first_clusters!
+        sw.sample_params(st.K, unit_weights=True)
     iter_count, nmi_hist, ll_hist, k_hist = [], [], [], []
     first = True
-    for i in range(1, cfg.iterations + 1):
+    start_time = time.time()
+    for i in range(first_iter, cfg.iterations + 1):
         final = i >= cfg.iterations - cfg.argmax_sample_stop
         no_more_splits = (i >= cfg.iterations - cfg.split_stop) or (st.K >= cfg.max_num_of_clusters)
         t0 = time.perf_counter()
@@ -210,4 +223,9 @@ def run_model_device(dp_model, cfg, rng, normalized_mutual_info):
                   f"NMI score: {nmi_hist[-1]} || Iter Time:{iter_count[-1]} || Total time:{sum(iter_count)}")
         else:
             ll_hist.append(1)
+        if i % cfg.model_save_interval == 0 and cfg.should_save_model:      # run_model :395-399
+            from .checkpoint import save_model
+            from .host import _clusters_from_device
+            _clusters_from_device(g, st, cfg)
+            save_model(dp_model, cfg.save_path, cfg.save_file_prefix, i, time.time() - start_time, cfg.global_params)
     return st, iter_count, nmi_hist, ll_hist, k_hist
