@@ -24,6 +24,7 @@
 #include "kernels_sort.cuh"
 #include "kernels_stats.cuh"
 #include "kernels_stats_tc.cuh"
+#include "kernels_stats_tc64.cuh"
 #include "kernels_substats_tc.cuh"
 
 #include "ctx.cuh"
@@ -1187,9 +1188,12 @@ static int stats_compute(dpmm_ctx* ctx, const int64_t* indices, int32_t n_indice
   // K5 on tcgen05: all clusters of a D = 32 NIW model (no work list: CTAs own ranges of the tile sequence)
   const bool stats_tc = !cached && ctx->prior == DPMM_PRIOR_NIW && D == STC_D && all && ctx->tc_ok &&
                         env_int("DPMM_STATS_TC", 1) != 0 && StatsTcSmem(K).total <= (size_t)ctx->smem_optin;
+  // ... and of a D = 64 model (kernels_stats_tc64.cuh)
+  const bool stats_tc64 = !cached && ctx->prior == DPMM_PRIOR_NIW && D == S64_D && all && env_int("DPMM_STATS_TC", 1) != 0 &&
+                          StatsTc64Smem(K).total <= (size_t)ctx->smem_optin;
   if (cached) {
     // nothing to accumulate
-  } else if (!stats_tc) {
+  } else if (!stats_tc && !stats_tc64) {
     KernelTimer kt(ctx, TK_STATS_AUX);
     stats_worklist_kernel<<<1, 256, (size_t)2 * K * 4, ctx->stream>>>(ctx->seg_off, ctx->lr_cursor,
                                                                       all ? nullptr : ctx->wanted, K, ctx->chunk,
@@ -1223,6 +1227,20 @@ static int stats_compute(dpmm_ctx* ctx, const int64_t* indices, int32_t n_indice
     KernelTimer kt(ctx, TK_STATS);
     niw_stats_tc_kernel<<<ctx->sm_count * occ, STC_THREADS, smem, ctx->stream>>>(ta);
     CK(cudaGetLastError());
+  } else if (stats_tc64) {
+    StatsTcArgs ta{};
+    ta.x = ctx->x; ta.perm2 = ctx->perm2; ta.seg_off = ctx->seg_off; ta.lr_cursor = ctx->lr_cursor; ta.K = K;
+    ta.acc = ctx->acc; ta.rec = rec; ta.centers = ctx->centers;
+    {
+      KernelTimer kt(ctx, TK_STATS_AUX);
+      stats_centers64_kernel<<<2 * K, 512, 0, ctx->stream>>>(ctx->x, ctx->perm2, ctx->seg_off, ctx->lr_cursor, ctx->centers);
+      CK(cudaGetLastError());
+    }
+    const size_t smem = StatsTc64Smem(K).total;
+    CK(cudaFuncSetAttribute(niw_stats_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KernelTimer kt(ctx, TK_STATS);
+    niw_stats_tc64_kernel<<<ctx->sm_count, S64_THREADS, smem, ctx->stream>>>(ta);
+    CK(cudaGetLastError());
   } else if (ctx->prior == DPMM_PRIOR_NIW) {
     rc = niw_launch_stats(ctx, sa);
     if (rc) return rc;
@@ -1247,7 +1265,7 @@ static int stats_compute(dpmm_ctx* ctx, const int64_t* indices, int32_t n_indice
     CK(cudaMemsetAsync(fin + (size_t)m * 3 * rec, 0, 8, ctx->stream));
     stats_finalize_kernel<<<grid, T, 0, ctx->stream>>>(ctx->acc, ctx->seg_off, ctx->lr_cursor, all ? nullptr : ctx->idx_list, m, D, rec,
                                                        ctx->prior == DPMM_PRIOR_NIW ? 1 : 0, fin,
-                                                       (stats_tc || cached) ? ctx->centers : nullptr,
+                                                       (stats_tc || stats_tc64 || cached) ? ctx->centers : nullptr,
                                                        cached ? ctx->lcount : nullptr,
                                                        cached ? fin + (size_t)m * 3 * rec : nullptr);
     CK(cudaGetLastError());

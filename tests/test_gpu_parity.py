@@ -172,6 +172,37 @@ def test_niw_fused_kernel_edge_shapes(pkg, K, n, empty):
     print(f"K={K} n={n} empty={empty}: {rep}; fused {fused}, served {served}, recomputed {redone}")
 
 
+@pytest.mark.parametrize("K,n,spread,empty", [(12, 30000, 10.0, None), (100, 60000, 30.0, None), (3, 1, 10.0, None),
+                                              (5, 129, 0.5, None), (4, 5000, 10.0, 2), (2, 1025, 40.0, 0), (40, 900, 2.5, None)])
+def test_niw_d64_tensor_core_statistics_kernel(pkg, K, n, spread, empty):
+    """niw_stats_tc64_kernel (D = 64, all clusters; M = 128 x N = 64 MN-major tcgen05 rank-8 updates) against the oracle
+    and against the FP32 -> FP64 kernel it replaces: ragged tiles, empty clusters, runs far from the origin."""
+    case = make_niw_case(64, K, n, seed=K * 3 + n, spread=spread)
+    if empty is not None:
+        w = case["weights"].astype(np.float64)
+        w[empty] = 1e-30
+        case["weights"] = (w / w.sum()).astype(np.float32)
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=4)
+    set_params(g, case)
+    g.sample_labels(False); g.sample_sublabels()
+    lab, sub = g.get_labels(), g.get_sublabels()
+    g.timing_enable(True)
+    got = g.suff_stats()
+    tim = g.timing_read()
+    o = O.OracleSweep(case["x"], O.NIW, seed=4)
+    o.K = K
+    o.set_labels(lab); o.set_sublabels(sub)
+    err = check_stats(got, o.suff_stats(), O.NIW, "D=64 tensor-core statistics")
+    os.environ["DPMM_STATS_TC"] = "0"
+    try:
+        ref = g.suff_stats()
+    finally:
+        os.environ.pop("DPMM_STATS_TC")
+    check_stats(got, ref, O.NIW, "D=64 tensor-core vs FP32 statistics kernel")
+    g.close()
+    print(f"K={K} n={n}: stats_err {err:.2e}; stats {tim['stats'][0] * 1e3:.1f} us")
+
+
 def test_small_dimension_statistics_kernel_on_a_large_input(pkg):
     """D <= 8 and n >= 2^18 points: the statistics run on niw_stats_small_kernel (one warp per run chunk)."""
     n, D, K = 300_000, 5, 12
