@@ -26,6 +26,7 @@
 #include "kernels_stats_tc.cuh"
 #include "kernels_stats_tc64.cuh"
 #include "kernels_substats_tc.cuh"
+#include "kernels_sublabel_tc64.cuh"
 
 #include "ctx.cuh"
 static int keff(const dpmm_ctx* c) { return std::max(std::max(c->K, c->label_bound), 1); }
@@ -109,6 +110,11 @@ static int ensure_k(dpmm_ctx* ctx, int K) {
     CK(dev_realloc(&ctx->ss_b, (size_t)cap * 2 * SS_D));
     CK(dev_realloc(&ctx->ss_c, (size_t)cap * SS_D));
     CK(dev_realloc(&ctx->lcount, (size_t)cap));
+  }
+  if (ctx->prior == DPMM_PRIOR_NIW && D == L64_D) {   // operands of the D = 64 tensor-core sub-label kernel
+    CK(dev_realloc(&ctx->ss_w, (size_t)cap * 2 * D * D));
+    CK(dev_realloc(&ctx->ss_b, (size_t)cap * 2 * D));
+    CK(dev_realloc(&ctx->ss_c, (size_t)cap * D));
   }
   CK(dev_realloc(&ctx->hist, (size_t)cap));
   CK(dev_realloc(&ctx->seg_off, (size_t)cap + 1));
@@ -734,7 +740,7 @@ static int niw_pack_launch(dpmm_ctx* ctx, int K, const double* lfac) {
     pa.mu = ctx->raw_params; pa.inv_sigma = ctx->raw_params + nrec * D; pa.logdet = ctx->raw_params + nrec * D + nrec * D * D;
     pa.recs = ctx->recs; pa.cst = ctx->cst;
     pa.tc_w = tcp ? ctx->tc_w : nullptr; pa.tc_b = ctx->tc_b; pa.tc_mu = ctx->tc_mu; pa.tc_fro = ctx->tc_fro;
-    pa.ss_w = ctx->tc_ok ? ctx->ss_w : nullptr; pa.ss_b = ctx->ss_b; pa.ss_c = ctx->ss_c;
+    pa.ss_w = (ctx->tc_ok || D == L64_D) ? ctx->ss_w : nullptr; pa.ss_b = ctx->ss_b; pa.ss_c = ctx->ss_c;
     pa.t2_piv = t2p ? ctx->t2_piv : nullptr; pa.t2_scr = ctx->t2_scr; pa.t2_u = ctx->t2_u; pa.t2_KS = t2_ks;
     pa.t2_n0 = gauss_tc2_n0(D); pa.t2_fro8 = ctx->t2_fro8; pa.lfac = lfac;
     KernelTimer kt(ctx, TK_PARAMS);
@@ -1101,6 +1107,22 @@ static int run_sublabels(dpmm_ctx* ctx, bool sample, float* dump) {
     ctx->partitioned = false;
     ctx->stats_cached = true;
     ++ctx->n_fused;
+    return 0;
+  }
+  // D = 64 on tcgen05: the draw only; the left / right partition of perm2 follows when the statistics ask for it
+  if (sample && ctx->prior == DPMM_PRIOR_NIW && ctx->D == L64_D && ctx->ss_w != nullptr && env_int("DPMM_SUBLABEL_TC64", 1) != 0 &&
+      SubLabel64Smem(ctx->K).total <= (size_t)ctx->smem_optin && keff(ctx) == ctx->K && ctx->n >= L64_TILE) {
+    SubLabel64Args f{};
+    f.x = ctx->x; f.n = ctx->n; f.K = ctx->K; f.perm = ctx->perm; f.seg_off = ctx->seg_off; f.w = ctx->ss_w; f.bias = ctx->ss_b;
+    f.cen = ctx->ss_c; f.cst = ctx->cst; f.loglr = ctx->loglr; f.sub = ctx->sub; f.u_inj = ctx->u_sub; f.seed = ctx->seed;
+    f.call = ctx->call; f.goff = ctx->goff; f.dump = dump;
+    const size_t smem = SubLabel64Smem(ctx->K).total;
+    CK(cudaFuncSetAttribute(niw_sublabel_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KernelTimer kt(ctx, TK_SUBLABEL);
+    niw_sublabel_tc64_kernel<<<ctx->sm_count, L64_THREADS, smem, ctx->stream>>>(f);
+    CK(cudaGetLastError());
+    ctx->partitioned = false;
+    ctx->stats_cached = false;
     return 0;
   }
   if (ctx->prior == DPMM_PRIOR_NIW) {

@@ -154,6 +154,45 @@ def test_niw_fused_sublabel_statistics_kernel(pkg, spread, K, n):
         check_stats(st1, st0, O.NIW, "fused vs separate statistics")
 
 
+@pytest.mark.parametrize("spread,K,n,empty", [(2.5, 12, 30000, None), (30.0, 100, 60000, None), (10.0, 3, 129, None),
+                                              (10.0, 4, 5000, 2), (40.0, 2, 1025, 0), (2.5, 40, 900, None)])
+def test_niw_d64_tensor_core_sublabel_kernel(pkg, spread, K, n, empty):
+    """D = 64: dpmm_sample_sublabels runs niw_sublabel_tc64_kernel (3-term TF32 product on tcgen05, M = N = 128).  Full
+    parity against the oracle at cluster means far from the origin, ragged tiles and empty clusters, the kernel must
+    really have run, and it must agree with the FP32 sub-label kernel on log-likelihoods and draws."""
+    case = make_niw_case(64, K, n, seed=int(spread) + K + n, spread=spread)
+    if empty is not None:
+        w = case["weights"].astype(np.float64)
+        w[empty] = 1e-30
+        case["weights"] = (w / w.sum()).astype(np.float32)
+    g = pkg.GpuSweep(case["x"], pkg.NIW, seed=7)
+    o = O.OracleSweep(case["x"], O.NIW, seed=7)
+    rep = compare_sweeps(g, o, case, np.random.default_rng(K))
+    g.close()
+    rng = np.random.default_rng(3)
+    u_label, u_sub = rng.random(n), rng.random(n)
+    res = []
+    for mode in ("1", "0"):
+        os.environ["DPMM_SUBLABEL_TC64"] = mode
+        try:
+            g = pkg.GpuSweep(case["x"], pkg.NIW, seed=7)
+            g.set_uniforms(u_label, u_sub, np.zeros(n, np.uint8))
+            set_params(g, case)
+            g.sample_labels(False)
+            ll = g.debug_loglik(1)
+            g.timing_enable(True)
+            g.sample_sublabels()
+            tim = g.timing_read()
+            res.append((ll, g.get_sublabels(), tim["sublabel"][0]))
+            g.close()
+        finally:
+            os.environ.pop("DPMM_SUBLABEL_TC64")
+    (ll1, s1, t1), (ll0, s0, t0) = res
+    check_loglik(ll1, ll0, "tcgen05 vs FP32 sub-label log-likelihood (D = 64)")
+    check_draws(ll0.astype(np.float32), u_sub, s1, s0, "tcgen05 vs FP32 sub-labels (D = 64)")
+    print(f"spread={spread} K={K} n={n}: {rep}; sub-label {t1 * 1e3:.1f} us (FP32 kernel {t0 * 1e3:.1f} us)")
+
+
 @pytest.mark.parametrize("K,n,empty", [(3, 1, None), (5, 129, None), (4, 4000, 2), (2, 257, 0), (40, 900, None)])
 def test_niw_fused_kernel_edge_shapes(pkg, K, n, empty):
     """Ragged and degenerate tile sequences of the fused D=32 kernel: a single point, one row past a tile,
