@@ -398,6 +398,11 @@ def main():
     # ---- value: device-resident sweep, CUDA events on the launching stream ----
     for _ in range(args.warmup):
         sweep_device()
+    # settle: the NIW label path adapts from the previous call's counters (cold labels send the next 8 calls to the
+    # FMA kernel); 12 synchronised steps put the timed region in the steady state whatever the warm-up count was
+    for _ in range(12):
+        sweep_device()
+        g.sync()
     barrier()
     sampler.start()
     l0 = g.launch_count()
