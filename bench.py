@@ -519,6 +519,11 @@ def main():
         stages["sublabel"].update({"bound": "hbm", "achieved_gbs": work["sublabel_bytes"] / sl_s / 1e9,
                                    "frac": work["sublabel_bytes"] / sl_s / 1e9 / pk["hbm_gbs"],
                                    "algorithmic_tflops": work["sublabel_flops"] / sl_s / 1e12})
+        if niw and D == 64:
+            stages["stats"]["kernel"] = ("niw_stats_tc64_kernel (left / right sum x x' as tcgen05 kind::tf32 rank-8 updates, "
+                                         "M = 128 x N = 64, MN-major operands; Float64 accumulators)")
+            stages["sublabel"]["kernel"] = ("niw_sublabel_tc64_kernel (3-term TF32 product on tcgen05, M = N = 128, + sub-label draw) "
+                                            "followed by the left / right partition pass")
     else:
         # NIW D=32: niw_substats_tc_kernel draws the sub-labels AND accumulates the statistics in ONE pass over X.
         # frac = the bytes of that one pass (B_3 of SURVEY 8d) over its time; two_stage_frac credits the bytes the two

@@ -9,7 +9,9 @@ keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'launch__shared_mem_per_block_dynamic', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio']
+        'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed']
 md = [f"# ncu --set full summaries, round 2 (capture {tag})", "",
       "Raw reports: gpurun_out/*.ncu-rep (scratch, not committed).  `--clock-control none`; durations under the profiler are "
       "cold-cache and serialised -- the timed numbers are the CUDA-event ones of the bench lines in this directory.", ""]
@@ -35,7 +37,8 @@ for rep, case in [(f"gpurun_out/{tag}_prof.ncu-rep", "c2"), (f"gpurun_out/{tag}_
         rd = unit_bytes(row[h.index('dram__bytes_read.sum')], r[1][h.index('dram__bytes_read.sum')])
         wr = unit_bytes(row[h.index('dram__bytes_write.sum')], r[1][h.index('dram__bytes_write.sum')])
         md += [f"| DRAM traffic (read + write) | {(rd + wr) / 1e6:.1f} | MB |", ""]
-        short = "label_tc2" if "tc2" in name else ("sublabel_stats_fused" if "substats" in name else ("label" if "label" in name else name[:20]))
+        short = ("label_tc2" if "tc2" in name else "sublabel_stats_fused" if "substats" in name else "sublabel" if "sublabel" in name
+                 else "stats" if "stats" in name else "label" if "label" in name else name[:20])
         traffic.setdefault(case, {})[short] = rd + wr
 # launch list
 p = f"gpurun_out/{tag}_launches_c2.csv"
