@@ -38,6 +38,7 @@ WORKLOADS = {
     "c3": ("mnm", 1_000_000, 100, 20),
     "c4": ("niw", 10_000_000, 5, 50),
     "c5s": ("niw", 2_000_000, 64, 100),   # a 1/50 slice of C5 (N=1e8) per GPU
+    "c5": ("niw", 12_500_000, 64, 100),   # C5 itself at 8 GPUs: N = 1e8 over 8 shards (3.2 GB of X per GPU)
 }
 
 
@@ -64,8 +65,12 @@ def build_case(name, rank=0, seed=0, mixture_var=100.0, shard=None):
         x, z, _, _ = generate_gaussian_data(n, D, K, mixture_var, np.random.default_rng(seed + 1000 + rank), mixture=mix)
         z = z.astype(np.int64)
         hyper = P.niw_hyperparams(1.0, np.zeros(D), D + 3, np.eye(D))    # fit() default, dp-parallel-sampling.jl:272-274
-        # parameters come from rank 0's shard so that every rank holds the same state
-        if rank != 0:
+        # parameters come from rank 0's shard so that every rank holds the same state (for shards beyond 2e6 x 64
+        # values: from a 2e6-point sample of the same mixture, generated identically on every rank)
+        if n * D > 150_000_000:
+            x0, z0, _, _ = generate_gaussian_data(2_000_000, D, K, mixture_var, np.random.default_rng(seed + 999), mixture=mix)
+            z0 = z0.astype(np.int64)
+        elif rank != 0:
             x0, z0, _, _ = generate_gaussian_data(n, D, K, mixture_var, np.random.default_rng(seed + 1000), mixture=mix)
             z0 = z0.astype(np.int64)
         else:

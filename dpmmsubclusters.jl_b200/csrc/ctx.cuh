@@ -57,6 +57,10 @@ struct dpmm_ctx {
   int smem_per_sm = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  // side stream of the device parameter step: kernels that do not depend on each other (mixture weights next to the
+  // Bartlett draws, the K x K merge table next to the posteriors) run on it between a fork and a join event
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int64_t n = 0;
   int D = 0;        // feature dimension the kernels run at (D_user zero-padded to an instantiated width)
   int D_user = 0;   // feature dimension at the boundary
@@ -101,6 +105,9 @@ struct dpmm_ctx {
   float* t2_bias = nullptr;
   float* t2_fro8 = nullptr;
   int32_t* t2_ctr = nullptr;
+  int32_t* ctr_sets = nullptr;   // [2][4]: tc_stats / t2_ctr point into the set of the current label call
+  int ctr_cur = 0;
+  bool ctr_clean = false;        // the set the next tensor-core label call takes is known to be zero
   bool t2_ok = false;       // shape supported
   bool t2_params = false;   // t2_* describe the current parameters
   int t2_KS = 0, t2_nch = 0;
@@ -245,6 +252,23 @@ struct KernelTimer {
     }
   }
 };
+
+// fork: `side` waits for everything enqueued on the main stream so far; join: the main stream waits for `side`
+inline int side_fork(dpmm_ctx* ctx) {
+  if (ctx->side == nullptr) {
+    CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  }
+  CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  return 0;
+}
+inline int side_join(dpmm_ctx* ctx) {
+  CK(cudaEventRecord(ctx->ev_join, ctx->side));
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  return 0;
+}
 
 inline int ensure_stage(dpmm_ctx* ctx, size_t bytes) {
   if (ctx->hstage_bytes >= bytes) return 0;

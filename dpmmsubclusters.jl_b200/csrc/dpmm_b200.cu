@@ -297,13 +297,16 @@ extern "C" int dpmm_create(dpmm_ctx** out, const float* x, int64_t n_local, int3
                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       ctx->tc_ok = (r == CUDA_SUCCESS);
     }
-    if (ctx->tc_ok) CKC(cudaMalloc((void**)&ctx->tc_stats, 2 * sizeof(int32_t)));
   }
-  if (prior_kind == DPMM_PRIOR_NIW && (dpad == 32 || dpad == 64) && n_local >= T2_TILE) {
-    ctx->t2_ok = true;
-    CKC(cudaMalloc((void**)&ctx->t2_ctr, 2 * sizeof(int32_t)));
-    if (ctx->tc_stats == nullptr) CKC(cudaMalloc((void**)&ctx->tc_stats, 2 * sizeof(int32_t)));
+  if (ctx->tc_ok || (prior_kind == DPMM_PRIOR_NIW && (dpad == 32 || dpad == 64) && n_local >= T2_TILE)) {
+    // two alternating counter sets [exact evaluations: points, evaluations | overflow count | pad]: the overflow
+    // kernel of a call clears the set of the next one, so no memset launches sit between the sweeps
+    CKC(cudaMalloc((void**)&ctx->ctr_sets, 8 * sizeof(int32_t)));
+    CKC(cudaMemset(ctx->ctr_sets, 0, 8 * sizeof(int32_t)));
+    ctx->tc_stats = ctx->ctr_sets;
+    ctx->t2_ctr = ctx->ctr_sets + 2;
   }
+  if (prior_kind == DPMM_PRIOR_NIW && (dpad == 32 || dpad == 64) && n_local >= T2_TILE) ctx->t2_ok = true;
   if (prior_kind == DPMM_PRIOR_MULTINOMIAL && d % 4 == 0 && d <= MTC_MAX_D && n_local >= MTC_TILE) {
     // the tensor-core likelihood is exact only for TF32-exact counts: integral, |x| < 2^11
     bool exact = false;
@@ -355,6 +358,12 @@ extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
     if (ctx->ipc_peer[p]) cudaIpcCloseMemHandle(ctx->ipc_peer[p]);
   if (ctx->ipc_local) cudaFree(ctx->ipc_local);
   dpmm_internal_smart_free(ctx);
+  if (ctx->side) {
+    cudaStreamSynchronize(ctx->side);
+    cudaStreamDestroy(ctx->side);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+  }
   if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
   for (auto& t : ctx->tev) {
     cudaEventDestroy(t.a);
@@ -362,7 +371,7 @@ extern "C" int dpmm_destroy(dpmm_ctx* ctx) {
   }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   void* ptrs[] = {ctx->x, ctx->labels, ctx->sub, ctx->perm, ctx->perm2, ctx->u_label, ctx->u_sub, ctx->r_bits,
-                  ctx->raw_params, ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->t2_piv, ctx->t2_scr, ctx->t2_u, ctx->t2_bias, ctx->t2_fro8, ctx->t2_ctr, ctx->tc_w, ctx->tc_b, ctx->tc_mu, ctx->tc_fro, ctx->tc_stats, ctx->ss_w, ctx->ss_b, ctx->ss_c, ctx->lcount, ctx->mtc_w, ctx->hist, ctx->seg_off,
+                  ctx->raw_params, ctx->recs, ctx->cst, ctx->logw, ctx->loglr, ctx->logp_t, ctx->t2_piv, ctx->t2_scr, ctx->t2_u, ctx->t2_bias, ctx->t2_fro8, ctx->ctr_sets, ctx->tc_w, ctx->tc_b, ctx->tc_mu, ctx->tc_fro, ctx->ss_w, ctx->ss_b, ctx->ss_c, ctx->lcount, ctx->mtc_w, ctx->hist, ctx->seg_off,
                   ctx->scat_cursor, ctx->lr_cursor, ctx->lut_l, ctx->lut_r, ctx->rule, ctx->wanted,
                   ctx->idx_list, ctx->acc, ctx->centers, ctx->outbuf, ctx->items, ctx->item_ctr, ctx->hyper_d, ctx->ptab,
                   ctx->ptab_alt, ctx->post, ctx->post_alt, ctx->lfac, ctx->pm_out, ctx->splittable_d, ctx->newof_d,
@@ -892,13 +901,16 @@ static int launch_label_tc2(dpmm_ctx* ctx, int final_iter, int nkeys) {
   a.perm = ctx->perm; a.seg_off = ctx->seg_off; a.nkeys = nkeys; a.wpiv = ctx->t2_piv; a.wscr = ctx->t2_scr;
   a.wbias = ctx->t2_bias; a.fro8 = ctx->t2_fro8;
   a.urows = ctx->t2_u; a.mu = ctx->tc_mu; a.cst = ctx->cst; a.logw = ctx->logw; a.fro = ctx->tc_fro;
+  // this call's counter set (the other one was cleared by the previous call's overflow kernel)
+  ctx->ctr_cur ^= 1;
+  ctx->tc_stats = ctx->ctr_sets + 4 * ctx->ctr_cur;
+  ctx->t2_ctr = ctx->tc_stats + 2;
   a.labels = ctx->labels; a.hist = ctx->hist; a.ovf_list = ctx->perm2; a.ovf_count = ctx->t2_ctr;
   a.u_inj = ctx->u_label; a.seed = ctx->seed; a.call = ctx->call; a.goff = ctx->goff; a.final_iter = final_iter;
   a.stats = ctx->tc_stats;
   const size_t sm = GaussTc2Smem(D, K, a.KS, a.nch, nkeys).total;
   CK(cudaFuncSetAttribute(gauss_label_tc2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  CK(cudaMemsetAsync(ctx->t2_ctr, 0, 8, ctx->stream));
-  CK(cudaMemsetAsync(ctx->tc_stats, 0, 8, ctx->stream));
+  if (!ctx->ctr_clean) CK(cudaMemsetAsync(ctx->ctr_sets, 0, 8 * sizeof(int32_t), ctx->stream));   // another path used them
   const int64_t grid = std::min<int64_t>((ctx->n + T2_TILE - 1) / T2_TILE, (int64_t)ctx->sm_count);
   {
     KernelTimer kt(ctx, TK_LABEL);
@@ -910,6 +922,8 @@ static int launch_label_tc2(dpmm_ctx* ctx, int final_iter, int nkeys) {
   l.x = ctx->x; l.K = K; l.list = ctx->perm2; l.count = ctx->t2_ctr; l.urows = ctx->t2_u; l.mu = ctx->tc_mu;
   l.cst = ctx->cst; l.logw = ctx->logw; l.labels = ctx->labels; l.hist = ctx->hist; l.u_inj = ctx->u_label;
   l.seed = ctx->seed; l.call = ctx->call; l.goff = ctx->goff; l.final_iter = final_iter; l.stats = a.stats;
+  l.zero_next = ctx->ctr_sets + 4 * (ctx->ctr_cur ^ 1);
+  ctx->ctr_clean = true;
   const size_t lsm = (size_t)8 * K * 4;
   if (lsm > 48 * 1024) CK(cudaFuncSetAttribute(gauss_label_list_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
   {
@@ -922,8 +936,7 @@ static int launch_label_tc2(dpmm_ctx* ctx, int final_iter, int nkeys) {
     CK(cudaMallocHost((void**)&ctx->t2_hstat, 4 * sizeof(int32_t)));
     CK(cudaEventCreateWithFlags(&ctx->t2_hstat_ev, cudaEventDisableTiming));
   }
-  CK(cudaMemcpyAsync(ctx->t2_hstat, ctx->tc_stats, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->t2_hstat + 2, ctx->t2_ctr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->t2_hstat, ctx->tc_stats, 12, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaEventRecord(ctx->t2_hstat_ev, ctx->stream));
   ctx->t2_hstat_pending = true;
   return 0;
@@ -978,7 +991,10 @@ static int run_sample_labels(dpmm_ctx* ctx, int final_iter, float* dump) {
     NEED(sm <= (size_t)ctx->smem_optin, DPMM_ELIMIT, "internal: tensor-core label kernel does not fit shared memory");
     CK(cudaFuncSetAttribute(gauss_label_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const int64_t grid = std::min<int64_t>((a.ntiles + 1) / 2, (int64_t)ctx->sm_count);
-    if (a.stats) CK(cudaMemsetAsync(ctx->tc_stats, 0, 8, ctx->stream));
+    if (a.stats) {
+      CK(cudaMemsetAsync(ctx->tc_stats, 0, 8, ctx->stream));
+      ctx->ctr_clean = false;
+    }
     KernelTimer kt(ctx, TK_LABEL);
     gauss_label_tc_kernel<<<(unsigned)grid, TC_THREADS, sm, ctx->stream>>>(ctx->tmap_x, a);
     CK(cudaGetLastError());
@@ -1460,8 +1476,8 @@ extern "C" int dpmm_posterior_step(dpmm_ctx* ctx, const int64_t* indices, int32_
     CK(cudaMemcpyAsync(ctx->idx_list, h_idx, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
     all = false;
   }
-  int rc = launch_post(ctx, all ? nullptr : ctx->idx_list, m, ctx->pm_out);
-  if (rc) return rc;
+  // the K x K table of merged log marginal likelihoods reads the statistics table only: it runs on the side stream
+  // next to the posteriors
   const bool want_merge = merge_logml != nullptr && splittable != nullptr && k_merge > 1;
   double* merge_d = ctx->pm_out + (size_t)m * 6;
   if (want_merge) {
@@ -1472,9 +1488,17 @@ extern "C" int dpmm_posterior_step(dpmm_ctx* ctx, const int64_t* indices, int32_
     ma.splittable = ctx->splittable_d; ma.out = merge_d;
     const size_t sm = niw_post_smem(ctx->D);
     if (sm > 48 * 1024) CK(cudaFuncSetAttribute(niw_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    KernelTimer kt(ctx, TK_PARAMS);
-    niw_merge_kernel<<<dim3((unsigned)k_merge, (unsigned)k_merge), 256, sm, ctx->stream>>>(ma);
+    int rcf = side_fork(ctx);
+    if (rcf) return rcf;
+    ctx->launches += 1;
+    niw_merge_kernel<<<dim3((unsigned)k_merge, (unsigned)k_merge), 256, sm, ctx->side>>>(ma);
     CK(cudaGetLastError());
+  }
+  int rc = launch_post(ctx, all ? nullptr : ctx->idx_list, m, ctx->pm_out);
+  if (rc) return rc;
+  if (want_merge) {
+    rc = side_join(ctx);
+    if (rc) return rc;
   }
   if (counts == nullptr && logml == nullptr && !want_merge) return 0;
   const size_t nd = (size_t)m * 6 + (want_merge ? (size_t)k_merge * k_merge : 0);
@@ -1511,6 +1535,17 @@ extern "C" int dpmm_sample_params(dpmm_ctx* ctx, int32_t K, int32_t from_prior, 
   const int D = ctx->D;
   const size_t nrec = (size_t)3 * K;
   ctx->pcall += 1;
+  {   // the Dirichlet weights depend on the posterior table only: side stream, next to the draws and the packing
+    WeightsArgs wa{};
+    wa.K = K; wa.D = D; wa.post = ctx->post; wa.stride = NIW_POST_DOUBLES(D); wa.alpha = ctx->alpha; wa.logw = ctx->logw;
+    wa.loglr = ctx->loglr; wa.w_out = ctx->w_out; wa.lr_out = ctx->lr_out; wa.seed = ctx->seed; wa.call = ctx->pcall;
+    wa.unit = unit_weights;
+    rc = side_fork(ctx);
+    if (rc) return rc;
+    ctx->launches += 1;
+    dpmm_weights_kernel<<<1, 256, (size_t)(K + 1) * 8, ctx->side>>>(wa);
+    CK(cudaGetLastError());
+  }
   {
     NiwDrawArgs da{};
     da.D = D; da.mu = ctx->raw_params; da.logdet = ctx->raw_params + nrec * D + nrec * D * D; da.hyper = ctx->hyper_d;
@@ -1521,16 +1556,9 @@ extern "C" int dpmm_sample_params(dpmm_ctx* ctx, int32_t K, int32_t from_prior, 
     niw_draw_kernel<<<(unsigned)nrec, NIW_PACK_THREADS, sm, ctx->stream>>>(da);
     CK(cudaGetLastError());
   }
-  {
-    WeightsArgs wa{};
-    wa.K = K; wa.D = D; wa.post = ctx->post; wa.stride = NIW_POST_DOUBLES(D); wa.alpha = ctx->alpha; wa.logw = ctx->logw;
-    wa.loglr = ctx->loglr; wa.w_out = ctx->w_out; wa.lr_out = ctx->lr_out; wa.seed = ctx->seed; wa.call = ctx->pcall;
-    wa.unit = unit_weights;
-    KernelTimer kt(ctx, TK_PARAMS);
-    dpmm_weights_kernel<<<1, 256, (size_t)(K + 1) * 8, ctx->stream>>>(wa);
-    CK(cudaGetLastError());
-  }
-  return niw_pack_launch(ctx, K, ctx->lfac);
+  rc = niw_pack_launch(ctx, K, ctx->lfac);
+  if (rc) return rc;
+  return side_join(ctx);
 }
 
 extern "C" int dpmm_params_merge(dpmm_ctx* ctx, int64_t i, int64_t j) {

@@ -765,6 +765,7 @@ struct GaussListArgs {
   int64_t goff;
   int final_iter;
   int32_t* stats;          // optional [2]: [1] += K per listed point
+  int32_t* zero_next;      // optional [4]: the counter set of the NEXT call, cleared here (no memset launches)
 };
 
 template <int D>
@@ -772,6 +773,7 @@ __global__ void __launch_bounds__(256) gauss_label_list_kernel(const GaussListAr
   extern __shared__ float gl_rs[];   // [8][K]
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
   const int nlist = *a.count;
+  if (a.zero_next != nullptr && blockIdx.x == 0 && threadIdx.x < 4) a.zero_next[threadIdx.x] = 0;
   float* rs = gl_rs + (size_t)wl * a.K;
   for (int e = blockIdx.x * 8 + wl; e < nlist; e += gridDim.x * 8) {
     const int32_t idx = a.list[e];

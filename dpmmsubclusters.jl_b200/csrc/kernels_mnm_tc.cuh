@@ -120,30 +120,33 @@ mnm_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const MnmTcArgs 
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    // (warp-uniform loop, one elected lane issues inside the instruction: issued from an `if (lane == 0)` branch every
+    //  tcgen05.mma costs ~100 cycles of R2UR / ELECT preamble, and 3 x ceil(D / 8) of them per tile paced the kernel)
+    {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = tc::idesc_tf32(MTC_N);
       const int ksteps = (a.D + 7) >> 3;
+      const uint64_t a0 = tc::smem_desc_k128(tc::smem_u32(stage0)), w0 = tc::smem_desc_k128(tc::smem_u32(wsm));
       int t = 0;
       for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++t) {
         const int s = t & 1, b = t & 3;
         tc::mbar_wait(&full[s], (t >> 1) & 1);
         tc::mbar_wait(&tempty[b], ((t >> 2) & 1) ^ 1);
         tc::tc_fence_after();
-        const uint32_t abase = tc::smem_u32(stage0 + (size_t)s * stage_bytes);
-        const uint32_t tmem_d = tmem_base + b * MTC_N;
-        uint32_t acc = 0;
+        const uint64_t ad = a0 + (uint64_t)(s * (stage_bytes >> 4));
+        const uint32_t tmem_d = tmem_u + b * MTC_N;
         for (int ks = 0; ks < ksteps; ++ks) {
           const int p = ks >> 2, kk = ks & 3;   // panel, 32-byte k-step inside the 128-byte rows
-          const uint64_t adesc = tc::smem_desc_k128(abase + p * MTC_PANEL_BYTES) + kk * 2;
+          const uint64_t adesc = ad + (uint64_t)(p * (MTC_PANEL_BYTES >> 4) + kk * 2);
 #pragma unroll
           for (int sp = 0; sp < 3; ++sp) {
-            const uint64_t bdesc = tc::smem_desc_k128(tc::smem_u32(wsm) + (sp * NP + p) * (MTC_N * 128)) + kk * 2;
-            tc::umma_tf32(tmem_d, adesc, bdesc, idesc, acc);
-            acc = 1;
+            const uint64_t bdesc = w0 + (uint64_t)((sp * NP + p) * ((MTC_N * 128) >> 4) + kk * 2);
+            if (ks == 0 && sp == 0) tc::umma_tf32_first_w(tmem_d, adesc, bdesc, idesc);
+            else tc::umma_tf32_acc_w(tmem_d, adesc, bdesc, idesc);
           }
         }
-        tc::umma_commit(&empty[s]);    // the stage may be refilled once these MMAs have read it
-        tc::umma_commit(&tfull[b]);
+        tc::umma_commit_w(&empty[s]);    // the stage may be refilled once these MMAs have read it
+        tc::umma_commit_w(&tfull[b]);
       }
     }
   } else {

@@ -198,7 +198,11 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
   uint64_t* d1full = bars + 28;      // [SS_NTB] GEMM1 accumulator complete
   uint64_t* d1empty = bars + 34;     // [SS_NTB] ... read by the epilogue
   uint64_t* permd = bars + 8;        // [2] permuted panels written
-  uint64_t* pfree = bars + 10;       // [2] GEMM2 that read them retired
+  // [4] GEMM2 of tile li retired: indexed li & 3, NOT by the panel slot li & 1.  With three epilogue groups the group
+  // of tile li can run up to four tiles ahead of the slowest one, so a barrier that turns over every two tiles could
+  // be two phases behind the waiter -- which a parity wait cannot tell from "complete".  Four tiles per turn-over
+  // puts that case (eight tiles of skew) beyond what the raw ring (5) and the accumulator buffers (6) allow.
+  uint64_t* pfree = bars + 4;
   uint64_t* d2full = bars + 12;      // [2] flush group complete
   uint64_t* d2empty = bars + 14;     // [2] ... drained
   uint64_t* wfull = bars + 16;       // factors of a cluster staged
@@ -228,10 +232,10 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
     }
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(&permd[b], 128);
-      tc::mbar_init(&pfree[b], 2);      // one commit per GEMM2 issuer
       tc::mbar_init(&d2full[b], 2);
       tc::mbar_init(&d2empty[b], 128);
     }
+    for (int b = 0; b < 4; ++b) tc::mbar_init(&pfree[b], 2);   // one commit per GEMM2 issuer
     for (int r = 0; r < SS_RAW; ++r) {
       tc::mbar_init(&landed[r], SS_GATHER);
       tc::mbar_init(&rfree[r], 128);
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
             ks = 1;
           }
           for (; ks < nk; ++ks, pd += 64) tc::umma_tf32_acc_w(tm, pd, pd, idesc2);
-          tc::umma_commit_w(&pfree[b]);
+          tc::umma_commit_w(&pfree[li & 3]);
           if (last) {
             tc::umma_commit_w(&d2full[g2 & 1]);
             ++g2;
@@ -538,7 +542,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
           a.sub[idx] = (uint8_t)side;
         }
         if (SS_DBG & 1024) {
-          ss_wait(SS_DBG, &pfree[b], ((li >> 1) & 1) ^ 1);
+          if (li >= 2) ss_wait(SS_DBG, &pfree[(li - 2) & 3], ((li - 2) >> 2) & 1);
           if (gt == 0) { kcnt[b * 2] = 8; kcnt[b * 2 + 1] = 8; }
           tc::fence_proxy_async();
           tc::mbar_arrive(&permd[b]);
@@ -569,7 +573,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) niw_substats_tc_kernel(const Su
                                 : (side == 1 ? (uint8_t)(nl8 + offr_ + __popc(br & lt_mask)) : (uint8_t)dinv);
         if (gt == 0 && nl > 0) atomicAdd(a.lcount + key, nl);
         if (!SS_GPHILOX) ss_wait(SS_DBG, &landed[li % SS_RAW], (li / SS_RAW) & 1);   // z of the tile (gathered and centred by the gather warps)
-        ss_wait(SS_DBG, &pfree[b], ((li >> 1) & 1) ^ 1);    // the GEMM2 that read this slot two tiles ago
+        if (li >= 2) ss_wait(SS_DBG, &pfree[(li - 2) & 3], ((li - 2) >> 2) & 1);   // the GEMM2 that read this slot two tiles ago
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         if (gt == 0) {
           kcnt[b * 2] = nl8 >> 3;

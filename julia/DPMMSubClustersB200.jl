@@ -198,6 +198,22 @@ Base.collect(l::DeviceLabels) = Array(l)
 Base.getindex(l::DeviceLabels, i::Int) = Array(l)[i]   # (debugging only: one device->host copy per call)
 # e.g.  local_group(model_hyperparams, DevicePoints(ctx), DeviceLabels(ctx, false), DeviceLabels(ctx, true), [], Float32[])
 
+# smart splits: the three worker calls of smart_cluster_init! (local_clusters_actions.jl:570-624); the eigen-decomposition
+# (:557-569) and the k-means bookkeeping stay in the Julia host
+function smart_project(c::Ctx, cluster::Integer, v::Vector{Float64}, μ::Vector{Float64})
+    lohi = Vector{Float64}(undef, 2); cnt = Ref{Int64}(0)
+    GC.@preserve v μ lohi check(ccall((:dpmm_smart_project, lib), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}), c.ptr, cluster, v, μ, lohi, cnt), c.ptr)
+    lohi[1], lohi[2], cnt[]
+end
+function smart_kmeans_iter(c::Ctx, min_mean::Real, max_mean::Real)
+    out = Vector{Float64}(undef, 4)      # (sum_1, count_1, sum_2, count_2) over all shards
+    check(ccall((:dpmm_smart_kmeans_iter, lib), Cint, (Ptr{Cvoid}, Float64, Float64, Ptr{Float64}), c.ptr, min_mean, max_mean, out), c.ptr)
+    out
+end
+smart_set_sublabels!(c::Ctx, cluster::Integer) =
+    check(ccall((:dpmm_smart_set_sublabels, lib), Cint, (Ptr{Cvoid}, Int64), c.ptr, cluster), c.ptr)
+
 # multi-GPU: one Julia process per GPU; rank 0 creates the id and ships it (e.g. over Distributed)
 function nccl_unique_id()
     id = Vector{UInt8}(undef, 128)

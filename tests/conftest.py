@@ -12,6 +12,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Every GPU test gets a hard limit (pytest-timeout, thread method: the process exits even when the host thread is
+    blocked inside a CUDA call), so that a kernel that never finishes fails the run instead of holding the box."""
+    for item in items:
+        if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(600, method="thread"))
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")

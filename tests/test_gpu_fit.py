@@ -82,3 +82,17 @@ def test_gpu_and_oracle_hosts_statistically_indistinguishable(pkg):
     assert abs(np.mean(nmi_g) - np.mean(nmi_o)) < 0.05
     assert abs(np.mean(k_g) - np.mean(k_o)) <= 1.0
     assert same >= 5
+
+
+@pytest.mark.timeout(300, method="thread")
+def test_full_size_c2_fit_from_one_cluster(pkg):
+    """fit() on the full C2 shape (N = 1e6, D = 32, K_true = 20) from K = 1, twice: every shape of the fused sub-label +
+    statistics kernel's tile sequence on the way (one huge cluster, freshly split clusters, tiny and empty ones), with
+    its three epilogue groups free to drift apart -- the run has to finish (no barrier phase may be skipped) and land
+    where the host-parameter path lands."""
+    x, z, _, _ = pkg.generate_gaussian_data(1_000_000, 32, 20, 100.0, np.random.default_rng(0))
+    for seed in (1, 2):
+        out = pkg.fit(x, 10.0, iters=100, seed=seed, burnout=20)
+        from dpmmsubclusters_jl_b200.host import normalized_mutual_info
+        nmi = normalized_mutual_info(z, out[0])
+        assert 10 <= len(out[1]) <= 24 and nmi > 0.9, (len(out[1]), nmi)
