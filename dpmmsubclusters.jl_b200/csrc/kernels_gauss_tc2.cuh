@@ -48,6 +48,11 @@
 #define T2_R 8             // screen rows per cluster
 #define T2_DELTA 30.0f
 #define T2_MAX_K 256        // bias tables are K x K
+#ifndef T2_COOP_MAX
+#define T2_COOP_MAX 12      // candidate pairs in a warp up to which they are evaluated one at a time by all lanes
+#endif
+// (measured and rejected: sending the candidate points of a warp with more pairs than that to the overflow list --
+//  the all-K list kernel then costs 6 ms on the overlapping-clusters state of C2, against 1 ms evaluated in place)
 #ifndef T2_NS32
 #define T2_NS32 4          // stage ring at D = 32 (D = 64: 3)
 #endif
@@ -193,6 +198,47 @@ template <int D>
 __device__ __noinline__ float gauss_tc2_exact_q_row(const float* __restrict__ U, const float* __restrict__ mu,
                                                     const float* __restrict__ xr) {
   return gauss_tc2_exact_q_impl<D>(U, mu, [&](int c) { return __ldg(reinterpret_cast<const float4*>(xr) + c); });
+}
+
+// The same quadratic form evaluated by a whole warp for ONE (point, cluster) pair: lane <-> rows lane, lane + 32, ... of
+// U_k (all of a row's loads are independent, rows run in parallel across lanes), then a butterfly sum.  One pair
+// costs about two L2 round trips instead of D dependent ones, which is what matters when a tile has only a few
+// candidate pairs: with one pair per lane such a tile waited ~20 us for a single lane (D = 64), and a cluster whose
+// points all carry a candidate made its CTA the straggler of the whole launch (C5: 4.3 ms, of which 1.9 ms work).
+// Rows hold exact zeros below the diagonal, so the full-row dot equals the triangular one; the sum over rows is
+// taken in a different order than gauss_tc2_exact_q_impl (last-ulp freedom, as the reference's @fastmath dot has).
+template <int D>
+__device__ __noinline__ float gauss_tc2_exact_q_coop(const float* __restrict__ U, const float* __restrict__ mu,
+                                                     const float* __restrict__ xr, int lane) {
+  f32x2_t z2[D / 2];
+#pragma unroll
+  for (int c = 0; c < D / 4; ++c) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xr) + c);
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mu) + c);
+    z2[2 * c] = f2_pack(v.x - m.x, v.y - m.y);
+    z2[2 * c + 1] = f2_pack(v.z - m.z, v.w - m.w);
+  }
+  float q = 0.f;
+#pragma unroll
+  for (int r = 0; r < D / 32; ++r) {
+    const float4* row = reinterpret_cast<const float4*>(U + (size_t)(lane + 32 * r) * D);
+    float4 uf[D / 4];
+#pragma unroll
+    for (int c = 0; c < D / 4; ++c) uf[c] = __ldg(row + c);
+    f32x2_t acc = 0ull;
+#pragma unroll
+    for (int c = 0; c < D / 4; ++c) {
+      acc = f2_fma(f2_pack(uf[c].x, uf[c].y), z2[2 * c], acc);
+      acc = f2_fma(f2_pack(uf[c].z, uf[c].w), z2[2 * c + 1], acc);
+    }
+    float lo, hi;
+    f2_unpack(acc, lo, hi);
+    const float y = lo + hi;
+    q = fmaf(y, y, q);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  return q;
 }
 
 // sample_log_cat_array! (utils.jl:19-31) over the m listed clusters (ascending indices ks[], values rs[]);
@@ -589,14 +635,30 @@ __global__ void __launch_bounds__(T2_THREADS(D), 1) gauss_label_tc2_kernel(const
           __syncwarp();
           // one pair per lane: 32 independent evaluations in flight per warp hide the L2 latency of the factor rows
           // (measured against a warp-cooperative form, lane <-> row of U_k: 3.6x slower, one pair's latency at a time)
-          for (int p = lane; p < total; p += 32) {
-            const int pr = wpairs[p], prow = pr >> 3, slot = pr & 7;
-            const int k = lists[prow * T2_CMAX + slot];
-            const int32_t pidx = __ldg(a.perm + w.pos + prow);
-            const float q = gauss_tc2_exact_q_row<D>(a.urows + (size_t)k * D * D, a.mu + (size_t)k * D, a.x + (size_t)pidx * D);
-            const float2 cf = cfin[k];
-            rl[prow * T2_CMAX + slot] = gauss_finish(cf.x, q, cf.y);
-            ++ncand_total;
+          // (measured against a warp-cooperative form, lane <-> row of U_k: 3.6x slower per pair when the lanes are full)
+          // ... but with only a few pairs in the warp the cooperative form wins on latency: one pair at a time, all lanes
+          if (total <= T2_COOP_MAX) {
+            for (int p = 0; p < total; ++p) {
+              const int pr = wpairs[p], prow = pr >> 3, slot = pr & 7;
+              const int k = lists[prow * T2_CMAX + slot];
+              const int32_t pidx = __ldg(a.perm + w.pos + prow);
+              const float q = gauss_tc2_exact_q_coop<D>(a.urows + (size_t)k * D * D, a.mu + (size_t)k * D, a.x + (size_t)pidx * D, lane);
+              if (lane == 0) {
+                const float2 cf = cfin[k];
+                rl[prow * T2_CMAX + slot] = gauss_finish(cf.x, q, cf.y);
+                ++ncand_total;
+              }
+            }
+          } else {
+            for (int p = lane; p < total; p += 32) {
+              const int pr = wpairs[p], prow = pr >> 3, slot = pr & 7;
+              const int k = lists[prow * T2_CMAX + slot];
+              const int32_t pidx = __ldg(a.perm + w.pos + prow);
+              const float q = gauss_tc2_exact_q_row<D>(a.urows + (size_t)k * D * D, a.mu + (size_t)k * D, a.x + (size_t)pidx * D);
+              const float2 cf = cfin[k];
+              rl[prow * T2_CMAX + slot] = gauss_finish(cf.x, q, cf.y);
+              ++ncand_total;
+            }
           }
           __syncwarp();
         }
