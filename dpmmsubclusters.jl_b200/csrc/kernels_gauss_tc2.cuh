@@ -136,28 +136,80 @@ __host__ __device__ inline int gauss_tc2_nch(int D, int K) {
   return K <= n0 ? 1 : 1 + (K - n0 + 15) / 16;
 }
 
+// The tile sequence (tiles of <= 128 positions that never straddle a key boundary) is cut into G * T2_ROUNDS segments of
+// equal length (+-1) and segment i goes to CTA i mod G: every CTA gets the same number of tiles (+-T2_ROUNDS) and
+// still sees runs of one pivot (its image is staged once per run), but a cluster whose tiles are expensive -- every
+// point carrying candidates because a neighbour overlaps it -- is spread over many CTAs instead of making the one CTA
+// that owned its contiguous range the straggler of the launch (C5 with freshly sampled parameters: 6.0 -> 2.4 ms).
+// Every new run re-stages the pivot image behind a drained MMA pipeline (~1.5 us), so the number of rounds adapts:
+// segments of at least T2_SEG_MIN tiles, at most T2_ROUNDS rounds (C2, 53 tiles per CTA: one contiguous range as
+// before; 8 rounds of 6.6 tiles cost it 76.6 -> 88 us).
+#ifndef T2_ROUNDS
+#define T2_ROUNDS 8
+#endif
+#ifndef T2_SEG_MIN
+#define T2_SEG_MIN 32
+#endif
+struct T2Seq {
+  const int32_t* B;   // [nkeys + 1] key boundaries (positions)
+  const int32_t* P;   // [nkeys + 1] exclusive prefix of tiles per key
+  int nkeys, ntot, G, cta, R;   // R rounds: min(T2_ROUNDS, max(1, ntot / (G * T2_SEG_MIN)))
+};
 struct T2Walk {
   int key, pos, end, tleft;
+  int t, send, seg;   // global tile index, end of the current segment, its index
 };
-__device__ __forceinline__ void t2_walk_init(T2Walk& w, const int32_t* B, const int32_t* P, int nkeys, int t0, int t1) {
-  int lo = 0, hi = nkeys - 1;   // first key with P[key + 1] > t0
+__device__ __forceinline__ int t2_seg_begin(const T2Seq& q, int seg) {
+  return (int)(((int64_t)q.ntot * seg) / ((int64_t)q.G * q.R));
+}
+// tiles CTA `cta` owns: segments cta, cta + G, ...
+__device__ __forceinline__ int t2_cta_tiles(const T2Seq& q) {
+  int n = 0;
+  for (int r = 0; r < q.R; ++r) n += t2_seg_begin(q, q.cta + r * q.G + 1) - t2_seg_begin(q, q.cta + r * q.G);
+  return n;
+}
+__device__ __forceinline__ void t2_seek(T2Walk& w, const T2Seq& q, int t) {
+  int lo = 0, hi = q.nkeys - 1;   // first key with P[key + 1] > t
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (P[mid + 1] > t0) hi = mid;
+    if (q.P[mid + 1] > t) hi = mid;
     else lo = mid + 1;
   }
   w.key = lo;
-  w.pos = B[lo] + (t0 - P[lo]) * T2_TILE;
-  w.end = B[lo + 1];
-  w.tleft = t1 - t0;
+  w.pos = q.B[lo] + (t - q.P[lo]) * T2_TILE;
+  w.end = q.B[lo + 1];
+  w.t = t;
 }
-__device__ __forceinline__ void t2_advance(T2Walk& w, const int32_t* B) {
+// first non-empty segment of this CTA at or after `seg`
+__device__ __forceinline__ void t2_enter(T2Walk& w, const T2Seq& q, int seg) {
+  int b = t2_seg_begin(q, seg), e = t2_seg_begin(q, seg + 1);
+  while (e <= b) {
+    seg += q.G;
+    b = t2_seg_begin(q, seg);
+    e = t2_seg_begin(q, seg + 1);
+  }
+  w.seg = seg;
+  w.send = e;
+  t2_seek(w, q, b);
+}
+__device__ __forceinline__ void t2_walk_init(T2Walk& w, const T2Seq& q) {
+  w.tleft = t2_cta_tiles(q);
+  w.key = 0; w.pos = 0; w.end = 0; w.t = 0; w.send = 0; w.seg = q.cta;
+  if (w.tleft > 0) t2_enter(w, q, q.cta);
+}
+__device__ __forceinline__ void t2_advance(T2Walk& w, const T2Seq& q) {
   --w.tleft;
+  if (w.tleft <= 0) return;
+  ++w.t;
+  if (w.t >= w.send) {                       // next segment of this CTA
+    t2_enter(w, q, w.seg + q.G);
+    return;
+  }
   w.pos += T2_TILE;
-  if (w.pos >= w.end && w.tleft > 0) {
-    do ++w.key; while (B[w.key + 1] == B[w.key]);
-    w.pos = B[w.key];
-    w.end = B[w.key + 1];
+  if (w.pos >= w.end) {
+    do ++w.key; while (q.B[w.key + 1] == q.B[w.key]);
+    w.pos = q.B[w.key];
+    w.end = q.B[w.key + 1];
   }
 }
 
@@ -382,9 +434,9 @@ __global__ void __launch_bounds__(T2_THREADS(D), 1) gauss_label_tc2_kernel(const
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int ntot = P[nkeys];
-  const int t0 = (int)(((int64_t)ntot * blockIdx.x) / gridDim.x);
-  const int t1 = (int)(((int64_t)ntot * (blockIdx.x + 1)) / gridDim.x);
-  const int nt = t1 - t0;
+  const T2Seq seq{B, P, nkeys, ntot, (int)gridDim.x, (int)blockIdx.x,
+                  min(T2_ROUNDS, max(1, ntot / ((int)gridDim.x * T2_SEG_MIN)))};
+  const int nt = t2_cta_tiles(seq);
 
   if (nt > 0) {
     if (warp < 2) {
@@ -398,10 +450,10 @@ __global__ void __launch_bounds__(T2_THREADS(D), 1) gauss_label_tc2_kernel(const
       const uint64_t aaug_desc = tc::smem_desc_k_noswz(tc::smem_u32(aaug));
       const uint32_t scr_stride = (uint32_t)L.scr_bytes;
       T2Walk w;
-      t2_walk_init(w, B, P, nkeys, t0, t1);
+      t2_walk_init(w, seq);
       uint32_t cc = 0;
       int prevkey = -1, ntile_g = 0;
-      for (int li = 0; li < nt; ++li, t2_advance(w, B)) {
+      for (int li = 0; li < nt; ++li, t2_advance(w, seq)) {
         if ((li & 1) != g) continue;
         const int s = li % NS;
         const int key = min(w.key, K - 1);
@@ -470,10 +522,10 @@ __global__ void __launch_bounds__(T2_THREADS(D), 1) gauss_label_tc2_kernel(const
       uint16_t* mylist = lists + row * T2_CMAX;
       float* myrl = rl + row * T2_CMAX;
       T2Walk w;
-      t2_walk_init(w, B, P, nkeys, t0, t1);
+      t2_walk_init(w, seq);
       uint32_t cc = 0;
       int ncand_total = 0, npts_total = 0;
-      for (int li = 0; li < nt; ++li, t2_advance(w, B)) {
+      for (int li = 0; li < nt; ++li, t2_advance(w, seq)) {
         if ((li & 1) != g) continue;
         const int s = li % NS;
         const int key = min(w.key, K - 1);
@@ -717,7 +769,7 @@ __global__ void __launch_bounds__(T2_THREADS(D), 1) gauss_label_tc2_kernel(const
       constexpr int NJ = T2_TILE / RS;      // passes per tile
       const int c = t64 % CPR, r0 = t64 / CPR;
       T2Walk wl, wc;
-      t2_walk_init(wl, B, P, nkeys, t0, t1);
+      t2_walk_init(wl, seq);
       wc = wl;
       int ckey = -1;
       float4 cen = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -745,7 +797,7 @@ __global__ void __launch_bounds__(T2_THREADS(D), 1) gauss_label_tc2_kernel(const
       for (int q = 0; q < PF; ++q) {
         if (q < nt) {
           issue(q % NS);
-          t2_advance(wl, B);
+          t2_advance(wl, seq);
           if (q + 1 < nt) load_idx();
         }
         cp_async_commit();
@@ -780,7 +832,7 @@ __global__ void __launch_bounds__(T2_THREADS(D), 1) gauss_label_tc2_kernel(const
               }
             }
           }
-          t2_advance(wc, B);
+          t2_advance(wc, seq);
         }
         tc::fence_proxy_async();
         tc::mbar_arrive(&full[li % NS]);
@@ -788,7 +840,7 @@ __global__ void __launch_bounds__(T2_THREADS(D), 1) gauss_label_tc2_kernel(const
         if (nx < nt) {
           T2_WAIT(1, tc::mbar_wait(&empty[nx % NS], ((nx / NS) & 1) ^ 1));
           issue(nx % NS);
-          t2_advance(wl, B);
+          t2_advance(wl, seq);
           if (nx + 1 < nt) load_idx();
         }
         cp_async_commit();
