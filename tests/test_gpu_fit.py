@@ -96,3 +96,15 @@ def test_full_size_c2_fit_from_one_cluster(pkg):
         from dpmmsubclusters_jl_b200.host import normalized_mutual_info
         nmi = normalized_mutual_info(z, out[0])
         assert 10 <= len(out[1]) <= 24 and nmi > 0.9, (len(out[1]), nmi)
+
+
+@pytest.mark.timeout(300, method="thread")
+def test_d64_fit_from_one_cluster(pkg):
+    """fit() at D = 64 from K = 1: the tcgen05 label, sub-label and statistics kernels of the C5 shape through every tile
+    sequence a run produces (one cluster, fresh splits, tiny and empty clusters), on both parameter paths."""
+    x, z, _, _ = pkg.generate_gaussian_data(300_000, 64, 10, 100.0, np.random.default_rng(4))
+    from dpmmsubclusters_jl_b200.host import normalized_mutual_info
+    for device_params in (True, False):
+        out = pkg.fit(x, 10.0, iters=60 if device_params else 40, seed=3, burnout=10, device_params=device_params)
+        nmi = normalized_mutual_info(z, out[0])
+        assert 5 <= len(out[1]) <= 14 and nmi > 0.85, (device_params, len(out[1]), nmi)
