@@ -1011,12 +1011,13 @@ static int run_sample_labels(dpmm_ctx* ctx, int final_iter, float* dump) {
     a.n = ctx->n; a.D = ctx->D; a.K = K; a.NP = (ctx->D + 31) / 32; a.wsplit = ctx->mtc_w; a.logw = ctx->logw;
     a.labels = ctx->labels; a.hist = ctx->hist; a.u_inj = ctx->u_label; a.seed = ctx->seed; a.call = ctx->call;
     a.goff = ctx->goff; a.final_iter = final_iter; a.sampler = ctx->sampler; a.ntiles = (ctx->n + MTC_TILE - 1) / MTC_TILE;
-    const size_t sm = MnmTcSmem(K, a.NP).total;
+    a.NG = MnmTcSmem(K, a.NP, MTC_NG).total <= (size_t)ctx->smem_optin ? MTC_NG : 2;
+    const size_t sm = MnmTcSmem(K, a.NP, a.NG).total;
     NEED(sm <= (size_t)ctx->smem_optin, DPMM_ELIMIT, "internal: multinomial tensor-core kernel does not fit shared memory");
     CK(cudaFuncSetAttribute(mnm_label_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const int64_t grid = std::min<int64_t>(a.ntiles, (int64_t)ctx->sm_count);
     KernelTimer kt(ctx, TK_LABEL);
-    mnm_label_tc_kernel<<<(unsigned)grid, MTC_THREADS, sm, ctx->stream>>>(ctx->tmap_x, a);
+    mnm_label_tc_kernel<<<(unsigned)grid, MTC_THREADS(a.NG), sm, ctx->stream>>>(ctx->tmap_x, a);
     CK(cudaGetLastError());
   } else {
     MnmLabelArgs a{};

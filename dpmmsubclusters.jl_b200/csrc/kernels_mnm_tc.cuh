@@ -12,9 +12,11 @@
 // refinement is needed here.  X streams through a 2-stage TMA ring (128B-swizzled 32-column panels),
 // which makes the kernel HBM-bound: one pass over X, K log-likelihoods per point straight out of TMEM.
 //
-// Warp roles (persistent CTA per SM, 320 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer,
-// warps 2-5 / 6-9 = draw warps of the even / odd tiles (thread = TMEM lane = point).  Four TMEM
-// accumulator buffers let the tensor pipe run two tiles ahead of the draws.
+// Warp roles (persistent CTA per SM, 576 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer,
+// warps 2-17 = four draw groups, group g on the tiles t = g (mod 4) and the accumulator buffer g (thread = TMEM
+// lane = point).  The draw is what the kernel spends its instructions on (62 % of them in the reference-exact
+// softmax + inverse-CDF walk over K entries, call-site profile of capture r2k), so the number of draw warps sets
+// the pace until HBM does.
 #pragma once
 #include "common.cuh"
 #include "kernels_gauss_tc.cuh"  // tc:: PTX wrappers
@@ -24,7 +26,8 @@
 #define MTC_MAX_K 32
 #define MTC_MAX_D 128
 #define MTC_PANEL_BYTES (MTC_TILE * 128)   // one 32-column panel of a tile
-#define MTC_THREADS 320
+#define MTC_NG 4                  // draw groups (4 warps each) when their parr slices fit shared memory, else 2
+#define MTC_THREADS(ng) (64 + (ng) * 128)
 
 struct MnmTcArgs {
   int64_t n;
@@ -40,15 +43,16 @@ struct MnmTcArgs {
   int final_iter;
   int sampler;
   int64_t ntiles;
+  int NG;                // draw groups: 4 or 2; tile t -> group t % NG (accumulator buffer t % 4)
 };
 
 struct MnmTcSmem {
   size_t w, stages, rs, logw, hist, bars, total;
-  __host__ __device__ MnmTcSmem(int K, int NP) {
+  __host__ __device__ MnmTcSmem(int K, int NP, int NG) {
     size_t o = 0;
     w = o;      o += (size_t)3 * NP * MTC_N * 128;
     stages = o; o += (size_t)2 * NP * MTC_PANEL_BYTES;
-    rs = o;     o += (size_t)2 * K * MTC_TILE * 4;
+    rs = o;     o += (size_t)NG * K * MTC_TILE * 4;
     logw = o;   o += (size_t)((K + 3) & ~3) * 4;
     hist = o;   o += (size_t)((K + 3) & ~3) * 4;
     o = (o + 15) & ~(size_t)15;
@@ -57,12 +61,13 @@ struct MnmTcSmem {
   }
 };
 
-__global__ void __launch_bounds__(MTC_THREADS, 1)
+__global__ void __launch_bounds__(MTC_THREADS(MTC_NG), 1)
 mnm_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const MnmTcArgs a) {
   extern __shared__ __align__(1024) uint8_t mtc_smem[];
   uint8_t* const smem = mtc_smem;
   const int K = a.K, NP = a.NP;
-  const MnmTcSmem L(K, NP);
+  const MnmTcSmem L(K, NP, a.NG);
+  const int NT = (int)blockDim.x;
   float* wsm = reinterpret_cast<float*>(smem + L.w);
   uint8_t* stage0 = smem + L.stages;
   float* rs_all = reinterpret_cast<float*>(smem + L.rs);
@@ -90,12 +95,12 @@ mnm_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const MnmTcArgs 
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, 128);   // 4 buffers x 32 columns
   // log-probability splits, 128B-swizzled rows of 32 floats: [split][panel][cluster row][32]
-  for (int e = tid; e < 3 * NP * MTC_N * 8; e += MTC_THREADS) {
+  for (int e = tid; e < 3 * NP * MTC_N * 8; e += NT) {
     const int r = e >> 3, c = e & 7;
     const float4 v = __ldg(reinterpret_cast<const float4*>(a.wsplit) + e);
     *reinterpret_cast<float4*>(wsm + (size_t)r * 32 + ((c ^ (r & 7)) << 2)) = v;
   }
-  for (int k = tid; k < K; k += MTC_THREADS) {
+  for (int k = tid; k < K; k += NT) {
     lwsm[k] = __ldg(a.logw + k);
     hs[k] = 0;
   }
@@ -157,7 +162,7 @@ mnm_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const MnmTcArgs 
     float* rs = rs_all + (size_t)g * K * MTC_TILE + row;
     int t = 0;
     for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++t) {
-      if ((t & 1) != g) continue;
+      if ((t & (a.NG - 1)) != g) continue;
       const int b = t & 3;
       tc::mbar_wait(&tfull[b], (t >> 2) & 1);
       tc::tc_fence_after();
@@ -188,6 +193,6 @@ mnm_label_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const MnmTcArgs 
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_base, 128);
-  for (int k = tid; k < K; k += MTC_THREADS)
+  for (int k = tid; k < K; k += NT)
     if (hs[k] != 0) atomicAdd(&a.hist[k], hs[k]);
 }
