@@ -159,6 +159,7 @@ struct dpmm_ctx {
   int hup_i = 0;
 
   bool hist_valid = false, sorted = false, partitioned = false;
+  bool scan_valid = false;     // seg_off / scatter cursors / left-right cursors already hold the scan of `hist`
   int64_t n_fused = 0, n_cached = 0, n_recompute = 0;   // DPMM_VERBOSE counters
   bool acc_cleared = false;    // acc / lcount were zeroed by the last label scatter and not touched since
   bool stats_cached = false;   // acc / lcount / centers hold the l/r statistics of every cluster for the current labels

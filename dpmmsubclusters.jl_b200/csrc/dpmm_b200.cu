@@ -131,7 +131,7 @@ static int ensure_k(dpmm_ctx* ctx, int K) {
   ctx->items_cap = ctx->n / ctx->chunk + 2 * (int64_t)cap + 2;
   CK(dev_realloc(&ctx->items, (size_t)ctx->items_cap));
   ctx->Kcap = cap;
-  ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
+  ctx->hist_valid = ctx->scan_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
   ctx->params_set = false;   // every parameter buffer above was reallocated: set_params must run again
   ctx->acc_cleared = ctx->cursors_fresh = false;
   if (ctx->dev_params) {
@@ -465,7 +465,7 @@ extern "C" int dpmm_init_labels(dpmm_ctx* ctx, int32_t init_clusters, int32_t ou
                                                     ctx->call, ctx->goff);
     CK(cudaGetLastError());
   }
-  ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
+  ctx->hist_valid = ctx->scan_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
   return dpmm_randomize_sublabels(ctx, nullptr, 0);
 }
 
@@ -520,7 +520,7 @@ extern "C" int dpmm_apply_split(dpmm_ctx* ctx, const int64_t* indices, const int
     }
   }
   ctx->label_bound = std::max(ctx->label_bound, K);
-  ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
+  ctx->hist_valid = ctx->scan_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
   return run_relabel(ctx, ll, lr, rule, true);
 }
 
@@ -550,7 +550,7 @@ extern "C" int dpmm_apply_merge(dpmm_ctx* ctx, const int64_t* indices, const int
         lab[k] = idx;
       }
   }
-  ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
+  ctx->hist_valid = ctx->scan_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
   return run_relabel(ctx, lab, lab, rule, false);
 }
 
@@ -596,7 +596,7 @@ extern "C" int dpmm_remove_empty(dpmm_ctx* ctx, const int64_t* pts_count, int32_
   ctx->label_bound = std::max(1, k - removed);
   ctx->K = std::min(ctx->K, ctx->label_bound);  // parameters of the dropped clusters are stale anyway
   ctx->params_set = false;
-  ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
+  ctx->hist_valid = ctx->scan_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
   return run_relabel(ctx, lab, lab, rule, false);
 }
 
@@ -674,7 +674,7 @@ extern "C" int dpmm_set_labels(dpmm_ctx* ctx, const int64_t* labels) {
   ctx->label_bound = mx;
   rc = ensure_k(ctx, mx);
   if (rc) return rc;
-  ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
+  ctx->hist_valid = ctx->scan_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;
   return 0;
 }
 
@@ -924,6 +924,9 @@ static int launch_label_tc2(dpmm_ctx* ctx, int final_iter, int nkeys) {
   l.seed = ctx->seed; l.call = ctx->call; l.goff = ctx->goff; l.final_iter = final_iter; l.stats = a.stats;
   l.zero_next = ctx->ctr_sets + 4 * (ctx->ctr_cur ^ 1);
   ctx->ctr_clean = true;
+  // the last block of the overflow kernel scans the new label histogram (label_scan_kernel's job) when the scan's
+  // width is the K of this call: one launch fewer between the label kernel and the sort
+  l.ticket = env_int("DPMM_SCAN_FUSED", 1) != 0 ? ctx->tc_stats + 3 : nullptr; l.scan_k = K; l.seg_off = ctx->seg_off; l.scat_cursor = ctx->scat_cursor; l.lr_cursor = ctx->lr_cursor;
   const size_t lsm = (size_t)8 * K * 4;
   if (lsm > 48 * 1024) CK(cudaFuncSetAttribute(gauss_label_list_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
   {
@@ -976,9 +979,11 @@ static int run_sample_labels(dpmm_ctx* ctx, int final_iter, float* dump) {
     if (rc) return rc;
   }
   CK(cudaMemsetAsync(ctx->hist, 0, (size_t)K * 4, ctx->stream));
+  bool scanned = false;
   if (use_t2) {
     int rc = ctx->D == 32 ? launch_label_tc2<32>(ctx, final_iter, nkeys) : launch_label_tc2<64>(ctx, final_iter, nkeys);
     if (rc) return rc;
+    scanned = env_int("DPMM_SCAN_FUSED", 1) != 0;
   } else if (ctx->prior == DPMM_PRIOR_NIW && ctx->tc_params && dump == nullptr && ctx->sampler == DPMM_SAMPLER_INVERSE_CDF &&
       env_int("DPMM_LABEL_TC", 2) != 0) {
     // K2: tcgen05 TF32 screen + FP32 refine
@@ -1040,6 +1045,7 @@ static int run_sample_labels(dpmm_ctx* ctx, int final_iter, float* dump) {
     CK(cudaGetLastError());
   }
   ctx->hist_valid = true;
+  ctx->scan_valid = scanned;   // the overflow kernel's last block already scanned the new histogram (width K)
   ctx->sorted = false;
   ctx->partitioned = ctx->stats_cached = false;
   ctx->label_bound = K;
@@ -1053,7 +1059,7 @@ static int ensure_sorted(dpmm_ctx* ctx) {
     int rc = ensure_k(ctx, K);
     if (rc) return rc;
   }
-  KernelTimer kt(ctx, TK_SORT, ctx->hist_valid ? 2 : 3);
+  KernelTimer kt(ctx, TK_SORT, 1 + (ctx->hist_valid ? 0 : 1) + (ctx->hist_valid && ctx->scan_valid ? 0 : 1));
   if (!ctx->hist_valid) {
     CK(cudaMemsetAsync(ctx->hist, 0, (size_t)K * 4, ctx->stream));
     const int T = 256;
@@ -1062,8 +1068,11 @@ static int ensure_sorted(dpmm_ctx* ctx) {
     CK(cudaGetLastError());
     ctx->hist_valid = true;
   }
-  label_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hist, K, ctx->seg_off, ctx->scat_cursor, ctx->lr_cursor);
-  CK(cudaGetLastError());
+  if (!(ctx->hist_valid && ctx->scan_valid)) {
+    label_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hist, K, ctx->seg_off, ctx->scat_cursor, ctx->lr_cursor);
+    CK(cudaGetLastError());
+  }
+  ctx->scan_valid = false;   // the scatter below consumes the cursors
   {
     const int T = 256;
     const unsigned grid = (unsigned)((ctx->n + (int64_t)T * SCATTER_PPT - 1) / ((int64_t)T * SCATTER_PPT));
@@ -1684,7 +1693,7 @@ extern "C" int dpmm_debug_loglik(dpmm_ctx* ctx, int32_t which, float* out) {
     ctx->labels = keep;
     ctx->call = call0;
     ctx->label_bound = lb0;
-    ctx->hist_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;  // the histogram describes the scratch labels
+    ctx->hist_valid = ctx->scan_valid = ctx->sorted = ctx->partitioned = ctx->stats_cached = false;  // the histogram describes the scratch labels
     cudaFree(scratch);
   } else {
     // sub-label matrix under the CURRENT labels; sub-labels are restored afterwards

@@ -880,6 +880,13 @@ struct GaussListArgs {
   int final_iter;
   int32_t* stats;          // optional [2]: [1] += K per listed point
   int32_t* zero_next;      // optional [4]: the counter set of the NEXT call, cleared here (no memset launches)
+  // optional: the last block to finish turns the completed label histogram into the segment offsets and cursors of the
+  // sort (what label_scan_kernel does), saving its launch.  ticket: zero on entry, reset on exit.
+  int32_t* ticket;
+  int scan_k;
+  int32_t* seg_off;
+  int32_t* scat_cursor;
+  int32_t* lr_cursor;
 };
 
 template <int D>
@@ -911,5 +918,48 @@ __global__ void __launch_bounds__(256) gauss_label_list_kernel(const GaussListAr
       if (a.stats != nullptr) atomicAdd(&a.stats[1], a.K);
     }
     __syncwarp();
+  }
+  if (a.ticket != nullptr) {
+    __shared__ int last_block;
+    __shared__ int wtot[8];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last_block = atomicAdd(a.ticket, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (last_block) {   // exclusive scan of hist[0 .. scan_k): 256 threads, chunks of 256
+      __threadfence();
+      int carry = 0;
+      for (int k0 = 0; k0 < a.scan_k; k0 += 256) {
+        const int k = k0 + (int)threadIdx.x;
+        const int v = k < a.scan_k ? __ldcg(a.hist + k) : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        if (lane == 31) wtot[wl] = inc;
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          before += w < wl ? wtot[w] : 0;
+          total += wtot[w];
+        }
+        const int excl = carry + before + inc - v;
+        if (k < a.scan_k) {
+          a.seg_off[k] = excl;
+          a.scat_cursor[k] = excl;
+          a.lr_cursor[2 * k] = excl;
+          a.lr_cursor[2 * k + 1] = excl + v;
+        }
+        carry += total;
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) {
+        a.seg_off[a.scan_k] = carry;
+        *a.ticket = 0;
+      }
+    }
   }
 }
