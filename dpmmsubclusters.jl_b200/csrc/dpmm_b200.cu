@@ -1135,19 +1135,20 @@ static int run_sublabels(dpmm_ctx* ctx, bool sample, float* dump) {
     ++ctx->n_fused;
     return 0;
   }
-  // D = 64 on tcgen05: the draw only; the left / right partition of perm2 follows when the statistics ask for it
+  // D = 64 on tcgen05: the draw and the left / right partition of perm2
   if (sample && ctx->prior == DPMM_PRIOR_NIW && ctx->D == L64_D && ctx->ss_w != nullptr && env_int("DPMM_SUBLABEL_TC64", 1) != 0 &&
       SubLabel64Smem(ctx->K).total <= (size_t)ctx->smem_optin && keff(ctx) == ctx->K && ctx->n >= L64_TILE) {
     SubLabel64Args f{};
     f.x = ctx->x; f.n = ctx->n; f.K = ctx->K; f.perm = ctx->perm; f.seg_off = ctx->seg_off; f.w = ctx->ss_w; f.bias = ctx->ss_b;
     f.cen = ctx->ss_c; f.cst = ctx->cst; f.loglr = ctx->loglr; f.sub = ctx->sub; f.u_inj = ctx->u_sub; f.seed = ctx->seed;
-    f.call = ctx->call; f.goff = ctx->goff; f.dump = dump;
+    f.call = ctx->call; f.goff = ctx->goff; f.dump = dump; f.perm2 = ctx->perm2; f.cursor = ctx->lr_cursor;
     const size_t smem = SubLabel64Smem(ctx->K).total;
     CK(cudaFuncSetAttribute(niw_sublabel_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTimer kt(ctx, TK_SUBLABEL);
     niw_sublabel_tc64_kernel<<<ctx->sm_count, L64_THREADS, smem, ctx->stream>>>(f);
     CK(cudaGetLastError());
-    ctx->partitioned = false;
+    ctx->partitioned = true;       // the kernel's epilogue partitioned perm2 (and consumed the cursors)
+    ctx->cursors_fresh = false;
     ctx->stats_cached = false;
     return 0;
   }

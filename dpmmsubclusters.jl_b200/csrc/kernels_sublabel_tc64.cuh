@@ -9,6 +9,7 @@
 // A tile = 128 consecutive positions of ONE cluster k in `perm`.  Its 256-byte rows are gathered with cp.async into
 // two K-major [128][32-feature] halves (128B swizzle), shifted by the cluster's centre c_k (exact in Float32, see
 // niw_pack_center) in place -- the tensor core reads h = the TF32 bits of z -- and l = z - h goes to a second pair.
+// The epilogue also partitions every label segment of perm2 into its left | right points for the statistics kernel.
 //       Y[128 x 128] = h Wh' + l Wh' + h Wl' - b,   W = [U_left; U_right] = Wh + Wl,   b = U_s (mu_s - c_k)
 // (25 tcgen05.mma kind::tf32, M = 128, N = 128: 8 k-steps per term + the bias k-step; only l Wl' is dropped).
 // Accumulator row p holds U_l (x_p - mu_l) | U_r (x_p - mu_r); the epilogue warps read it with tcgen05.ld, form
@@ -46,6 +47,8 @@ struct SubLabel64Args {
   const float* cst;        // [3K]
   const float* loglr;      // [2K]
   uint8_t* sub;            // [n] out
+  int32_t* perm2;          // [n] out: every label segment partitioned into its left | right points
+  int32_t* cursor;         // [2K] in/out: (first free left position, end of the free right positions) per cluster
   const double* u_inj;
   uint64_t seed;
   uint32_t call;
@@ -332,26 +335,46 @@ __global__ void __launch_bounds__(L64_THREADS, 1) niw_sublabel_tc64_kernel(const
         tc::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + tb * 128;
         float ql, qr;
-        {
-          uint32_t v0[32], v1[32];
-          tc::tmem_ld32(taddr, v0);
-          tc::tmem_ld32(taddr + 32, v1);
+        {   // 32 columns at a time: two register arrays in flight would not fit next to the partition bookkeeping
+          uint32_t v[32];
+          tc::tmem_ld32(taddr, v);
           tc::tmem_ld_wait();
-          ql = gauss_tc_screen_q(v0) + gauss_tc_screen_q(v1);
-          tc::tmem_ld32(taddr + 64, v0);
-          tc::tmem_ld32(taddr + 96, v1);
+          ql = gauss_tc_screen_q(v);
+          tc::tmem_ld32(taddr + 32, v);
           tc::tmem_ld_wait();
-          qr = gauss_tc_screen_q(v0) + gauss_tc_screen_q(v1);
+          ql += gauss_tc_screen_q(v);
+          tc::tmem_ld32(taddr + 64, v);
+          tc::tmem_ld_wait();
+          qr = gauss_tc_screen_q(v);
+          tc::tmem_ld32(taddr + 96, v);
+          tc::tmem_ld_wait();
+          qr += gauss_tc_screen_q(v);
         }
         tc::tc_fence_before();
         tc::mbar_arrive(&d1empty[tb]);
+        int side = 2;
         if (valid) {
           const float rl = gauss_finish(cl, ql, lwl), rr = gauss_finish(cr, qr, lwr);
           if (a.dump != nullptr) {
             a.dump[idx] = rl;
             a.dump[a.n + idx] = rr;
           }
-          a.sub[idx] = (uint8_t)dpmm_draw_two(rl, rr, u);
+          side = dpmm_draw_two(rl, rr, u);
+          a.sub[idx] = (uint8_t)side;
+        }
+        {   // left / right partition of the segment (what the FP32 sub-label kernel leaves in perm2): the left points
+            // grow from the segment's start, the right ones from its end; one atomic per warp and side
+          const uint32_t bl = __ballot_sync(0xffffffffu, side == 0), br = __ballot_sync(0xffffffffu, side == 1);
+          int basel = 0, baser = 0;
+          if (lane == 0) {
+            if (bl) basel = atomicAdd(a.cursor + 2 * key, __popc(bl));
+            if (br) baser = atomicSub(a.cursor + 2 * key + 1, __popc(br)) - __popc(br);
+          }
+          basel = __shfl_sync(0xffffffffu, basel, 0);
+          baser = __shfl_sync(0xffffffffu, baser, 0);
+          const uint32_t lt = (1u << lane) - 1u;
+          if (side == 0) a.perm2[basel + __popc(bl & lt)] = idx;
+          else if (side == 1) a.perm2[baser + __popc(br & lt)] = idx;
         }
         stc_advance(we, B);
       }
