@@ -552,6 +552,10 @@ def main():
         roofline = {"kernel": ds.get("kernel", dom), "stage": dom, "bound": "hbm", "achieved": ds["achieved_gbs"], "peak": pk["hbm_gbs"],
                     "unit": "GB/s", "frac": ds["frac"], "traffic": traffic, "peak_source": pk["source"],
                     "algorithmic_bytes_per_launch": work["stats_bytes"] if dom != "label" else work["label_bytes"]}
+        if "fused_stages" in ds:
+            roofline["note"] = ("HBM is the roofline this pass is measured against by its bytes; what bounds the kernel is the shared-memory "
+                                "data pipe: ncu l1tex__data_pipe_lsu_wavefronts 55 % + l1tex__data_pipe_tc_wavefronts_mem_shared 35 % of "
+                                "peak, DRAM 20 %, tensor pipe 27 % (profiles/r2n_ncu_summary.md, DESIGN.md section 4)")
     else:
         roofline = {"kernel": ds["kernel"], "stage": dom, "bound": "tensor" if ds["bound"] == "tensor" else "tensor",
                     "achieved": ds["algorithmic_tflops"], "peak": ds["peak_tflops"], "unit": "TFLOP/s", "frac": ds["frac"],
